@@ -1,0 +1,546 @@
+// pf_api.cu -- C-ABI of libpyflow_b200 (see include/pyflow_b200.h).
+//
+// Host side of the device step: owns the context, carves the caller's
+// workspace into fields, sequences the kernels of one projection step on the
+// caller's stream and returns the step scalars with one small D2H.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "pf_cg.cuh"
+#include "pf_comm.h"
+#include "pf_kernels.cuh"
+
+using namespace pf;
+
+struct pf_ctx {
+  int device = 0;
+  int sm_count = 0;
+  Slab s{};
+  size_t field_elems = 0;
+  // fields (device): velocity ping-pong, rhs, CG vectors
+  double *u = nullptr, *v = nullptr, *uo = nullptr, *vo = nullptr;
+  double *b = nullptr, *x = nullptr, *r = nullptr, *p0 = nullptr, *p1 = nullptr;
+  // small device buffers
+  double* red_part = nullptr;
+  unsigned* red_counter = nullptr;
+  double* scal = nullptr;
+  double* cg_part = nullptr;
+  double* center = nullptr;
+  // pinned host mirrors
+  double* h_scal = nullptr;
+  double* h_center = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int cg_grid = 0;
+  bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
+  dim3 sgrid;                      // grid of the simple kernels
+  pf::Comm* comm = nullptr;        // multi-GPU slabs (null when nranks == 1)
+  char err[512] = {0};
+};
+
+namespace {
+
+constexpr size_t ALIGN = 256;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int fail(pf_ctx* c, int code, const char* what, const char* detail) {
+  if (c) snprintf(c->err, sizeof(c->err), "%s: %s", what, detail ? detail : "");
+  return code;
+}
+
+#define PF_CUDA(ctx, call)                                                         \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) return fail((ctx), PF_ERR_CUDA, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define PF_TRY(expr)                \
+  do {                              \
+    int rc__ = (expr);              \
+    if (rc__ != PF_OK) return rc__; \
+  } while (0)
+
+int pitch_of(int64_t nx) { return (int)align_up((size_t)nx, PITCH_ALIGN); }
+size_t field_elems_of(int64_t nx, int64_t nyl) { return (size_t)(nyl + 2 * HALO) * (size_t)pitch_of(nx); }
+
+struct SmallLayout {
+  size_t red_part, red_counter, scal, cg_part, center, total;
+};
+SmallLayout small_layout(int64_t nyl) {
+  SmallLayout L{};
+  size_t o = 0;
+  L.red_part = o;    o = align_up(o + sizeof(double) * MAX_RED_VALS * MAX_RED_BLOCKS, ALIGN);
+  L.red_counter = o; o = align_up(o + sizeof(unsigned) * 4, ALIGN);
+  L.scal = o;        o = align_up(o + sizeof(double) * S_COUNT, ALIGN);
+  L.cg_part = o;     o = align_up(o + sizeof(double) * 3 * CG_MAX_GRID, ALIGN);
+  L.center = o;      o = align_up(o + sizeof(double) * (size_t)nyl, ALIGN);
+  L.total = o;
+  return L;
+}
+
+constexpr int NFIELDS = 9;
+
+dim3 simple_grid(const Slab& s) {
+  const int gx = (s.nx + KT - 1) / KT;
+  int gy = std::max(1, 2368 / gx);
+  gy = std::min(gy, s.nyl);
+  return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+bool is_unit(double dx, double dy) { return dx == 1.0 && dy == 1.0; }
+
+// Geometry of the CG tiles for this slab and grid size (see pf_cg.cuh).
+void cg_geometry(const pf_ctx* c, CgArgs& a) {
+  const Slab& s = c->s;
+  const int nstrips = (s.nx + STRIP - 1) / STRIP;
+  int wx = 1;
+  while (wx * 2 <= CG_WARPS && wx * 2 <= nstrips) wx *= 2;
+  a.wx = wx;
+  a.wy = CG_WARPS / wx;
+  a.nchunks = (nstrips + wx - 1) / wx;
+  const int G = c->cg_grid;
+  // Bands: aim for one tile per CTA (a multiple of the grid when the slab is
+  // tall enough), at least ~4 rows per warp so halo rows stay a small share.
+  const int rows_min = 4 * a.wy;
+  const int max_bands = std::max(1, s.nyl / rows_min);
+  int want = std::max(1, G / a.nchunks);
+  a.nbands = std::min(want, max_bands);
+  a.ntiles = a.nchunks * a.nbands;
+}
+
+template <bool UNIT>
+int launch_cg(pf_ctx* c, CgArgs& a, cudaStream_t st) {
+  void* args[] = {&a};
+  PF_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_cg_persistent<UNIT>, dim3(c->cg_grid), dim3(CG_THREADS),
+                                         args, 0, st));
+  return PF_OK;
+}
+
+// rhs already in c->b (raw); finishes it, solves, leaves x in c->x and the true
+// residual in S_RES_SUMSQ.
+int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_interior, double tol, int maxiter,
+                    int subtract_mean, int pin, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+  const Slab& s = c->s;
+  const Red red{c->red_part, c->red_counter, c->scal};
+  const double invd = jacobi ? invd_interior : 1.0;
+  const double ncells = (double)s.nx * (double)s.nyg;
+  if (c->comm && subtract_mean) PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_RHS_SUM, 1, /*max=*/0, st, c->err));
+  k_rhs2<<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, c->r, ncells, subtract_mean, pin, invd, red);
+  PF_CUDA(c, cudaGetLastError());
+  if (e0) PF_CUDA(c, cudaEventRecord(e0, st));
+  if (c->comm) {
+    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
+    return fail(c, PF_ERR_UNSUPPORTED, "solve_on_device", "multi-GPU CG not built yet");
+  } else {
+    CgArgs a{};
+    a.s = s; a.b = c->b; a.x = c->x; a.r = c->r; a.p0 = c->p0; a.p1 = c->p1;
+    a.part = c->cg_part; a.scal = c->scal;
+    a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
+    cg_geometry(c, a);
+    if (is_unit(dx, dy)) PF_TRY(launch_cg<true>(c, a, st));
+    else PF_TRY(launch_cg<false>(c, a, st));
+  }
+  if (e1) PF_CUDA(c, cudaEventRecord(e1, st));
+  if (is_unit(dx, dy)) k_resid<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
+  else k_resid<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
+  PF_CUDA(c, cudaGetLastError());
+  return PF_OK;
+}
+
+int read_scalars(pf_ctx* c, cudaStream_t st, bool with_center) {
+  PF_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
+  if (with_center)
+    PF_CUDA(c, cudaMemcpyAsync(c->h_center, c->center, sizeof(double) * (size_t)c->s.nyl, cudaMemcpyDeviceToHost, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+double nanmax(double mx, double nancount) { return nancount > 0.0 ? NAN : mx; }
+
+// dense host array (row stride `stride`) <-> device field
+int h2d_field(pf_ctx* c, double* dst, const double* src, int64_t stride, cudaStream_t st) {
+  PF_CUDA(c, cudaMemcpy2DAsync(dst + cell(c->s, 0, 0), sizeof(double) * (size_t)c->s.pitch, src,
+                               sizeof(double) * (size_t)stride, sizeof(double) * (size_t)c->s.nx, (size_t)c->s.nyl,
+                               cudaMemcpyHostToDevice, st));
+  return PF_OK;
+}
+int d2h_field(pf_ctx* c, double* dst, const double* src, int64_t stride, cudaStream_t st) {
+  PF_CUDA(c, cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)stride, src + cell(c->s, 0, 0),
+                               sizeof(double) * (size_t)c->s.pitch, sizeof(double) * (size_t)c->s.nx, (size_t)c->s.nyl,
+                               cudaMemcpyDeviceToHost, st));
+  return PF_OK;
+}
+
+template <bool UNIT>
+int launch_predict(pf_ctx* c, int scheme, double dt, double dx, double dy, cudaStream_t st) {
+  const Slab& s = c->s;
+  switch (scheme) {
+    case PF_ADV_UPWIND:
+      k_predict<UNIT, PF_ADV_UPWIND><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->uo, c->vo, dt, dx, dy);
+      break;
+    case PF_ADV_QUICK:
+      k_predict<UNIT, PF_ADV_QUICK><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->uo, c->vo, dt, dx, dy);
+      break;
+    case PF_ADV_NONE:
+      k_predict<UNIT, PF_ADV_NONE><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->uo, c->vo, dt, dx, dy);
+      break;
+    default:
+      return fail(c, PF_ERR_ARG, "pf_step", "unknown advection scheme");
+  }
+  PF_CUDA(c, cudaGetLastError());
+  return PF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pf_abi_version(void) { return PF_ABI_VERSION; }
+
+const char* pf_strerror(int status) {
+  switch (status) {
+    case PF_OK: return "ok";
+    case PF_ERR_ARG: return "invalid argument";
+    case PF_ERR_CUDA: return "CUDA error";
+    case PF_ERR_NCCL: return "NCCL error";
+    case PF_ERR_STATE: return "invalid call order / state";
+    case PF_ERR_UNSUPPORTED: return "unsupported device or configuration";
+    default: return "unknown status";
+  }
+}
+
+const char* pf_last_error(const pf_ctx* ctx) { return ctx ? ctx->err : ""; }
+
+size_t pf_workspace_bytes(int64_t nx, int64_t ny_local) {
+  if (nx < 2 || ny_local < 1) return 0;
+  const size_t fb = align_up(field_elems_of(nx, ny_local) * sizeof(double), ALIGN);
+  return NFIELDS * fb + small_layout(ny_local).total + ALIGN;
+}
+
+int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int64_t row_offset, int device,
+              void* workspace, size_t workspace_bytes) {
+  if (!out) return PF_ERR_ARG;
+  *out = nullptr;
+  if (nx < 2 || ny_global < 2 || ny_local < 1 || row_offset < 0 || row_offset + ny_local > ny_global) return PF_ERR_ARG;
+  if (nx > (1 << 20) || ny_global > (1 << 28) || field_elems_of(nx, ny_local) > (size_t)0x7fffffff) return PF_ERR_ARG;
+  if (!workspace || ((uintptr_t)workspace % ALIGN) != 0 || workspace_bytes < pf_workspace_bytes(nx, ny_local))
+    return PF_ERR_ARG;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return PF_ERR_CUDA;
+  pf_ctx* c = new pf_ctx();
+  c->device = device;
+  int coop = 0, major = 0;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (!coop || major < 10) {
+    delete c;
+    return PF_ERR_UNSUPPORTED;
+  }
+  c->s.nx = (int)nx;
+  c->s.nyl = (int)ny_local;
+  c->s.nyg = (int)ny_global;
+  c->s.row0 = (int)row_offset;
+  c->s.pitch = pitch_of(nx);
+  c->field_elems = field_elems_of(nx, ny_local);
+  const size_t fb = align_up(c->field_elems * sizeof(double), ALIGN);
+  char* base = (char*)workspace;
+  double** fields[NFIELDS] = {&c->u, &c->v, &c->uo, &c->vo, &c->b, &c->x, &c->r, &c->p0, &c->p1};
+  for (int k = 0; k < NFIELDS; ++k) *fields[k] = (double*)(base + (size_t)k * fb);
+  char* small = base + (size_t)NFIELDS * fb;
+  const SmallLayout L = small_layout(ny_local);
+  c->red_part = (double*)(small + L.red_part);
+  c->red_counter = (unsigned*)(small + L.red_counter);
+  c->scal = (double*)(small + L.scal);
+  c->cg_part = (double*)(small + L.cg_part);
+  c->center = (double*)(small + L.center);
+  c->sgrid = simple_grid(c->s);
+#define PF_CREATE_CUDA(call)                                  \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) {                                 \
+      fprintf(stderr, "pf_create: %s: %s\n", #call, cudaGetErrorString(e__)); \
+      pf_destroy(c);                                          \
+      return PF_ERR_CUDA;                                     \
+    }                                                         \
+  } while (0)
+  PF_CREATE_CUDA(cudaMemset(workspace, 0, pf_workspace_bytes(nx, ny_local) - ALIGN));
+  PF_CREATE_CUDA(cudaHostAlloc((void**)&c->h_scal, sizeof(double) * S_COUNT, cudaHostAllocDefault));
+  PF_CREATE_CUDA(cudaHostAlloc((void**)&c->h_center, sizeof(double) * (size_t)ny_local, cudaHostAllocDefault));
+  for (auto& ev : c->ev) PF_CREATE_CUDA(cudaEventCreate(&ev));
+  int occ_u = 0, occ_g = 0;
+  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_cg_persistent<true>, CG_THREADS, 0));
+  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, k_cg_persistent<false>, CG_THREADS, 0));
+  const int occ = std::min(occ_u, occ_g);
+  if (occ < 1) {
+    pf_destroy(c);
+    return PF_ERR_UNSUPPORTED;
+  }
+  c->cg_grid = std::min(c->sm_count * occ, CG_MAX_GRID);
+#undef PF_CREATE_CUDA
+  *out = c;
+  return PF_OK;
+}
+
+int pf_destroy(pf_ctx* c) {
+  if (!c) return PF_OK;
+  cudaSetDevice(c->device);
+  if (c->comm) comm_destroy(c->comm);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->h_center) cudaFreeHost(c->h_center);
+  for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  delete c;
+  return PF_OK;
+}
+
+int pf_device_info(pf_ctx* c, int* sm_count, int* cg_grid_blocks, int* cg_block_threads) {
+  if (!c) return PF_ERR_ARG;
+  if (sm_count) *sm_count = c->sm_count;
+  if (cg_grid_blocks) *cg_grid_blocks = c->cg_grid;
+  if (cg_block_threads) *cg_block_threads = CG_THREADS;
+  return PF_OK;
+}
+
+int pf_upload(pf_ctx* c, const double* u, const double* v, const double* p, int64_t row_stride, void* stream) {
+  if (!c || row_stride < c->s.nx) return PF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (u) c->center_valid = false;
+  if (u) PF_TRY(h2d_field(c, c->u, u, row_stride, st));
+  if (v) PF_TRY(h2d_field(c, c->v, v, row_stride, st));
+  if (p) PF_TRY(h2d_field(c, c->x, p, row_stride, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+int pf_download(pf_ctx* c, double* u, double* v, double* p, int64_t row_stride, void* stream) {
+  if (!c || row_stride < c->s.nx) return PF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (u) PF_TRY(d2h_field(c, u, c->u, row_stride, st));
+  if (v) PF_TRY(d2h_field(c, v, c->v, row_stride, st));
+  if (p) PF_TRY(d2h_field(c, p, c->x, row_stride, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+int pf_prestep_reduce(pf_ctx* c, double out[3], void* stream) {
+  if (!c || !out) return PF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Red red{c->red_part, c->red_counter, c->scal};
+  if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 1, st, c->err));
+  k_prestep<<<c->sgrid, KT, 0, st>>>(c->s, c->u, c->v, red);
+  PF_CUDA(c, cudaGetLastError());
+  if (c->comm) {
+    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_UMAX, 2, 1, st, c->err));
+    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVC_SUMSQ, 1, 0, st, c->err));
+    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_UNAN, 2, 0, st, c->err));
+  }
+  PF_TRY(read_scalars(c, st, false));
+  out[0] = nanmax(c->h_scal[S_UMAX], c->h_scal[S_UNAN]);
+  out[1] = nanmax(c->h_scal[S_VMAX], c->h_scal[S_VNAN]);
+  out[2] = c->h_scal[S_DIVC_SUMSQ];
+  return PF_OK;
+}
+
+int pf_step(pf_ctx* c, const pf_step_params* P, pf_step_out* out, void* stream) {
+  if (!c || !P || !out) return PF_ERR_ARG;
+  if (P->lin_maxiter < 0) return fail(c, PF_ERR_ARG, "pf_step", "lin_maxiter < 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Slab& s = c->s;
+  const Red red{c->red_part, c->red_counter, c->scal};
+  const bool unit = is_unit(P->dx, P->dy);
+  const double dt = P->dt, dx = P->dx, dy = P->dy;
+  const double dt_safe = (1e-14 > dt) ? 1e-14 : dt;      // Python max(dt, 1e-14) incl. NaN behaviour
+  PF_CUDA(c, cudaEventRecord(c->ev[0], st));
+
+  if (!P->projection_only) {
+    // predictor: (u, v) -> (uo, vo) buffers, then swap so that u/v hold u*, v*
+    // and uo/vo keep the previous step's fields for the residuals.
+    if (c->comm) {
+      PF_TRY(comm_halo(c->comm, c->u, 2, 2, st, c->err));
+      PF_TRY(comm_halo(c->comm, c->v, 2, 2, st, c->err));
+    }
+    if (unit) PF_TRY(launch_predict<true>(c, P->scheme, dt, dx, dy, st));
+    else PF_TRY(launch_predict<false>(c, P->scheme, dt, dx, dy, st));
+    std::swap(c->u, c->uo);
+    std::swap(c->v, c->vo);
+  }
+  // rhs pass 1
+  if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 0, st, c->err));
+  if (unit) k_rhs1<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
+  else k_rhs1<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
+  PF_CUDA(c, cudaGetLastError());
+  if (c->comm) PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVB_SUMSQ, 1, 0, st, c->err));
+  // rhs pass 2 + CG + true residual
+  PF_TRY(solve_on_device(c, dx, dy, P->jacobi, P->inv_diag_interior, P->lin_tol, P->lin_maxiter, 1, 1, st, c->ev[1],
+                         c->ev[2]));
+  // correction
+  if (unit) k_correct<true><<<c->sgrid, KT, 0, st>>>(s, c->x, c->x, c->u, c->v, dt, dx, dy, c->scal);
+  else k_correct<false><<<c->sgrid, KT, 0, st>>>(s, c->x, c->x, c->u, c->v, dt, dx, dy, c->scal);
+  PF_CUDA(c, cudaGetLastError());
+  if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 0, st, c->err));
+  if (unit) k_divnorm<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, red, S_DIVA_SUMSQ);
+  else k_divnorm<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, red, S_DIVA_SUMSQ);
+  PF_CUDA(c, cudaGetLastError());
+  if (!P->projection_only) {
+    if (P->lid_set) {
+      k_lid<<<(s.nx + KT - 1) / KT, KT, 0, st>>>(s, c->u, P->lid_velocity);
+      PF_CUDA(c, cudaGetLastError());
+    }
+    if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 1, st, c->err));
+    k_post<<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->uo, c->vo, c->x, c->center, red);
+    PF_CUDA(c, cudaGetLastError());
+  }
+  PF_CUDA(c, cudaEventRecord(c->ev[3], st));
+  PF_TRY(read_scalars(c, st, !P->projection_only));
+  c->center_valid = !P->projection_only;
+
+  const double* h = c->h_scal;
+  memset(out, 0, sizeof(*out));
+  const double ncells = (double)s.nx * (double)s.nyg;
+  out->div_before_norm = sqrt(h[S_DIVB_SUMSQ]);
+  out->rhs_mean = h[S_RHS_SUM] / ncells;
+  out->bnorm = sqrt(h[S_BB]);
+  out->rnorm = sqrt(h[S_RES_SUMSQ]);
+  out->div_after_norm = sqrt(h[S_DIVA_SUMSQ]);
+  out->p00 = h[S_X0] - h[S_X0];   /* p -= p.flat[0] (pressure_solver.py:148) */
+  out->info = (int32_t)h[S_INFO];
+  out->true_iters = (int32_t)h[S_ITERS];
+  if (!P->projection_only) {
+    out->ru_sumsq = h[S_RU_SUMSQ];
+    out->rv_sumsq = h[S_RV_SUMSQ];
+    out->cont_sumsq = h[S_DIVC_SUMSQ];
+    out->umax_raw = nanmax(h[S_UMAX], h[S_UNAN]);
+    out->vmax_raw = nanmax(h[S_VMAX], h[S_VNAN]);
+    out->nonfinite = h[S_NONFINITE] > 0.0 ? 1 : 0;
+  }
+  float ms = 0.f;
+  PF_CUDA(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
+  out->cg_ms = ms;
+  PF_CUDA(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]));
+  out->step_ms = ms;
+  return PF_OK;
+}
+
+int pf_centerline(pf_ctx* c, double* host_out, void* stream) {
+  if (!c || !host_out) return PF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->center_valid) {           // came back with the last pf_step's scalar read-back
+    memcpy(host_out, c->h_center, sizeof(double) * (size_t)c->s.nyl);
+    return PF_OK;
+  }
+  k_centerline<<<(c->s.nyl + KT - 1) / KT, KT, 0, st>>>(c->s, c->u, c->center);
+  PF_CUDA(c, cudaGetLastError());
+  PF_CUDA(c, cudaMemcpyAsync(c->h_center, c->center, sizeof(double) * (size_t)c->s.nyl, cudaMemcpyDeviceToHost, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  memcpy(host_out, c->h_center, sizeof(double) * (size_t)c->s.nyl);
+  return PF_OK;
+}
+
+// ---- operator-level seams ------------------------------------------------------
+// Scratch use: inputs land in b / r / p0, outputs in p1 / uo-like scratch.  The
+// State fields (u, v, x) are left untouched.
+#define PF_OP_PROLOGUE()                                             \
+  if (!c) return PF_ERR_ARG;                                         \
+  if (c->comm) return fail(c, PF_ERR_STATE, "operator seam", "single-GPU contexts only"); \
+  cudaStream_t st = (cudaStream_t)stream;                            \
+  const Slab& s = c->s;                                              \
+  const int64_t nxs = s.nx;                                          \
+  (void)nxs
+
+int pf_op_gradient_coherent(pf_ctx* c, const double* p, double* gx, double* gy, double dx, double dy, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!p || !gx || !gy) return PF_ERR_ARG;
+  PF_TRY(h2d_field(c, c->b, p, nxs, st));
+  if (is_unit(dx, dy)) k_op_grad<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, c->p1, dx, dy);
+  else k_op_grad<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, c->p1, dx, dy);
+  PF_CUDA(c, cudaGetLastError());
+  PF_TRY(d2h_field(c, gx, c->p0, nxs, st));
+  PF_TRY(d2h_field(c, gy, c->p1, nxs, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+static int op_div(pf_ctx* c, const double* u, const double* v, double* out, double dx, double dy, int central,
+                  void* stream) {
+  PF_OP_PROLOGUE();
+  if (!u || !v || !out) return PF_ERR_ARG;
+  PF_TRY(h2d_field(c, c->b, u, nxs, st));
+  PF_TRY(h2d_field(c, c->r, v, nxs, st));
+  if (is_unit(dx, dy)) k_op_div<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, dx, dy, central);
+  else k_op_div<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, dx, dy, central);
+  PF_CUDA(c, cudaGetLastError());
+  PF_TRY(d2h_field(c, out, c->p0, nxs, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+int pf_op_divergence_coherent(pf_ctx* c, const double* u, const double* v, double* out, double dx, double dy,
+                              void* stream) {
+  return op_div(c, u, v, out, dx, dy, 0, stream);
+}
+int pf_op_divergence_central(pf_ctx* c, const double* u, const double* v, double* out, double dx, double dy,
+                             void* stream) {
+  return op_div(c, u, v, out, dx, dy, 1, stream);
+}
+
+int pf_op_laplacian_coherent(pf_ctx* c, const double* p, double* out, double dx, double dy, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!p || !out) return PF_ERR_ARG;
+  PF_TRY(h2d_field(c, c->b, p, nxs, st));
+  if (is_unit(dx, dy)) k_op_lap<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, dx, dy);
+  else k_op_lap<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, dx, dy);
+  PF_CUDA(c, cudaGetLastError());
+  PF_TRY(d2h_field(c, out, c->p0, nxs, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+int pf_op_advect(pf_ctx* c, int scheme, const double* u, const double* v, const double* f, double* out, double dx,
+                 double dy, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!u || !v || !f || !out) return PF_ERR_ARG;
+  if (scheme != PF_ADV_UPWIND && scheme != PF_ADV_QUICK) return fail(c, PF_ERR_ARG, "pf_op_advect", "scheme");
+  PF_TRY(h2d_field(c, c->b, u, nxs, st));
+  PF_TRY(h2d_field(c, c->r, v, nxs, st));
+  PF_TRY(h2d_field(c, c->p0, f, nxs, st));
+  const bool unit = is_unit(dx, dy);
+  if (scheme == PF_ADV_UPWIND) {
+    if (unit) k_op_advect<true, PF_ADV_UPWIND><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, c->p1, dx, dy);
+    else k_op_advect<false, PF_ADV_UPWIND><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, c->p1, dx, dy);
+  } else {
+    if (unit) k_op_advect<true, PF_ADV_QUICK><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, c->p1, dx, dy);
+    else k_op_advect<false, PF_ADV_QUICK><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, c->p1, dx, dy);
+  }
+  PF_CUDA(c, cudaGetLastError());
+  PF_TRY(d2h_field(c, out, c->p1, nxs, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+int pf_op_pcg(pf_ctx* c, const double* b, double* x, double dx, double dy, int jacobi, double inv_diag_interior,
+              double tol, int maxiter, int* info, int* true_iters, double* rnorm, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!b || !x || maxiter < 0) return PF_ERR_ARG;
+  // this seam overwrites the p field (x) of the context
+  PF_TRY(h2d_field(c, c->b, b, nxs, st));
+  PF_TRY(solve_on_device(c, dx, dy, jacobi, inv_diag_interior, tol, maxiter, 0, 0, st, nullptr, nullptr));
+  PF_TRY(d2h_field(c, x, c->x, nxs, st));
+  PF_TRY(read_scalars(c, st, false));
+  if (info) *info = (int)c->h_scal[S_INFO];
+  if (true_iters) *true_iters = (int)c->h_scal[S_ITERS];
+  if (rnorm) *rnorm = sqrt(c->h_scal[S_RES_SUMSQ]);
+  return PF_OK;
+}
+
+int pf_comm_unique_id(void* out128) { return comm_unique_id(out128); }
+
+int pf_comm_init(pf_ctx* c, const void* id128, int rank, int nranks) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return PF_ERR_ARG;
+  if (c->comm) return fail(c, PF_ERR_STATE, "pf_comm_init", "already initialised");
+  if (nranks == 1) return PF_OK;
+  return comm_create(&c->comm, id128, rank, nranks, c->s, c->err);
+}
+
+}  // extern "C"

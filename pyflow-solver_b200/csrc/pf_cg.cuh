@@ -1,0 +1,356 @@
+// pf_cg.cuh -- matrix-free Jacobi-preconditioned Conjugate Gradient on the
+// pinned Neumann operator, as ONE persistent cooperative kernel.
+//
+// What it replaces: scipy.sparse.linalg.cg as called from
+// linear_solvers/interface.py:43 with A = _NegLaplacianPinned
+// (pressure_solver.py:97-105) and M = Jacobi of the ring-identity matrix
+// (pressure_solver.py:15-40, preconditioners.py:8-25).  The recurrence,
+// stopping rule and operation order are scipy's; the
+// classical (non-pipelined) form is kept so results match.
+//
+// Traffic per cell per iteration: 8 doubles = 64 B (SURVEY 8d contract):
+//   phase A: read r, p_old  -> write p_new = (p_old*beta) + M r ; q = A p_new is
+//            formed on the fly from a 3-row register window and only p.q kept
+//   phase B: read x, r, p   -> recompute q = A p ; x += alpha p ; r -= alpha q ;
+//            accumulate r.r and r.(M r)
+// Two grid-wide reductions per iteration (p.q, then {r.r, r.z}): per-CTA
+// partials, grid barrier, every CTA folds the partials in the same fixed
+// order => all CTAs hold bit-identical scalars and take the same branch.
+//
+// Work decomposition: the slab is cut into column chunks of 64*wx columns and
+// row bands; a CTA tile is chunk x band, its 8 warps are arranged wx x wy.  A
+// warp owns a 64-column strip (2 columns per lane, 16-byte vector accesses)
+// and marches along the rows of its sub-band keeping rows j-1, j, j+1 in
+// registers; left/right neighbours come from warp shuffles, strip-edge columns
+// from one extra scalar load on lanes 0 / 31 (an L1 hit: the neighbouring warp
+// of the same CTA streams that line).  Each value is fetched from HBM once per
+// phase.  Phase A marches top->bottom and phase B bottom->top so the rows one
+// phase touched last are the first the next one reads (L2 reuse, 126 MB).
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "pf_common.cuh"
+
+namespace pf {
+namespace cg = cooperative_groups;
+
+constexpr int CG_THREADS = 256;
+constexpr int CG_WARPS = CG_THREADS / 32;
+constexpr int STRIP = 64;     // columns per warp
+constexpr int CG_U = 4;       // rows fetched per batch (loads in flight per lane)
+constexpr int CG_MAX_GRID = 2048;
+
+struct CgArgs {
+  Slab s;
+  const double* b;
+  double* x;
+  double* r;
+  double* p0;
+  double* p1;
+  double* part;       // [3][CG_MAX_GRID] per-CTA partials: p.q, r.r, r.z
+  double* scal;       // device scalar block
+  double dx, dy;
+  double invd;        // interior inverse diagonal (1.0 when M = I)
+  double tol;
+  int maxiter;
+  int wx, wy;         // warp arrangement inside a CTA tile, wx*wy == CG_WARPS
+  int nchunks, nbands, ntiles;
+};
+
+struct Row {
+  double a, b;        // this lane's two columns
+  double h;           // strip halo column (lane 0: left, lane 31: right)
+};
+
+struct WarpTile {
+  int i0, j0, j1;
+  bool active;
+};
+
+__device__ __forceinline__ WarpTile warp_tile(const CgArgs& a, int t) {
+  const int warp = threadIdx.x >> 5;
+  const int wxi = warp % a.wx, wyi = warp / a.wx;
+  const int c = t % a.nchunks, bd = t / a.nchunks;
+  WarpTile w;
+  w.i0 = (c * a.wx + wxi) * STRIP;
+  const int bj0 = (int)((long long)bd * a.s.nyl / a.nbands);
+  const int bj1 = (int)((long long)(bd + 1) * a.s.nyl / a.nbands);
+  const int th = bj1 - bj0;
+  w.j0 = bj0 + (int)((long long)wyi * th / a.wy);
+  w.j1 = bj0 + (int)((long long)(wyi + 1) * th / a.wy);
+  w.active = (w.i0 < a.s.nx) && (w.j1 > w.j0);
+  return w;
+}
+
+// Per-lane column geometry of a strip.
+struct Cols {
+  int ia, ib, ih;
+  bool va, vb, vh;          // column exists
+  bool hw_a, he_a, he_b;    // has west / east neighbour inside the domain
+  bool ring_a, ring_b, ring_h;
+};
+
+__device__ __forceinline__ Cols strip_cols(const Slab& s, int i0) {
+  const int lane = threadIdx.x & 31;
+  Cols c;
+  c.ia = i0 + 2 * lane;
+  c.ib = c.ia + 1;
+  c.ih = (lane == 0) ? i0 - 1 : i0 + STRIP;
+  c.va = c.ia < s.nx;
+  c.vb = c.ib < s.nx;
+  c.vh = (lane == 0 || lane == 31) && c.ih >= 0 && c.ih < s.nx;
+  c.hw_a = c.ia > 0;
+  c.he_a = c.ia < s.nx - 1;
+  c.he_b = c.ib < s.nx - 1;
+  c.ring_a = (c.ia == 0) || (c.ia == s.nx - 1);
+  c.ring_b = (c.ib == 0) || (c.ib == s.nx - 1);
+  c.ring_h = (c.ih == 0) || (c.ih == s.nx - 1);
+  return c;
+}
+
+// q = A p at the two columns of the centre row `cur`.
+template <bool UNIT>
+__device__ __forceinline__ void apply_A(const CgArgs& a, const Cols& c, const Row& south, const Row& cur,
+                                        const Row& north, int jgc, double& qa, double& qb) {
+  const int lane = threadIdx.x & 31;
+  double w_a = __shfl_up_sync(0xffffffffu, cur.b, 1);
+  double e_b = __shfl_down_sync(0xffffffffu, cur.a, 1);
+  if (lane == 0) w_a = cur.h;
+  if (lane == 31) e_b = cur.h;
+  const bool hs = jgc > 0, hn = jgc < a.s.nyg - 1;
+  qa = neg_lap<UNIT>(cur.a, w_a, cur.b, south.a, north.a, c.hw_a, c.he_a, hs, hn, a.dx, a.dy);
+  qb = neg_lap<UNIT>(cur.b, cur.a, e_b, south.b, north.b, true, c.he_b, hs, hn, a.dx, a.dy);
+  if (jgc == 0 && c.ia == 0) qa = cur.a;   // pinned row: out[0] = x[0]
+}
+
+// ---- phase A over one warp tile ------------------------------------------------
+template <bool UNIT>
+__device__ __forceinline__ double phaseA_warp(const CgArgs& a, const double* r, const double* pold, double* pnew,
+                                              bool first, double beta, int dir, const WarpTile& w) {
+  const Slab& s = a.s;
+  const Cols c = strip_cols(s, w.i0);
+  const int TH = w.j1 - w.j0;
+  const int nrows = TH + 2;          // visiting index t: 0 halo, 1..TH band, TH+1 halo
+  double acc = 0.0;
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  for (int tb = 0; tb < nrows; tb += CG_U) {
+    double2 rr[CG_U], pp[CG_U];
+    double rh[CG_U], ph[CG_U];
+#pragma unroll
+    for (int u = 0; u < CG_U; ++u) {
+      const int t = tb + u;
+      const int jl = dir > 0 ? (w.j0 - 1 + t) : (w.j1 - t);
+      const int jg = s.row0 + jl;
+      rr[u] = make_double2(0.0, 0.0);
+      pp[u] = make_double2(0.0, 0.0);
+      rh[u] = 0.0;
+      ph[u] = 0.0;
+      if (t < nrows && jg >= 0 && jg < s.nyg) {
+        if (c.va) {
+          const size_t o = cell(s, jl, c.ia);
+          rr[u] = ld2(r + o);
+          if (!first) pp[u] = ld2(pold + o);
+        }
+        if (c.vh) {
+          const size_t oh = cell(s, jl, c.ih);
+          rh[u] = ld1(r + oh);
+          if (!first) ph[u] = ld1(pold + oh);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CG_U; ++u) {
+      const int t = tb + u;
+      if (t < nrows) {               // warp-uniform
+        const int jl = dir > 0 ? (w.j0 - 1 + t) : (w.j1 - t);
+        const int jg = s.row0 + jl;
+        const bool ring_row = (jg == 0) || (jg == s.nyg - 1);
+        const double za = ((ring_row || c.ring_a) ? 1.0 : a.invd) * rr[u].x;
+        const double zb = ((ring_row || c.ring_b) ? 1.0 : a.invd) * rr[u].y;
+        const double zh = ((ring_row || c.ring_h) ? 1.0 : a.invd) * rh[u];
+        Row nw;
+        if (first) {                 // p = z
+          nw.a = za; nw.b = zb; nw.h = zh;
+        } else {                     // p *= beta ; p += z
+          nw.a = (pp[u].x * beta) + za;
+          nw.b = (pp[u].y * beta) + zb;
+          nw.h = (ph[u] * beta) + zh;
+        }
+        if (t >= 1 && t <= TH) {
+          double* dst = pnew + cell(s, jl, c.ia);
+          if (c.vb) st2(dst, nw.a, nw.b);
+          else if (c.va) st1(dst, nw.a);
+        }
+        if (t >= 2) {
+          const int jgc = dir > 0 ? jg - 1 : jg + 1;
+          double qa, qb;
+          if (dir > 0) apply_A<UNIT>(a, c, prev, cur, nw, jgc, qa, qb);
+          else apply_A<UNIT>(a, c, nw, cur, prev, jgc, qa, qb);
+          if (c.va) acc += cur.a * qa;
+          if (c.vb) acc += cur.b * qb;
+        }
+        prev = cur;
+        cur = nw;
+      }
+    }
+  }
+  return acc;
+}
+
+// ---- phase B over one warp tile ------------------------------------------------
+template <bool UNIT>
+__device__ __forceinline__ void phaseB_warp(const CgArgs& a, const double* p, double* x, double* r, double alpha,
+                                            int dir, const WarpTile& w, double& acc_rr, double& acc_rz) {
+  const Slab& s = a.s;
+  const Cols c = strip_cols(s, w.i0);
+  const int TH = w.j1 - w.j0;
+  const int nrows = TH + 2;
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  for (int tb = 0; tb < nrows; tb += CG_U) {
+    double2 pr[CG_U], xx[CG_U], rr[CG_U];
+    double ph[CG_U];
+#pragma unroll
+    for (int u = 0; u < CG_U; ++u) {
+      const int t = tb + u;
+      const int jl = dir > 0 ? (w.j0 - 1 + t) : (w.j1 - t);
+      const int jg = s.row0 + jl;
+      pr[u] = make_double2(0.0, 0.0);
+      xx[u] = make_double2(0.0, 0.0);
+      rr[u] = make_double2(0.0, 0.0);
+      ph[u] = 0.0;
+      if (t < nrows) {
+        if (jg >= 0 && jg < s.nyg) {
+          if (c.va) pr[u] = ld2(p + cell(s, jl, c.ia));
+          if (c.vh) ph[u] = ld1(p + cell(s, jl, c.ih));
+        }
+        if (t >= 2 && c.va) {        // centre row of this visit: always a band row
+          const int jc = dir > 0 ? jl - 1 : jl + 1;
+          const size_t o = cell(s, jc, c.ia);
+          xx[u] = ld2(x + o);
+          rr[u] = ld2(r + o);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CG_U; ++u) {
+      const int t = tb + u;
+      if (t < nrows) {
+        const int jl = dir > 0 ? (w.j0 - 1 + t) : (w.j1 - t);
+        const int jg = s.row0 + jl;
+        Row nw = {pr[u].x, pr[u].y, ph[u]};
+        if (t >= 2) {
+          const int jc = dir > 0 ? jl - 1 : jl + 1;
+          const int jgc = dir > 0 ? jg - 1 : jg + 1;
+          double qa, qb;
+          if (dir > 0) apply_A<UNIT>(a, c, prev, cur, nw, jgc, qa, qb);
+          else apply_A<UNIT>(a, c, nw, cur, prev, jgc, qa, qb);
+          const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
+          const double xa = xx[u].x + alpha * cur.a;      // x += alpha*p
+          const double xb = xx[u].y + alpha * cur.b;
+          const double ra = rr[u].x - alpha * qa;         // r -= alpha*q
+          const double rb = rr[u].y - alpha * qb;
+          const size_t o = cell(s, jc, c.ia);
+          if (c.vb) {
+            st2(x + o, xa, xb);
+            st2(r + o, ra, rb);
+          } else if (c.va) {
+            st1(x + o, xa);
+            st1(r + o, ra);
+          }
+          if (c.va) {
+            const double za = ((ring_row || c.ring_a) ? 1.0 : a.invd) * ra;
+            acc_rr += ra * ra;
+            acc_rz += ra * za;
+          }
+          if (c.vb) {
+            const double zb = ((ring_row || c.ring_b) ? 1.0 : a.invd) * rb;
+            acc_rr += rb * rb;
+            acc_rz += rb * zb;
+          }
+        }
+        prev = cur;
+        cur = nw;
+      }
+    }
+  }
+}
+
+// Fold per-CTA partials; identical in every CTA.
+__device__ __forceinline__ double fold_partials(const double* part, int n, double* sm) {
+  double acc = 0.0;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) acc += ld_cg(part + q);
+  return block_sum(acc, sm);
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent(CgArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sm[32];
+  const int G = gridDim.x;
+  const int bid = blockIdx.x;
+
+  const double bb = ld_cg(a.scal + S_BB);
+  const double bnorm = sqrt(bb);
+  const double t0 = a.tol * bnorm;
+  const double atol = (t0 > 0.0) ? t0 : 0.0;        // max(0.0, rtol*||b||) with Python's NaN behaviour
+  int iters = 0;
+  int info = a.maxiter;
+  double rr = bb;
+  double rho = ld_cg(a.scal + S_BZ);
+  double rho_prev = 0.0;
+  double* pcur = a.p0;
+  double* pnext = a.p1;
+
+  if (bnorm == 0.0) {                                 // scipy: "return b, 0"; x was zeroed by k_rhs2
+    info = 0;
+  } else {
+    // number of tiles this CTA owns: t = bid + k*G
+    const int ktiles = (a.ntiles > bid) ? (a.ntiles - bid + G - 1) / G : 0;
+    for (int it = 0; it < a.maxiter; ++it) {
+      if (sqrt(rr) < atol) {                          // top-of-loop test on the recursive residual
+        info = 0;
+        break;
+      }
+      const bool first = (it == 0);
+      const double beta = first ? 0.0 : rho / rho_prev;
+      // ---- phase A: top -> bottom
+      double acc = 0.0;
+      for (int k = 0; k < ktiles; ++k) {
+        const WarpTile w = warp_tile(a, bid + k * G);
+        if (w.active) acc += phaseA_warp<UNIT>(a, a.r, pcur, pnext, first, beta, +1, w);
+      }
+      acc = block_sum(acc, sm);
+      if (threadIdx.x == 0) a.part[bid] = acc;
+      grid.sync();
+      const double pq = fold_partials(a.part, G, sm);
+      const double alpha = rho / pq;
+      // ---- phase B: bottom -> top
+      double arr = 0.0, arz = 0.0;
+      for (int k = ktiles - 1; k >= 0; --k) {
+        const WarpTile w = warp_tile(a, bid + k * G);
+        if (w.active) phaseB_warp<UNIT>(a, pnext, a.x, a.r, alpha, -1, w, arr, arz);
+      }
+      arr = block_sum(arr, sm);
+      arz = block_sum(arz, sm);
+      if (threadIdx.x == 0) {
+        a.part[CG_MAX_GRID + bid] = arr;
+        a.part[2 * CG_MAX_GRID + bid] = arz;
+      }
+      grid.sync();
+      rr = fold_partials(a.part + CG_MAX_GRID, G, sm);
+      const double rz = fold_partials(a.part + 2 * CG_MAX_GRID, G, sm);
+      rho_prev = rho;
+      rho = rz;
+      double* tmp = pcur; pcur = pnext; pnext = tmp;
+      ++iters;
+    }
+  }
+  if (bid == 0 && threadIdx.x == 0) {
+    a.scal[S_INFO] = (double)info;
+    a.scal[S_ITERS] = (double)iters;
+    a.scal[S_RR] = rr;
+  }
+}
+
+}  // namespace pf

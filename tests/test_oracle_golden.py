@@ -1,0 +1,81 @@
+"""CPU: the oracle against the golden vectors produced from the unmodified
+reference by oracle/make_golden.py (element-wise operators bit-exact; CG-driven
+quantities within the reference's own summation-order noise)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import pyflow_oracle as orc
+
+OP_TAGS = ["8x8", "16x12", "5x9", "11x7", "33x17", "70x66"]
+
+
+@pytest.mark.parametrize("tag", OP_TAGS)
+def test_operators_bit_exact(golden, tag):
+    g = {k.split("/", 1)[1]: v for k, v in golden["operators"].items() if k.startswith(tag + "/")}
+    dx, dy = g["dxdy"]
+    gx, gy = orc.gradient_coherent(g["p"], dx, dy)
+    assert np.array_equal(gx, g["gx"]) and np.array_equal(gy, g["gy"])
+    assert np.array_equal(orc.divergence_coherent(g["u"], g["v"], dx, dy), g["div"])
+    assert np.array_equal(orc.laplacian_coherent(g["p"], dx, dy), g["lap"])
+    assert np.array_equal(orc.divergence_central(g["u"], g["v"], dx, dy), g["divc"])
+    assert np.array_equal(orc.divergence_central(g["u"], g["v"], 1.0, 1.0), g["divc1"])
+    assert np.array_equal(orc.advect_upwind(g["u"], g["v"], g["f"], dx, dy), g["upwind"])
+    assert np.array_equal(orc.advect_quick(g["u"], g["v"], g["f"], dx, dy), g["quick"])
+
+
+def test_central_divergence_right_column_quirk(golden):
+    g = golden["operators"]
+    d = g["16x12/divc"]
+    assert np.all(d[1:-1, -1] == 0.0) and np.any(d[1:-1, 0] != 0.0)
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) or 1.0))
+
+
+@pytest.mark.parametrize("pc", [True, False])
+def test_pressure_bump(golden, pc):
+    g = golden["pressure"]
+    nx, ny = 24, 20
+    cfg = SimpleNamespace(lin_tol=1e-10, lin_maxiter=300, enable_jacobi_pc=pc)
+    st = orc.allocate_state(nx, ny)
+    orc.interior(st.fields["u"])[ny // 3, nx // 3] = 1.0
+    p, diag = orc.solve_pressure_poisson(st, 0.01, 1.0, 1.0, cfg)
+    tag = f"bump_pc{int(pc)}"
+    assert rel(p, g[f"{tag}/p"]) < 1e-9
+    assert rel(st.fields["u"], g[f"{tag}/u"]) < 1e-9
+    assert abs(diag["true_iterations"] - g[f"{tag}/scalars"][0]) <= 1
+
+
+@pytest.mark.parametrize("name", ["quick32_conv", "quick128_trunc", "upwind96x64_trunc", "quick40x24_spacing",
+                                  "upwind17x33_nopc"])
+def test_trajectories(golden, name):
+    meta = golden["trajectories_meta"][name]
+    cfg = SimpleNamespace(lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
+                          disable_advection=False, diagnostics=False, **meta["cfg"])
+    st, diags = orc.run(cfg, meta["steps"])
+    g = golden["trajectories"]
+    floor = meta["noise_floor"]
+    for f in ("u", "v", "p"):
+        tol = max(1e-9, 100 * floor[f])
+        assert rel(orc.interior(st.fields[f]), g[f"{name}/{f}"][1:-1, 1:-1]) < tol
+    sc = g[f"{name}/scalars"]
+    assert np.array_equal([d["dt"] for d in diags], sc[:, 0])     # dt is summation-order independent
+    it_tol = max(1, 2 * floor["iters_maxdiff"])
+    assert max(abs(a["true_iterations"] - b) for a, b in zip(diags, g[f"{name}/true_iters"])) <= it_tol
+
+
+def test_survey_kats():
+    """Known answers measured on the reference."""
+    cfg = SimpleNamespace(nx=32, ny=32, Re=100.0, advection_scheme="quick", lin_maxiter=10000, lid_velocity=1.0,
+                          cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10)
+    st, diags = orc.run(cfg, 5)
+    assert [d["dt"] for d in diags][:4] == [0.0105, 0.011025000000000002, 0.011576250000000003, 0.012155062500000004]
+    assert diags[-1]["dt"] == 0.0063814078125000026
+    assert diags[0]["true_iterations"] == 0
+    assert all(abs(a - b) <= 1 for a, b in zip([d["true_iterations"] for d in diags], [0, 279, 301, 298, 291]))
+    assert abs(np.linalg.norm(orc.interior(st.fields["u"])) - 5.738896948423326) < 1e-9
+    assert abs(np.linalg.norm(orc.interior(st.fields["p"])) - 1.970969104493264e+01) < 1e-7
+    assert diags[-1]["Rp_iterations"] == 1
