@@ -143,6 +143,8 @@ int pf_comm_init(pf_ctx* ctx, const void* id128, int rank, int nranks);
 
 /* Introspection used by bench.py / tests. */
 int pf_device_info(pf_ctx* ctx, int* sm_count, int* cg_grid_blocks, int* cg_block_threads);
+/* number of kernels of this library launched on the context so far */
+int pf_launch_count(pf_ctx* ctx, int64_t* out);
 
 #ifdef __cplusplus
 }

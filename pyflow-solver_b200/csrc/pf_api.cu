@@ -33,6 +33,7 @@ struct pf_ctx {
   double* h_center = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int cg_grid = 0;
+  long long launches = 0;          // kernels of this library launched so far
   bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
   dim3 sgrid;                      // grid of the simple kernels
   pf::Comm* comm = nullptr;        // multi-GPU slabs (null when nranks == 1)
@@ -53,6 +54,13 @@ int fail(pf_ctx* c, int code, const char* what, const char* detail) {
   do {                                                                             \
     cudaError_t e__ = (call);                                                      \
     if (e__ != cudaSuccess) return fail((ctx), PF_ERR_CUDA, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+// after every kernel launch: surface launch errors, count the launch
+#define PF_LAUNCHED(ctx)                      \
+  do {                                        \
+    PF_CUDA((ctx), cudaGetLastError());       \
+    (ctx)->launches++;                        \
   } while (0)
 
 #define PF_TRY(expr)                \
@@ -114,6 +122,7 @@ int launch_cg(pf_ctx* c, CgArgs& a, cudaStream_t st) {
   void* args[] = {&a};
   PF_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_cg_persistent<UNIT>, dim3(c->cg_grid), dim3(CG_THREADS),
                                          args, 0, st));
+  c->launches++;
   return PF_OK;
 }
 
@@ -127,7 +136,7 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   const double ncells = (double)s.nx * (double)s.nyg;
   if (c->comm && subtract_mean) PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_RHS_SUM, 1, /*max=*/0, st, c->err));
   k_rhs2<<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, c->r, ncells, subtract_mean, pin, invd, red);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   if (e0) PF_CUDA(c, cudaEventRecord(e0, st));
   if (c->comm) {
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
@@ -144,7 +153,7 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   if (e1) PF_CUDA(c, cudaEventRecord(e1, st));
   if (is_unit(dx, dy)) k_resid<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
   else k_resid<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   return PF_OK;
 }
 
@@ -188,7 +197,7 @@ int launch_predict(pf_ctx* c, int scheme, double dt, double dx, double dy, cudaS
     default:
       return fail(c, PF_ERR_ARG, "pf_step", "unknown advection scheme");
   }
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   return PF_OK;
 }
 
@@ -303,6 +312,12 @@ int pf_device_info(pf_ctx* c, int* sm_count, int* cg_grid_blocks, int* cg_block_
   return PF_OK;
 }
 
+int pf_launch_count(pf_ctx* c, int64_t* out) {
+  if (!c || !out) return PF_ERR_ARG;
+  *out = (int64_t)c->launches;
+  return PF_OK;
+}
+
 int pf_upload(pf_ctx* c, const double* u, const double* v, const double* p, int64_t row_stride, void* stream) {
   if (!c || row_stride < c->s.nx) return PF_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -330,7 +345,7 @@ int pf_prestep_reduce(pf_ctx* c, double out[3], void* stream) {
   const Red red{c->red_part, c->red_counter, c->scal};
   if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 1, st, c->err));
   k_prestep<<<c->sgrid, KT, 0, st>>>(c->s, c->u, c->v, red);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   if (c->comm) {
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_UMAX, 2, 1, st, c->err));
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVC_SUMSQ, 1, 0, st, c->err));
@@ -370,7 +385,7 @@ int pf_step(pf_ctx* c, const pf_step_params* P, pf_step_out* out, void* stream) 
   if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 0, st, c->err));
   if (unit) k_rhs1<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
   else k_rhs1<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   if (c->comm) PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVB_SUMSQ, 1, 0, st, c->err));
   // rhs pass 2 + CG + true residual
   PF_TRY(solve_on_device(c, dx, dy, P->jacobi, P->inv_diag_interior, P->lin_tol, P->lin_maxiter, 1, 1, st, c->ev[1],
@@ -378,19 +393,19 @@ int pf_step(pf_ctx* c, const pf_step_params* P, pf_step_out* out, void* stream) 
   // correction
   if (unit) k_correct<true><<<c->sgrid, KT, 0, st>>>(s, c->x, c->x, c->u, c->v, dt, dx, dy, c->scal);
   else k_correct<false><<<c->sgrid, KT, 0, st>>>(s, c->x, c->x, c->u, c->v, dt, dx, dy, c->scal);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 0, st, c->err));
   if (unit) k_divnorm<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, red, S_DIVA_SUMSQ);
   else k_divnorm<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, red, S_DIVA_SUMSQ);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   if (!P->projection_only) {
     if (P->lid_set) {
       k_lid<<<(s.nx + KT - 1) / KT, KT, 0, st>>>(s, c->u, P->lid_velocity);
-      PF_CUDA(c, cudaGetLastError());
+      PF_LAUNCHED(c);
     }
     if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 1, st, c->err));
     k_post<<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->uo, c->vo, c->x, c->center, red);
-    PF_CUDA(c, cudaGetLastError());
+    PF_LAUNCHED(c);
   }
   PF_CUDA(c, cudaEventRecord(c->ev[3], st));
   PF_TRY(read_scalars(c, st, !P->projection_only));
@@ -431,7 +446,7 @@ int pf_centerline(pf_ctx* c, double* host_out, void* stream) {
     return PF_OK;
   }
   k_centerline<<<(c->s.nyl + KT - 1) / KT, KT, 0, st>>>(c->s, c->u, c->center);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   PF_CUDA(c, cudaMemcpyAsync(c->h_center, c->center, sizeof(double) * (size_t)c->s.nyl, cudaMemcpyDeviceToHost, st));
   PF_CUDA(c, cudaStreamSynchronize(st));
   memcpy(host_out, c->h_center, sizeof(double) * (size_t)c->s.nyl);
@@ -455,7 +470,7 @@ int pf_op_gradient_coherent(pf_ctx* c, const double* p, double* gx, double* gy, 
   PF_TRY(h2d_field(c, c->b, p, nxs, st));
   if (is_unit(dx, dy)) k_op_grad<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, c->p1, dx, dy);
   else k_op_grad<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, c->p1, dx, dy);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   PF_TRY(d2h_field(c, gx, c->p0, nxs, st));
   PF_TRY(d2h_field(c, gy, c->p1, nxs, st));
   PF_CUDA(c, cudaStreamSynchronize(st));
@@ -470,7 +485,7 @@ static int op_div(pf_ctx* c, const double* u, const double* v, double* out, doub
   PF_TRY(h2d_field(c, c->r, v, nxs, st));
   if (is_unit(dx, dy)) k_op_div<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, dx, dy, central);
   else k_op_div<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, dx, dy, central);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   PF_TRY(d2h_field(c, out, c->p0, nxs, st));
   PF_CUDA(c, cudaStreamSynchronize(st));
   return PF_OK;
@@ -491,7 +506,7 @@ int pf_op_laplacian_coherent(pf_ctx* c, const double* p, double* out, double dx,
   PF_TRY(h2d_field(c, c->b, p, nxs, st));
   if (is_unit(dx, dy)) k_op_lap<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, dx, dy);
   else k_op_lap<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, dx, dy);
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   PF_TRY(d2h_field(c, out, c->p0, nxs, st));
   PF_CUDA(c, cudaStreamSynchronize(st));
   return PF_OK;
@@ -513,7 +528,7 @@ int pf_op_advect(pf_ctx* c, int scheme, const double* u, const double* v, const 
     if (unit) k_op_advect<true, PF_ADV_QUICK><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, c->p1, dx, dy);
     else k_op_advect<false, PF_ADV_QUICK><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p0, c->p1, dx, dy);
   }
-  PF_CUDA(c, cudaGetLastError());
+  PF_LAUNCHED(c);
   PF_TRY(d2h_field(c, out, c->p1, nxs, st));
   PF_CUDA(c, cudaStreamSynchronize(st));
   return PF_OK;

@@ -83,6 +83,11 @@ class DeviceSlab:
         _lib.check(self._lib.pf_device_info(self.ctx, C.byref(sm), C.byref(grid), C.byref(thr)), self.ctx)
         return {"sm_count": sm.value, "cg_grid_blocks": grid.value, "cg_block_threads": thr.value}
 
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _lib.check(self._lib.pf_launch_count(self.ctx, C.byref(n)), self.ctx)
+        return int(n.value)
+
     def init_comm(self, unique_id: bytes, rank: int, nranks: int):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _lib.check(self._lib.pf_comm_init(self.ctx, buf, rank, nranks), self.ctx, "pf_comm_init")

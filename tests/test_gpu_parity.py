@@ -272,7 +272,7 @@ def test_host_mutation_between_steps_is_uploaded():
     from pyflow.core.ghost_fields import allocate_state, interior_view
     from pyflow.residuals.manager import ResidualManager
     from pyflow.solvers.solver import step
-    cfg = _cfg(dict(nx=24, ny=24, Re=100.0, advection_scheme="upwind", lin_maxiter=100))
+    cfg = _cfg(dict(nx=24, ny=24, Re=100.0, advection_scheme="upwind", lin_maxiter=2000))   # converged regime
     a, b = allocate_state(24, 24), orc.allocate_state(24, 24)
     tr = ResidualManager()
     step(cfg, a, tr, 0)
@@ -288,7 +288,7 @@ def test_host_mutation_between_steps_is_uploaded():
 def test_foreign_state_object_is_synchronised_eagerly():
     from pyflow.residuals.manager import ResidualManager
     from pyflow.solvers.solver import step
-    cfg = _cfg(dict(nx=20, ny=16, Re=100.0, advection_scheme="quick", lin_maxiter=100))
+    cfg = _cfg(dict(nx=20, ny=16, Re=100.0, advection_scheme="quick", lin_maxiter=2000))   # converged regime
     foreign = orc.allocate_state(20, 16)          # plain dataclass with dict fields
     ref = orc.allocate_state(20, 16)
     held = foreign.fields["u"]
