@@ -160,6 +160,8 @@ def run_reference_arm(args, wl, rank):
     n = 2048
     while n > 128 and n * n * 300 * per_cell_iter * total_steps > budget_s:
         n //= 2
+    if args.ref_grid:
+        n = args.ref_grid
     mlups, sps, iters = oracle_sample(n, wl["Re"], 300, args.steps, args.warmup)
     cores = cpu_threads()
     sample = (f"{args.steps} steps (after {max(1, args.warmup)} warm-up) of a {n}x{n} cavity from rest, Re={wl['Re']}, "
@@ -334,6 +336,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cavity4096", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-grid", type=int, default=0, help="reference arm: force the sample grid size (tests)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
