@@ -25,7 +25,19 @@
 // from one extra scalar load on lanes 0 / 31 (an L1 hit: the neighbouring warp
 // of the same CTA streams that line).  Each value is fetched from HBM once per
 // phase.  Phase A marches top->bottom and phase B bottom->top so the rows one
-// phase touched last are the first the next one reads (L2 reuse, 126 MB).
+// phase touched last are the first the next one reads (L2 reuse, 126 MB);
+// x and the old search direction, which nobody re-reads soon, are streamed
+// with evict-first hints so they do not displace r and p in L2.
+//
+// Rows are processed in batches of CG_U: all loads of a batch are issued, then
+// consumed.  Rows strictly inside a band (the vast majority) take a LEAN path
+// with no boundary masks; only the first/last rows of a band (which may touch
+// the domain boundary, the Jacobi ring or the pinned cell) and strips on the
+// left/right walls (template XE) evaluate the Neumann / ring predicates.
+//
+// Sign bookkeeping that keeps results bit-identical while saving negations:
+// q = -lap exactly, so r - alpha*q == r + alpha*lap and sum p*q == -(sum p*lap)
+// (IEEE negation is exact and round-to-nearest is sign-symmetric).
 #pragma once
 
 #include <cooperative_groups.h>
@@ -85,195 +97,291 @@ __device__ __forceinline__ WarpTile warp_tile(const CgArgs& a, int t) {
 
 // Per-lane column geometry of a strip.
 struct Cols {
-  int ia, ib, ih;
+  int ia, ih;
   bool va, vb, vh;          // column exists
   bool hw_a, he_a, he_b;    // has west / east neighbour inside the domain
   bool ring_a, ring_b, ring_h;
 };
 
+template <bool XE>
 __device__ __forceinline__ Cols strip_cols(const Slab& s, int i0) {
   const int lane = threadIdx.x & 31;
   Cols c;
   c.ia = i0 + 2 * lane;
-  c.ib = c.ia + 1;
   c.ih = (lane == 0) ? i0 - 1 : i0 + STRIP;
-  c.va = c.ia < s.nx;
-  c.vb = c.ib < s.nx;
-  c.vh = (lane == 0 || lane == 31) && c.ih >= 0 && c.ih < s.nx;
-  c.hw_a = c.ia > 0;
-  c.he_a = c.ia < s.nx - 1;
-  c.he_b = c.ib < s.nx - 1;
-  c.ring_a = (c.ia == 0) || (c.ia == s.nx - 1);
-  c.ring_b = (c.ib == 0) || (c.ib == s.nx - 1);
-  c.ring_h = (c.ih == 0) || (c.ih == s.nx - 1);
+  if (XE) {
+    const int ib = c.ia + 1;
+    c.va = c.ia < s.nx;
+    c.vb = ib < s.nx;
+    c.vh = (lane == 0 || lane == 31) && c.ih >= 0 && c.ih < s.nx;
+    c.hw_a = c.ia > 0;
+    c.he_a = c.ia < s.nx - 1;
+    c.he_b = ib < s.nx - 1;
+    c.ring_a = (c.ia == 0) || (c.ia == s.nx - 1);
+    c.ring_b = (ib == 0) || (ib == s.nx - 1);
+    c.ring_h = (c.ih == 0) || (c.ih == s.nx - 1);
+  } else {                    // strip strictly inside the domain in x
+    c.va = c.vb = true;
+    c.vh = (lane == 0 || lane == 31);
+    c.hw_a = c.he_a = c.he_b = true;
+    c.ring_a = c.ring_b = c.ring_h = false;
+  }
   return c;
 }
 
-// q = A p at the two columns of the centre row `cur`.
-template <bool UNIT>
-__device__ __forceinline__ void apply_A(const CgArgs& a, const Cols& c, const Row& south, const Row& cur,
-                                        const Row& north, int jgc, double& qa, double& qb) {
+// laplacian_coherent (NOT negated) at the two columns of the centre row.
+// GEN: evaluate the Neumann predicates of this row / strip; otherwise every
+// neighbour exists.
+template <bool UNIT, bool XE, bool GEN>
+__device__ __forceinline__ void lap_pair(const CgArgs& a, const Cols& c, const Row& south, const Row& cur,
+                                         const Row& north, bool hs, bool hn, double& la, double& lb) {
   const int lane = threadIdx.x & 31;
   double w_a = __shfl_up_sync(0xffffffffu, cur.b, 1);
   double e_b = __shfl_down_sync(0xffffffffu, cur.a, 1);
   if (lane == 0) w_a = cur.h;
   if (lane == 31) e_b = cur.h;
-  const bool hs = jgc > 0, hn = jgc < a.s.nyg - 1;
-  qa = neg_lap<UNIT>(cur.a, w_a, cur.b, south.a, north.a, c.hw_a, c.he_a, hs, hn, a.dx, a.dy);
-  qb = neg_lap<UNIT>(cur.b, cur.a, e_b, south.b, north.b, true, c.he_b, hs, hn, a.dx, a.dy);
-  if (jgc == 0 && c.ia == 0) qa = cur.a;   // pinned row: out[0] = x[0]
+  if (XE || GEN) {
+    la = -neg_lap<UNIT>(cur.a, w_a, cur.b, south.a, north.a, c.hw_a, c.he_a, hs, hn, a.dx, a.dy);
+    lb = -neg_lap<UNIT>(cur.b, cur.a, e_b, south.b, north.b, true, c.he_b, hs, hn, a.dx, a.dy);
+  } else {
+    la = -neg_lap<UNIT>(cur.a, w_a, cur.b, south.a, north.a, true, true, true, true, a.dx, a.dy);
+    lb = -neg_lap<UNIT>(cur.b, cur.a, e_b, south.b, north.b, true, true, true, true, a.dx, a.dy);
+  }
 }
 
-// ---- phase A over one warp tile ------------------------------------------------
-template <bool UNIT>
-__device__ __forceinline__ double phaseA_warp(const CgArgs& a, const double* r, const double* pold, double* pnew,
-                                              bool first, double beta, int dir, const WarpTile& w) {
+// Visiting order of a warp tile: index t = 0 is the halo row in front of the
+// band, t = 1..TH the band rows, t = TH+1 the halo row behind it.
+struct March {
+  int jl0;      // local row of t = 0
+  int dj;       // +1 / -1
+  int TH;
+};
+template <int DIR>
+__device__ __forceinline__ March make_march(const WarpTile& w) {
+  March m;
+  m.TH = w.j1 - w.j0;
+  m.dj = DIR;
+  m.jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
+  return m;
+}
+
+// ---- phase A -------------------------------------------------------------------
+// One batch of n (<= CG_U) consecutive visits starting at t0.  GEN rows evaluate
+// existence / ring / pin predicates; lean rows are strictly inside the band.
+template <bool UNIT, bool XE, bool GEN, int DIR>
+__device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, const March& m, const double* r,
+                                             const double* pold, double* pnew, bool first, double beta, int t0, int n,
+                                             Row& prev, Row& cur, double& acc) {
   const Slab& s = a.s;
-  const Cols c = strip_cols(s, w.i0);
-  const int TH = w.j1 - w.j0;
-  const int nrows = TH + 2;          // visiting index t: 0 halo, 1..TH band, TH+1 halo
+  const uint64_t pol = policy_evict_first();
+  double2 rr[CG_U], pp[CG_U];
+  double rh[CG_U], ph[CG_U];
+#pragma unroll
+  for (int u = 0; u < CG_U; ++u) {
+    const int jl = m.jl0 + DIR * (t0 + u);
+    const int jg = s.row0 + jl;
+    rr[u] = make_double2(0.0, 0.0);
+    pp[u] = make_double2(0.0, 0.0);
+    rh[u] = 0.0;
+    ph[u] = 0.0;
+    const bool ok = GEN ? (u < n && jg >= 0 && jg < s.nyg) : true;
+    if (ok) {
+      if (c.va) {
+        const size_t o = cell(s, jl, c.ia);
+        rr[u] = ld2(r + o);
+        if (!first) pp[u] = ld2_hint(pold + o, pol);
+      }
+      if (c.vh) {
+        const size_t oh = cell(s, jl, c.ih);
+        rh[u] = ld1(r + oh);
+        if (!first) ph[u] = ld1(pold + oh);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < CG_U; ++u) {
+    if (!GEN || u < n) {               // warp-uniform
+      const int t = t0 + u;
+      const int jl = m.jl0 + DIR * t;
+      const int jg = s.row0 + jl;
+      double da = a.invd, db = a.invd, dh = a.invd;
+      if (GEN || XE) {
+        const bool ring_row = GEN && ((jg == 0) || (jg == s.nyg - 1));
+        da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+        db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+        dh = (ring_row || c.ring_h) ? 1.0 : a.invd;
+      }
+      const double za = da * rr[u].x, zb = db * rr[u].y, zh = dh * rh[u];
+      Row nw;
+      if (first) {                     // p = z
+        nw.a = za; nw.b = zb; nw.h = zh;
+      } else {                         // p *= beta ; p += z
+        nw.a = (pp[u].x * beta) + za;
+        nw.b = (pp[u].y * beta) + zb;
+        nw.h = (ph[u] * beta) + zh;
+      }
+      if (!GEN || (t >= 1 && t <= m.TH)) {
+        double* dst = pnew + cell(s, jl, c.ia);
+        if (c.vb) st2(dst, nw.a, nw.b);
+        else if (c.va) st1(dst, nw.a);
+      }
+      if (!GEN || t >= 2) {
+        const int jgc = jg - DIR;
+        const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+        double la, lb;
+        if (DIR > 0) lap_pair<UNIT, XE, GEN>(a, c, prev, cur, nw, hs, hn, la, lb);
+        else lap_pair<UNIT, XE, GEN>(a, c, nw, cur, prev, hs, hn, la, lb);
+        if (GEN && jgc == 0 && c.ia == 0) la = -cur.a;      // pinned row: q[0] = p[0]
+        // acc holds sum p*lap = -(p.q)
+        if (XE) {
+          if (c.va) acc += cur.a * la;
+          if (c.vb) acc += cur.b * lb;
+        } else {
+          acc += cur.a * la;
+          acc += cur.b * lb;
+        }
+      }
+      prev = cur;
+      cur = nw;
+    }
+  }
+}
+
+template <bool UNIT, bool XE, int DIR>
+__device__ __forceinline__ double phaseA_strip(const CgArgs& a, const double* r, const double* pold, double* pnew,
+                                               bool first, double beta, const WarpTile& w) {
+  const Cols c = strip_cols<XE>(a.s, w.i0);
+  const March m = make_march<DIR>(w);
+  const int nrows = m.TH + 2;
   double acc = 0.0;
   Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
-  for (int tb = 0; tb < nrows; tb += CG_U) {
-    double2 rr[CG_U], pp[CG_U];
-    double rh[CG_U], ph[CG_U];
-#pragma unroll
-    for (int u = 0; u < CG_U; ++u) {
-      const int t = tb + u;
-      const int jl = dir > 0 ? (w.j0 - 1 + t) : (w.j1 - t);
-      const int jg = s.row0 + jl;
-      rr[u] = make_double2(0.0, 0.0);
-      pp[u] = make_double2(0.0, 0.0);
-      rh[u] = 0.0;
-      ph[u] = 0.0;
-      if (t < nrows && jg >= 0 && jg < s.nyg) {
-        if (c.va) {
-          const size_t o = cell(s, jl, c.ia);
-          rr[u] = ld2(r + o);
-          if (!first) pp[u] = ld2(pold + o);
-        }
-        if (c.vh) {
-          const size_t oh = cell(s, jl, c.ih);
-          rh[u] = ld1(r + oh);
-          if (!first) ph[u] = ld1(pold + oh);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < CG_U; ++u) {
-      const int t = tb + u;
-      if (t < nrows) {               // warp-uniform
-        const int jl = dir > 0 ? (w.j0 - 1 + t) : (w.j1 - t);
-        const int jg = s.row0 + jl;
-        const bool ring_row = (jg == 0) || (jg == s.nyg - 1);
-        const double za = ((ring_row || c.ring_a) ? 1.0 : a.invd) * rr[u].x;
-        const double zb = ((ring_row || c.ring_b) ? 1.0 : a.invd) * rr[u].y;
-        const double zh = ((ring_row || c.ring_h) ? 1.0 : a.invd) * rh[u];
-        Row nw;
-        if (first) {                 // p = z
-          nw.a = za; nw.b = zb; nw.h = zh;
-        } else {                     // p *= beta ; p += z
-          nw.a = (pp[u].x * beta) + za;
-          nw.b = (pp[u].y * beta) + zb;
-          nw.h = (ph[u] * beta) + zh;
-        }
-        if (t >= 1 && t <= TH) {
-          double* dst = pnew + cell(s, jl, c.ia);
-          if (c.vb) st2(dst, nw.a, nw.b);
-          else if (c.va) st1(dst, nw.a);
-        }
-        if (t >= 2) {
-          const int jgc = dir > 0 ? jg - 1 : jg + 1;
-          double qa, qb;
-          if (dir > 0) apply_A<UNIT>(a, c, prev, cur, nw, jgc, qa, qb);
-          else apply_A<UNIT>(a, c, nw, cur, prev, jgc, qa, qb);
-          if (c.va) acc += cur.a * qa;
-          if (c.vb) acc += cur.b * qb;
-        }
-        prev = cur;
-        cur = nw;
-      }
-    }
+  // generic head: t = 0, 1, 2 (halo row, first band row, and the row that
+  // completes the first centre); lean body: t = 3 .. TH-1; generic tail.
+  const int head = nrows < 3 ? nrows : 3;
+  phaseA_batch<UNIT, XE, true, DIR>(a, c, m, r, pold, pnew, first, beta, 0, head, prev, cur, acc);
+  int t = head;
+  const int lean_end = m.TH;                       // lean rows are t in [3, TH)
+  for (; t + CG_U <= lean_end; t += CG_U)
+    phaseA_batch<UNIT, XE, false, DIR>(a, c, m, r, pold, pnew, first, beta, t, CG_U, prev, cur, acc);
+  for (; t < nrows; t += CG_U) {
+    const int n = (nrows - t) < CG_U ? (nrows - t) : CG_U;
+    phaseA_batch<UNIT, XE, true, DIR>(a, c, m, r, pold, pnew, first, beta, t, n, prev, cur, acc);
   }
   return acc;
 }
 
-// ---- phase B over one warp tile ------------------------------------------------
-template <bool UNIT>
-__device__ __forceinline__ void phaseB_warp(const CgArgs& a, const double* p, double* x, double* r, double alpha,
-                                            int dir, const WarpTile& w, double& acc_rr, double& acc_rz) {
+// ---- phase B -------------------------------------------------------------------
+template <bool UNIT, bool XE, bool GEN, int DIR>
+__device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, const March& m, const double* p,
+                                             double* x, double* r, double alpha, int t0, int n, Row& prev, Row& cur,
+                                             double& acc_rr, double& acc_rz) {
   const Slab& s = a.s;
-  const Cols c = strip_cols(s, w.i0);
-  const int TH = w.j1 - w.j0;
-  const int nrows = TH + 2;
-  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
-  for (int tb = 0; tb < nrows; tb += CG_U) {
-    double2 pr[CG_U], xx[CG_U], rr[CG_U];
-    double ph[CG_U];
+  const uint64_t pol = policy_evict_first();
+  double2 pr[CG_U], xx[CG_U], rr[CG_U];
+  double ph[CG_U];
 #pragma unroll
-    for (int u = 0; u < CG_U; ++u) {
-      const int t = tb + u;
-      const int jl = dir > 0 ? (w.j0 - 1 + t) : (w.j1 - t);
-      const int jg = s.row0 + jl;
-      pr[u] = make_double2(0.0, 0.0);
-      xx[u] = make_double2(0.0, 0.0);
-      rr[u] = make_double2(0.0, 0.0);
-      ph[u] = 0.0;
-      if (t < nrows) {
-        if (jg >= 0 && jg < s.nyg) {
-          if (c.va) pr[u] = ld2(p + cell(s, jl, c.ia));
-          if (c.vh) ph[u] = ld1(p + cell(s, jl, c.ih));
-        }
-        if (t >= 2 && c.va) {        // centre row of this visit: always a band row
-          const int jc = dir > 0 ? jl - 1 : jl + 1;
-          const size_t o = cell(s, jc, c.ia);
-          xx[u] = ld2(x + o);
-          rr[u] = ld2(r + o);
-        }
+  for (int u = 0; u < CG_U; ++u) {
+    const int t = t0 + u;
+    const int jl = m.jl0 + DIR * t;
+    const int jg = s.row0 + jl;
+    pr[u] = make_double2(0.0, 0.0);
+    xx[u] = make_double2(0.0, 0.0);
+    rr[u] = make_double2(0.0, 0.0);
+    ph[u] = 0.0;
+    if (!GEN || u < n) {
+      if (!GEN || (jg >= 0 && jg < s.nyg)) {
+        if (c.va) pr[u] = ld2(p + cell(s, jl, c.ia));
+        if (c.vh) ph[u] = ld1(p + cell(s, jl, c.ih));
       }
-    }
-#pragma unroll
-    for (int u = 0; u < CG_U; ++u) {
-      const int t = tb + u;
-      if (t < nrows) {
-        const int jl = dir > 0 ? (w.j0 - 1 + t) : (w.j1 - t);
-        const int jg = s.row0 + jl;
-        Row nw = {pr[u].x, pr[u].y, ph[u]};
-        if (t >= 2) {
-          const int jc = dir > 0 ? jl - 1 : jl + 1;
-          const int jgc = dir > 0 ? jg - 1 : jg + 1;
-          double qa, qb;
-          if (dir > 0) apply_A<UNIT>(a, c, prev, cur, nw, jgc, qa, qb);
-          else apply_A<UNIT>(a, c, nw, cur, prev, jgc, qa, qb);
-          const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
-          const double xa = xx[u].x + alpha * cur.a;      // x += alpha*p
-          const double xb = xx[u].y + alpha * cur.b;
-          const double ra = rr[u].x - alpha * qa;         // r -= alpha*q
-          const double rb = rr[u].y - alpha * qb;
-          const size_t o = cell(s, jc, c.ia);
-          if (c.vb) {
-            st2(x + o, xa, xb);
-            st2(r + o, ra, rb);
-          } else if (c.va) {
-            st1(x + o, xa);
-            st1(r + o, ra);
-          }
-          if (c.va) {
-            const double za = ((ring_row || c.ring_a) ? 1.0 : a.invd) * ra;
-            acc_rr += ra * ra;
-            acc_rz += ra * za;
-          }
-          if (c.vb) {
-            const double zb = ((ring_row || c.ring_b) ? 1.0 : a.invd) * rb;
-            acc_rr += rb * rb;
-            acc_rz += rb * zb;
-          }
-        }
-        prev = cur;
-        cur = nw;
+      if ((!GEN || t >= 2) && c.va) {          // centre row of this visit: always a band row
+        const size_t o = cell(s, jl - DIR, c.ia);
+        xx[u] = ld2_hint_nol1(x + o, pol);
+        rr[u] = ld2(r + o);
       }
     }
   }
+#pragma unroll
+  for (int u = 0; u < CG_U; ++u) {
+    if (!GEN || u < n) {
+      const int t = t0 + u;
+      const int jl = m.jl0 + DIR * t;
+      const int jg = s.row0 + jl;
+      Row nw = {pr[u].x, pr[u].y, ph[u]};
+      if (!GEN || t >= 2) {
+        const int jc = jl - DIR;
+        const int jgc = jg - DIR;
+        const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+        double la, lb;
+        if (DIR > 0) lap_pair<UNIT, XE, GEN>(a, c, prev, cur, nw, hs, hn, la, lb);
+        else lap_pair<UNIT, XE, GEN>(a, c, nw, cur, prev, hs, hn, la, lb);
+        if (GEN && jgc == 0 && c.ia == 0) la = -cur.a;    // pinned row: q[0] = p[0]
+        const double xa = xx[u].x + alpha * cur.a;        // x += alpha*p
+        const double xb = xx[u].y + alpha * cur.b;
+        const double ra = rr[u].x + alpha * la;           // r -= alpha*q,  q = -lap
+        const double rb = rr[u].y + alpha * lb;
+        const size_t o = cell(s, jc, c.ia);
+        if (c.vb) {
+          st2_hint(x + o, xa, xb, pol);
+          st2(r + o, ra, rb);
+        } else if (c.va) {
+          st1(x + o, xa);
+          st1(r + o, ra);
+        }
+        double da = a.invd, db = a.invd;
+        if (GEN || XE) {
+          const bool ring_row = GEN && ((jgc == 0) || (jgc == s.nyg - 1));
+          da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+          db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+        }
+        if (!XE || c.va) {
+          acc_rr += ra * ra;
+          acc_rz += ra * (da * ra);
+        }
+        if (!XE || c.vb) {
+          acc_rr += rb * rb;
+          acc_rz += rb * (db * rb);
+        }
+      }
+      prev = cur;
+      cur = nw;
+    }
+  }
+}
+
+template <bool UNIT, bool XE, int DIR>
+__device__ __forceinline__ void phaseB_strip(const CgArgs& a, const double* p, double* x, double* r, double alpha,
+                                             const WarpTile& w, double& acc_rr, double& acc_rz) {
+  const Cols c = strip_cols<XE>(a.s, w.i0);
+  const March m = make_march<DIR>(w);
+  const int nrows = m.TH + 2;
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  const int head = nrows < 3 ? nrows : 3;
+  phaseB_batch<UNIT, XE, true, DIR>(a, c, m, p, x, r, alpha, 0, head, prev, cur, acc_rr, acc_rz);
+  int t = head;
+  const int lean_end = m.TH;
+  for (; t + CG_U <= lean_end; t += CG_U)
+    phaseB_batch<UNIT, XE, false, DIR>(a, c, m, p, x, r, alpha, t, CG_U, prev, cur, acc_rr, acc_rz);
+  for (; t < nrows; t += CG_U) {
+    const int n = (nrows - t) < CG_U ? (nrows - t) : CG_U;
+    phaseB_batch<UNIT, XE, true, DIR>(a, c, m, p, x, r, alpha, t, n, prev, cur, acc_rr, acc_rz);
+  }
+}
+
+// Warp-level dispatch: strips touching the left / right wall (or only partly
+// inside the domain) take the XE instantiation.
+template <bool UNIT, int DIR>
+__device__ __forceinline__ double phaseA_warp(const CgArgs& a, const double* r, const double* pold, double* pnew,
+                                              bool first, double beta, const WarpTile& w) {
+  const bool xe = (w.i0 == 0) || (w.i0 + STRIP >= a.s.nx);
+  if (xe) return phaseA_strip<UNIT, true, DIR>(a, r, pold, pnew, first, beta, w);
+  return phaseA_strip<UNIT, false, DIR>(a, r, pold, pnew, first, beta, w);
+}
+template <bool UNIT, int DIR>
+__device__ __forceinline__ void phaseB_warp(const CgArgs& a, const double* p, double* x, double* r, double alpha,
+                                            const WarpTile& w, double& acc_rr, double& acc_rz) {
+  const bool xe = (w.i0 == 0) || (w.i0 + STRIP >= a.s.nx);
+  if (xe) phaseB_strip<UNIT, true, DIR>(a, p, x, r, alpha, w, acc_rr, acc_rz);
+  else phaseB_strip<UNIT, false, DIR>(a, p, x, r, alpha, w, acc_rr, acc_rz);
 }
 
 // Fold per-CTA partials; identical in every CTA.
@@ -318,10 +426,10 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent(CgArgs a) {
       double acc = 0.0;
       for (int k = 0; k < ktiles; ++k) {
         const WarpTile w = warp_tile(a, bid + k * G);
-        if (w.active) acc += phaseA_warp<UNIT>(a, a.r, pcur, pnext, first, beta, +1, w);
+        if (w.active) acc += phaseA_warp<UNIT, +1>(a, a.r, pcur, pnext, first, beta, w);
       }
       acc = block_sum(acc, sm);
-      if (threadIdx.x == 0) a.part[bid] = acc;
+      if (threadIdx.x == 0) a.part[bid] = -acc;       // p.q = -(sum p*lap)
       grid.sync();
       const double pq = fold_partials(a.part, G, sm);
       const double alpha = rho / pq;
@@ -329,7 +437,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent(CgArgs a) {
       double arr = 0.0, arz = 0.0;
       for (int k = ktiles - 1; k >= 0; --k) {
         const WarpTile w = warp_tile(a, bid + k * G);
-        if (w.active) phaseB_warp<UNIT>(a, pnext, a.x, a.r, alpha, -1, w, arr, arz);
+        if (w.active) phaseB_warp<UNIT, -1>(a, pnext, a.x, a.r, alpha, w, arr, arz);
       }
       arr = block_sum(arr, sm);
       arz = block_sum(arz, sm);

@@ -86,21 +86,34 @@ __device__ __forceinline__ double ld1(const double* p) {
   asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
-// streaming variants: data with no reuse before eviction (x in phase B, old p)
-__device__ __forceinline__ double2 ld2_stream(const double* p) {
+// Streaming accesses: an L2 evict-first cache policy (createpolicy) attached to
+// the access, for data nobody re-reads before it would be evicted anyway (x in
+// phase B, the old search direction in phase A), so that it does not displace
+// r and p, which the next (reversed) sweep re-reads from L2.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double2 ld2_hint(const double* p, uint64_t pol) {
   double2 v;
-  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v2.f64 {%0,%1}, [%2];"
-               : "=d"(v.x), "=d"(v.y) : "l"(p));
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
   return v;
+}
+__device__ __forceinline__ double2 ld2_hint_nol1(const double* p, uint64_t pol) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+               : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st2_hint(double* p, double a, double b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void st2(double* p, double a, double b) {
   asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 __device__ __forceinline__ void st1(double* p, double a) {
   asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
-}
-__device__ __forceinline__ void st2_stream(double* p, double a, double b) {
-  asm volatile("st.global.L2::evict_first.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 __device__ __forceinline__ double ld_cg(const double* p) {  // L2-only (partials, scalars)
   double v;
