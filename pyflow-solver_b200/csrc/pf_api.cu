@@ -138,22 +138,53 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   k_rhs2<<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, c->r, ncells, subtract_mean, pin, invd, red);
   PF_LAUNCHED(c);
   if (e0) PF_CUDA(c, cudaEventRecord(e0, st));
+  CgArgs a{};
+  a.s = s; a.b = c->b; a.x = c->x; a.r = c->r; a.p0 = c->p0; a.p1 = c->p1;
+  a.part = c->cg_part; a.scal = c->scal;
+  a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
+  cg_geometry(c, a);
+  const bool unit = is_unit(dx, dy);
   if (c->comm) {
+    // split-phase CG: halo rows + scalar all-reduces between the phases (NCCL, same stream)
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
-    return fail(c, PF_ERR_UNSUPPORTED, "solve_on_device", "multi-GPU CG not built yet");
+    PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
+    k_cg_begin<<<1, 32, 0, st>>>(c->scal, tol);
+    PF_LAUNCHED(c);
+    unsigned* counter = c->red_counter + 1;
+    const int poll = 50;
+    for (int it = 0; it < maxiter; ++it) {
+      double* pnext = (it & 1) ? c->p0 : c->p1;
+      if (unit) k_cg_phaseA<true><<<c->cg_grid, CG_THREADS, 0, st>>>(a, it, counter);
+      else k_cg_phaseA<false><<<c->cg_grid, CG_THREADS, 0, st>>>(a, it, counter);
+      PF_LAUNCHED(c);
+      PF_TRY(comm_halo(c->comm, pnext, 1, 1, st, c->err));
+      PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_PQ, 1, 0, st, c->err));
+      if (unit) k_cg_phaseB<true><<<c->cg_grid, CG_THREADS, 0, st>>>(a, it, counter);
+      else k_cg_phaseB<false><<<c->cg_grid, CG_THREADS, 0, st>>>(a, it, counter);
+      PF_LAUNCHED(c);
+      PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
+      PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_RR_NEW, 2, 0, st, c->err));
+      k_cg_update<<<1, 32, 0, st>>>(c->scal, it, maxiter);
+      PF_LAUNCHED(c);
+      if ((it + 1) % poll == 0 && it + 1 < maxiter) {
+        // all ranks hold identical scalars, so they all leave at the same iteration
+        PF_CUDA(c, cudaMemcpyAsync(c->h_scal + S_DONE, c->scal + S_DONE, sizeof(double), cudaMemcpyDeviceToHost, st));
+        PF_CUDA(c, cudaStreamSynchronize(st));
+        if (c->h_scal[S_DONE] != 0.0) break;
+      }
+    }
+    k_cg_finish<<<1, 32, 0, st>>>(c->scal, maxiter);
+    PF_LAUNCHED(c);
   } else {
-    CgArgs a{};
-    a.s = s; a.b = c->b; a.x = c->x; a.r = c->r; a.p0 = c->p0; a.p1 = c->p1;
-    a.part = c->cg_part; a.scal = c->scal;
-    a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
-    cg_geometry(c, a);
-    if (is_unit(dx, dy)) PF_TRY(launch_cg<true>(c, a, st));
+    if (unit) PF_TRY(launch_cg<true>(c, a, st));
     else PF_TRY(launch_cg<false>(c, a, st));
   }
   if (e1) PF_CUDA(c, cudaEventRecord(e1, st));
-  if (is_unit(dx, dy)) k_resid<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
+  if (c->comm) PF_TRY(comm_halo(c->comm, c->x, 1, 1, st, c->err));
+  if (unit) k_resid<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
   else k_resid<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
   PF_LAUNCHED(c);
+  if (c->comm) PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_RES_SUMSQ, 2, 0, st, c->err));
   return PF_OK;
 }
 
@@ -348,8 +379,7 @@ int pf_prestep_reduce(pf_ctx* c, double out[3], void* stream) {
   PF_LAUNCHED(c);
   if (c->comm) {
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_UMAX, 2, 1, st, c->err));
-    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVC_SUMSQ, 1, 0, st, c->err));
-    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_UNAN, 2, 0, st, c->err));
+    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVC_SUMSQ, 7, 0, st, c->err));
   }
   PF_TRY(read_scalars(c, st, false));
   out[0] = nanmax(c->h_scal[S_UMAX], c->h_scal[S_UNAN]);
@@ -406,6 +436,10 @@ int pf_step(pf_ctx* c, const pf_step_params* P, pf_step_out* out, void* stream) 
     if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 1, st, c->err));
     k_post<<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->uo, c->vo, c->x, c->center, red);
     PF_LAUNCHED(c);
+  }
+  if (c->comm) {
+    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_UMAX, 2, 1, st, c->err));
+    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVC_SUMSQ, 7, 0, st, c->err));
   }
   PF_CUDA(c, cudaEventRecord(c->ev[3], st));
   PF_TRY(read_scalars(c, st, !P->projection_only));

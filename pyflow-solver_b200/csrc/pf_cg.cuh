@@ -461,4 +461,118 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent(CgArgs a) {
   }
 }
 
+
+// ---- split-phase variant (multi-GPU slabs) -----------------------------------
+// Same tile functions, one launch per phase, so that the host can put the
+// neighbour halo exchange and the scalar all-reduce (NCCL, same stream) between
+// the phases.  All per-iteration scalars live in the device scalar block; a
+// device-side `done` flag turns the remaining launches into no-ops once the
+// stop test fires, the host only polls it now and then.
+//   begin -> [A -> halo(p) + allreduce(p.q) -> B -> halo(r) + allreduce(r.r, r.z) -> update] x maxiter
+struct FoldScratch {
+  unsigned* counter;
+};
+
+// Last CTA to finish folds the per-CTA partials of `nv` values in fixed order.
+template <int NV>
+__device__ __forceinline__ void split_fold_store(const CgArgs& a, double (&vals)[NV], unsigned* counter,
+                                                 const int (&slots)[NV], double* sm) {
+  __shared__ bool is_last;
+  const int G = gridDim.x;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double t = block_sum(vals[k], sm);
+    if (threadIdx.x == 0) a.part[k * CG_MAX_GRID + blockIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == (unsigned)G - 1u);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double t = fold_partials(a.part + k * CG_MAX_GRID, G, sm);
+    if (threadIdx.x == 0) a.scal[slots[k]] = t;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+__global__ void k_cg_begin(double* scal, double tol) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double bb = scal[S_BB];
+  const double bnorm = sqrt(bb);
+  const double t0 = tol * bnorm;
+  const double atol = (t0 > 0.0) ? t0 : 0.0;
+  scal[S_ATOL] = atol;
+  scal[S_RR] = bb;
+  scal[S_RHO] = scal[S_BZ];
+  scal[S_RHO_PREV] = 0.0;
+  scal[S_ITERS] = 0.0;
+  double done = 0.0, info = -1.0;          // info < 0: still running (host turns it into maxiter)
+  if (bnorm == 0.0 || sqrt(bb) < atol) {   // "return b, 0" / converged before the first iteration
+    done = 1.0;
+    info = 0.0;
+  }
+  scal[S_DONE] = done;
+  scal[S_INFO] = info;
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(CG_THREADS, 2) k_cg_phaseA(CgArgs a, int it, unsigned* counter) {
+  __shared__ double sm[32];
+  if (ld_cg(a.scal + S_DONE) != 0.0) return;
+  const int G = gridDim.x, bid = blockIdx.x;
+  const bool first = (it == 0);
+  const double beta = first ? 0.0 : ld_cg(a.scal + S_RHO) / ld_cg(a.scal + S_RHO_PREV);
+  double* pcur = (it & 1) ? a.p1 : a.p0;
+  double* pnext = (it & 1) ? a.p0 : a.p1;
+  const int ktiles = (a.ntiles > bid) ? (a.ntiles - bid + G - 1) / G : 0;
+  double acc = 0.0;
+  for (int k = 0; k < ktiles; ++k) {
+    const WarpTile w = warp_tile(a, bid + k * G);
+    if (w.active) acc += phaseA_warp<UNIT, +1>(a, a.r, pcur, pnext, first, beta, w);
+  }
+  double vals[1] = {-acc};
+  const int slots[1] = {S_PQ};
+  split_fold_store<1>(a, vals, counter, slots, sm);
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(CG_THREADS, 2) k_cg_phaseB(CgArgs a, int it, unsigned* counter) {
+  __shared__ double sm[32];
+  if (ld_cg(a.scal + S_DONE) != 0.0) return;
+  const int G = gridDim.x, bid = blockIdx.x;
+  const double alpha = ld_cg(a.scal + S_RHO) / ld_cg(a.scal + S_PQ);
+  double* pnext = (it & 1) ? a.p0 : a.p1;
+  const int ktiles = (a.ntiles > bid) ? (a.ntiles - bid + G - 1) / G : 0;
+  double vals[2] = {0.0, 0.0};
+  for (int k = ktiles - 1; k >= 0; --k) {
+    const WarpTile w = warp_tile(a, bid + k * G);
+    if (w.active) phaseB_warp<UNIT, -1>(a, pnext, a.x, a.r, alpha, w, vals[0], vals[1]);
+  }
+  const int slots[2] = {S_RR_NEW, S_RZ_NEW};
+  split_fold_store<2>(a, vals, counter, slots, sm);
+}
+
+__global__ void k_cg_finish(double* scal, int maxiter) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (scal[S_INFO] < 0.0) scal[S_INFO] = (double)maxiter;     // loop exhausted: info = maxiter
+}
+
+__global__ void k_cg_update(double* scal, int it, int maxiter) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (scal[S_DONE] != 0.0) return;
+  scal[S_RHO_PREV] = scal[S_RHO];
+  scal[S_RHO] = scal[S_RZ_NEW];
+  const double rr = scal[S_RR_NEW];
+  scal[S_RR] = rr;
+  scal[S_ITERS] = (double)(it + 1);
+  // top-of-loop test of the NEXT iteration; none after the last one (scipy)
+  if (it + 1 < maxiter && sqrt(rr) < scal[S_ATOL]) {
+    scal[S_DONE] = 1.0;
+    scal[S_INFO] = 0.0;
+  }
+}
+
 }  // namespace pf

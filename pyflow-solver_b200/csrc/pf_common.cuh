@@ -36,15 +36,16 @@ __host__ __device__ __forceinline__ size_t cell(const Slab& s, int jl, int i) {
 
 // Slots of the device scalar block (doubles).
 enum Scalar {
-  S_UMAX = 0, S_VMAX, S_DIVC_SUMSQ,          // pre/post-step reductions
+  // [0,1] all-reduced with MAX, [2..8] with SUM at the end of a step (multi-GPU)
+  S_UMAX = 0, S_VMAX,
+  S_DIVC_SUMSQ, S_DIVA_SUMSQ, S_RU_SUMSQ, S_RV_SUMSQ, S_NONFINITE, S_UNAN, S_VNAN,
   S_DIVB_SUMSQ, S_RHS_SUM,                    // rhs pass 1
   S_BB, S_BZ,                                 // rhs pass 2: b.b, b.(M b)
-  S_RR, S_INFO, S_ITERS,                      // CG results
   S_RES_SUMSQ, S_X0,                          // ||b - A x||^2, x[0]
-  S_DIVA_SUMSQ,                               // divergence after correction
-  S_RU_SUMSQ, S_RV_SUMSQ, S_NONFINITE,        // post-step
-  S_PQ, S_RHO, S_RHO_PREV, S_DONE,            // split-phase CG (multi-GPU) state
-  S_UNAN, S_VNAN,                             // NaN counts (max is NaN-propagating in numpy)
+  S_RR, S_INFO, S_ITERS,                      // CG results
+  S_PQ,                                       // split-phase CG (multi-GPU) state
+  S_RR_NEW, S_RZ_NEW,
+  S_RHO, S_RHO_PREV, S_DONE, S_ATOL,
   S_COUNT = 32
 };
 

@@ -58,7 +58,11 @@ def attach(state) -> Binding:
     nx, ny = _dims(u)
     slab = f._slab if lazy else getattr(state, "_pf_slab", None)
     if slab is None or (slab.nx, slab.ny_local) != (nx, ny):
-        slab = DeviceSlab(nx, ny)
+        if getattr(state, "slab", None) is not None:      # row slab of a multi-GPU grid
+            from .distributed import make_slab
+            slab = make_slab(state)
+        else:
+            slab = DeviceSlab(nx, ny)
         if lazy:
             f._slab = slab
             f._touched.update(("u", "v", "p"))

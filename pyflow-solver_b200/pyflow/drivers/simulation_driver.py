@@ -42,6 +42,12 @@ class SimulationDriver:
         f = state.fields
         if isinstance(f, SyncedFields) and f._slab is not None:
             u_center = f._slab.centerline()
+            if f._slab.nranks > 1:                 # concatenate the slabs' column segments
+                import numpy as np
+                import torch.distributed as dist
+                parts = [None] * f._slab.nranks
+                dist.all_gather_object(parts, u_center)
+                u_center = np.concatenate(parts)
             n = u_center.shape[0]
         else:
             ui = interior_view(f["u"])

@@ -1,0 +1,34 @@
+"""Row-slab (multi-GPU) path: host logic on CPU with gloo (world_size 2 and 3),
+device parity on >= 2 GPUs with NCCL."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCRIPT = os.path.join(ROOT, "tests", "mp_slab_check.py")
+
+
+def _torchrun(nproc, mode, port, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), SCRIPT, mode]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_host_logic_gloo(world):
+    r = _torchrun(world, "gloo", 29611 + world)
+    assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_slab_parity_nccl():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    r = _torchrun(world, "nccl", 29641)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "FAIL" not in r.stdout and r.stdout.count("PARITY") == 3, r.stdout[-3000:] + r.stderr[-3000:]
