@@ -281,6 +281,8 @@ def run_gpu_arm(args, wl, rank, world):
                        "step, per-step scalar block + centre-line D2H, 3 fields D2H after the last step, all timed"}
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel (persistent CG) -------------------------
     peak, peak_src = measured_peak()
