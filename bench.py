@@ -280,6 +280,7 @@ def run_gpu_arm(args, wl, rank, world):
                "note": "SimulationDriver.run from host State arrays (pageable numpy): 3 fields H2D before the first "
                        "step, per-step scalar block + centre-line D2H, 3 fields D2H after the last step, all timed"}
 
+    peer_mode = bool(getattr(slab, "peer_mode", False))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,7 +319,10 @@ def run_gpu_arm(args, wl, rank, world):
         "metric": "MLUPS per projection step", "value": value, "unit": "MLUPS", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps,
         "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args.workload, wl, world),
+        "data": "synthetic", "config": dict(workload_config(args.workload, wl, world),
+                                            cg_comm=("single GPU" if world == 1 else
+                                                     "one persistent kernel per rank, halo rows + dot-product partials over NVLink peer memory"
+                                                     if peer_mode else "NCCL send/recv + all-reduce between phase kernels")),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "cg_iters_per_s": sum(cg_iters) / cg_s if cg_s > 0 else None,

@@ -140,6 +140,13 @@ int pf_op_pcg(pf_ctx* ctx, const double* b, double* x, double dx, double dy,
  * bytes (torch.distributed), every rank calls pf_comm_init.                  */
 int pf_comm_unique_id(void* out128);
 int pf_comm_init(pf_ctx* ctx, const void* id128, int rank, int nranks);
+/* Optional, after pf_comm_init: hand over the device workspaces of ALL ranks as
+ * mapped into this process (symmetric memory / CUDA IPC peer pointers, entry
+ * [rank] == own workspace, every rank's workspace zero-initialised by pf_create
+ * and equal slabs).  The CG solve then runs as ONE persistent kernel per rank
+ * that stores halo rows into the neighbours' HBM and exchanges the dot-product
+ * partials through peer mailboxes (NVLink), instead of NCCL calls per phase.  */
+int pf_comm_set_peers(pf_ctx* ctx, const void* const* peer_workspaces, int n);
 
 /* Introspection used by bench.py / tests. */
 int pf_device_info(pf_ctx* ctx, int* sm_count, int* cg_grid_blocks, int* cg_block_threads);

@@ -37,6 +37,11 @@ struct pf_ctx {
   bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
   dim3 sgrid;                      // grid of the simple kernels
   pf::Comm* comm = nullptr;        // multi-GPU slabs (null when nranks == 1)
+  char* ws_base = nullptr;         // device workspace (field k lives at k * field_stride)
+  size_t field_stride = 0;
+  size_t sync_off = 0;             // byte offset of the cross-GPU sync block inside the workspace
+  char* peer_ws[pf::CG_MAX_RANKS] = {nullptr};   // the other ranks' workspaces mapped into this process
+  bool peers = false;
   char err[512] = {0};
 };
 
@@ -73,7 +78,7 @@ int pitch_of(int64_t nx) { return (int)align_up((size_t)nx, PITCH_ALIGN); }
 size_t field_elems_of(int64_t nx, int64_t nyl) { return (size_t)(nyl + 2 * HALO) * (size_t)pitch_of(nx); }
 
 struct SmallLayout {
-  size_t red_part, red_counter, scal, cg_part, center, total;
+  size_t red_part, red_counter, scal, cg_part, sync, center, total;
 };
 SmallLayout small_layout(int64_t nyl) {
   SmallLayout L{};
@@ -82,6 +87,7 @@ SmallLayout small_layout(int64_t nyl) {
   L.red_counter = o; o = align_up(o + sizeof(unsigned) * 4, ALIGN);
   L.scal = o;        o = align_up(o + sizeof(double) * S_COUNT, ALIGN);
   L.cg_part = o;     o = align_up(o + sizeof(double) * 3 * CG_MAX_GRID, ALIGN);
+  L.sync = o;        o = align_up(o + 1024, ALIGN);
   L.center = o;      o = align_up(o + sizeof(double) * (size_t)nyl, ALIGN);
   L.total = o;
   return L;
@@ -117,6 +123,41 @@ void cg_geometry(const pf_ctx* c, CgArgs& a) {
   a.ntiles = a.nchunks * a.nbands;
 }
 
+// Sync block layout (1 KiB, zeroed at creation): u64 arrive, release, epoch, err, pad[4], flags[8];
+// then 64 doubles of mailbox ([2][8][4]) and 8 doubles of folded sums.
+void fill_sync(const pf_ctx* c, CgSync& y) {
+  auto u64 = [](char* p, int i) { return (unsigned long long*)p + i; };
+  char* mine = c->ws_base + c->sync_off;
+  y.arrive = u64(mine, 0);
+  y.release = u64(mine, 1);
+  y.epoch = u64(mine, 2);
+  y.err = u64(mine, 3);
+  y.flags = u64(mine, 8);
+  y.mbox = (double*)(mine + 128);
+  y.gsum = (double*)(mine + 128 + 64 * sizeof(double));
+  y.rank = comm_rank(c->comm);
+  y.nranks = comm_nranks(c->comm);
+  for (int q = 0; q < CG_MAX_RANKS; ++q) {
+    y.peer_flags[q] = nullptr;
+    y.peer_mbox[q] = nullptr;
+    if (q < y.nranks) {
+      char* theirs = c->peer_ws[q] + c->sync_off;
+      y.peer_flags[q] = u64(theirs, 8);
+      y.peer_mbox[q] = (double*)(theirs + 128);
+    }
+  }
+  const Slab& s = c->s;
+  auto field = [&](int q, int k, int jl) { return (double*)(c->peer_ws[q] + (size_t)k * c->field_stride) + cell(s, jl, 0); };
+  const bool has_below = y.rank > 0, has_above = y.rank < y.nranks - 1;
+  // field indices in the workspace: r = 6, p0 = 7, p1 = 8 (see pf_create)
+  y.below_r = has_below ? field(y.rank - 1, 6, s.nyl) : nullptr;
+  y.below_p0 = has_below ? field(y.rank - 1, 7, s.nyl) : nullptr;
+  y.below_p1 = has_below ? field(y.rank - 1, 8, s.nyl) : nullptr;
+  y.above_r = has_above ? field(y.rank + 1, 6, -1) : nullptr;
+  y.above_p0 = has_above ? field(y.rank + 1, 7, -1) : nullptr;
+  y.above_p1 = has_above ? field(y.rank + 1, 8, -1) : nullptr;
+}
+
 template <bool UNIT>
 int launch_cg(pf_ctx* c, CgArgs& a, cudaStream_t st) {
   void* args[] = {&a};
@@ -144,7 +185,16 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
   cg_geometry(c, a);
   const bool unit = is_unit(dx, dy);
-  if (c->comm) {
+  if (c->comm && c->peers) {
+    // ONE persistent kernel per rank: halo rows and partial sums travel over NVLink peer memory
+    PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
+    PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
+    fill_sync(c, a.y);
+    void* args[] = {&a};
+    const void* fn = unit ? (const void*)k_cg_persistent_multi<true> : (const void*)k_cg_persistent_multi<false>;
+    PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->cg_grid), dim3(CG_THREADS), args, 0, st));
+    c->launches++;
+  } else if (c->comm) {
     // split-phase CG: halo rows + scalar all-reduces between the phases (NCCL, same stream)
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
     PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
@@ -288,6 +338,8 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   char* base = (char*)workspace;
   double** fields[NFIELDS] = {&c->u, &c->v, &c->uo, &c->vo, &c->b, &c->x, &c->r, &c->p0, &c->p1};
   for (int k = 0; k < NFIELDS; ++k) *fields[k] = (double*)(base + (size_t)k * fb);
+  c->ws_base = base;
+  c->field_stride = fb;
   char* small = base + (size_t)NFIELDS * fb;
   const SmallLayout L = small_layout(ny_local);
   c->red_part = (double*)(small + L.red_part);
@@ -295,6 +347,7 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   c->scal = (double*)(small + L.scal);
   c->cg_part = (double*)(small + L.cg_part);
   c->center = (double*)(small + L.center);
+  c->sync_off = (size_t)NFIELDS * fb + L.sync;
   c->sgrid = simple_grid(c->s);
 #define PF_CREATE_CUDA(call)                                  \
   do {                                                        \
@@ -312,7 +365,10 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   int occ_u = 0, occ_g = 0;
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_cg_persistent<true>, CG_THREADS, 0));
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, k_cg_persistent<false>, CG_THREADS, 0));
-  const int occ = std::min(occ_u, occ_g);
+  int occ_mu = 0, occ_mg = 0;
+  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_cg_persistent_multi<true>, CG_THREADS, 0));
+  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mg, k_cg_persistent_multi<false>, CG_THREADS, 0));
+  const int occ = std::min(std::min(occ_u, occ_g), std::min(occ_mu, occ_mg));
   if (occ < 1) {
     pf_destroy(c);
     return PF_ERR_UNSUPPORTED;
@@ -454,6 +510,7 @@ int pf_step(pf_ctx* c, const pf_step_params* P, pf_step_out* out, void* stream) 
   out->rnorm = sqrt(h[S_RES_SUMSQ]);
   out->div_after_norm = sqrt(h[S_DIVA_SUMSQ]);
   out->p00 = h[S_X0] - h[S_X0];   /* p -= p.flat[0] (pressure_solver.py:148) */
+  if (h[S_INFO] == -2.0) return fail(c, PF_ERR_STATE, "pf_step", "cross-GPU exchange timed out inside the CG kernel");
   out->info = (int32_t)h[S_INFO];
   out->true_iters = (int32_t)h[S_ITERS];
   if (!P->projection_only) {
@@ -590,6 +647,22 @@ int pf_comm_init(pf_ctx* c, const void* id128, int rank, int nranks) {
   if (c->comm) return fail(c, PF_ERR_STATE, "pf_comm_init", "already initialised");
   if (nranks == 1) return PF_OK;
   return comm_create(&c->comm, id128, rank, nranks, c->s, c->err);
+}
+
+int pf_comm_set_peers(pf_ctx* c, const void* const* peer_workspaces, int n) {
+  if (!c || !peer_workspaces) return PF_ERR_ARG;
+  if (!c->comm) return fail(c, PF_ERR_STATE, "pf_comm_set_peers", "pf_comm_init first");
+  if (n != comm_nranks(c->comm) || n > CG_MAX_RANKS) return fail(c, PF_ERR_ARG, "pf_comm_set_peers", "rank count");
+  if (c->s.nyg % n != 0 || c->s.nyl != c->s.nyg / n)
+    return fail(c, PF_ERR_ARG, "pf_comm_set_peers", "peer mode needs equal slabs (ny_global % nranks == 0)");
+  for (int q = 0; q < n; ++q) {
+    if (!peer_workspaces[q]) return fail(c, PF_ERR_ARG, "pf_comm_set_peers", "null peer pointer");
+    c->peer_ws[q] = (char*)peer_workspaces[q];
+  }
+  if (c->peer_ws[comm_rank(c->comm)] != c->ws_base)
+    return fail(c, PF_ERR_ARG, "pf_comm_set_peers", "own entry must be the workspace given to pf_create");
+  c->peers = true;
+  return PF_OK;
 }
 
 }  // extern "C"

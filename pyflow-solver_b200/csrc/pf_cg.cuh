@@ -53,6 +53,28 @@ constexpr int STRIP = 64;     // columns per warp
 constexpr int CG_U = 4;       // rows fetched per batch (loads in flight per lane)
 constexpr int CG_MAX_GRID = 2048;
 
+constexpr int CG_MAX_RANKS = 8;
+
+// Cross-GPU exchange state of the persistent kernel (multi-GPU slabs).  The
+// `peer_*` pointers are the SAME buffers of the other ranks, mapped into this
+// process through symmetric memory (NVLink / NVSwitch peer access).
+struct CgSync {
+  unsigned long long* arrive;    // local: monotonic count of CTA arrivals
+  unsigned long long* release;   // local: last epoch released to the local CTAs
+  unsigned long long* flags;     // local, written by peers: epoch published by rank q
+  double* mbox;                  // local, written by peers: [2][CG_MAX_RANKS][4] partial sums
+  double* gsum;                  // local: [2][4] sums over all ranks for the local CTAs
+  unsigned long long* epoch;     // local: epoch counter persisted between launches
+  unsigned long long* err;       // local: != 0 after a spin-wait timeout
+  unsigned long long* peer_flags[CG_MAX_RANKS];
+  double* peer_mbox[CG_MAX_RANKS];
+  // neighbour halo rows (null when there is no neighbour): my bottom row goes to
+  // the upper halo of the slab below, my top row to the lower halo of the slab above
+  double* below_r; double* below_p0; double* below_p1;
+  double* above_r; double* above_p0; double* above_p1;
+  int rank, nranks;
+};
+
 struct CgArgs {
   Slab s;
   const double* b;
@@ -68,6 +90,7 @@ struct CgArgs {
   int maxiter;
   int wx, wy;         // warp arrangement inside a CTA tile, wx*wy == CG_WARPS
   int nchunks, nbands, ntiles;
+  CgSync y;           // only used by the multi-GPU persistent kernel
 };
 
 struct Row {
@@ -168,9 +191,29 @@ __device__ __forceinline__ March make_march(const WarpTile& w) {
 // ---- phase A -------------------------------------------------------------------
 // One batch of n (<= CG_U) consecutive visits starting at t0.  GEN rows evaluate
 // existence / ring / pin predicates; lean rows are strictly inside the band.
+// Mirror a freshly written slab-boundary row into the neighbour's halo row
+// (peer memory over NVLink).  Only ever reached from GEN rows.
+__device__ __forceinline__ void peer_row_store(const Slab& s, const Cols& c, int jl, double* below, double* above,
+                                               double va, double vb) {
+  double* dst = nullptr;
+  if (jl == 0 && below) dst = below;                 // -> upper halo row of the slab below
+  if (jl == s.nyl - 1 && above) {                    // -> lower halo row of the slab above
+    if (dst) {                                       // one-row slab: feeds both neighbours
+      if (c.vb) st2(dst + c.ia, va, vb);
+      else if (c.va) st1(dst + c.ia, va);
+    }
+    dst = above;
+  }
+  if (dst) {
+    if (c.vb) st2(dst + c.ia, va, vb);
+    else if (c.va) st1(dst + c.ia, va);
+  }
+}
+
 template <bool UNIT, bool XE, bool GEN, int DIR>
 __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, const March& m, const double* r,
-                                             const double* pold, double* pnew, bool first, double beta, int t0, int n,
+                                             const double* pold, double* pnew, double* peer_lo, double* peer_hi,
+                                             bool first, double beta, int t0, int n,
                                              Row& prev, Row& cur, double& acc) {
   const Slab& s = a.s;
   const uint64_t pol = policy_evict_first();
@@ -224,6 +267,7 @@ __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, con
         double* dst = pnew + cell(s, jl, c.ia);
         if (c.vb) st2(dst, nw.a, nw.b);
         else if (c.va) st1(dst, nw.a);
+        if (GEN) peer_row_store(s, c, jl, peer_lo, peer_hi, nw.a, nw.b);
       }
       if (!GEN || t >= 2) {
         const int jgc = jg - DIR;
@@ -249,7 +293,8 @@ __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, con
 
 template <bool UNIT, bool XE, int DIR>
 __device__ __forceinline__ double phaseA_strip(const CgArgs& a, const double* r, const double* pold, double* pnew,
-                                               bool first, double beta, const WarpTile& w) {
+                                               double* peer_lo, double* peer_hi, bool first, double beta,
+                                               const WarpTile& w) {
   const Cols c = strip_cols<XE>(a.s, w.i0);
   const March m = make_march<DIR>(w);
   const int nrows = m.TH + 2;
@@ -258,14 +303,14 @@ __device__ __forceinline__ double phaseA_strip(const CgArgs& a, const double* r,
   // generic head: t = 0, 1, 2 (halo row, first band row, and the row that
   // completes the first centre); lean body: t = 3 .. TH-1; generic tail.
   const int head = nrows < 3 ? nrows : 3;
-  phaseA_batch<UNIT, XE, true, DIR>(a, c, m, r, pold, pnew, first, beta, 0, head, prev, cur, acc);
+  phaseA_batch<UNIT, XE, true, DIR>(a, c, m, r, pold, pnew, peer_lo, peer_hi, first, beta, 0, head, prev, cur, acc);
   int t = head;
   const int lean_end = m.TH;                       // lean rows are t in [3, TH)
   for (; t + CG_U <= lean_end; t += CG_U)
-    phaseA_batch<UNIT, XE, false, DIR>(a, c, m, r, pold, pnew, first, beta, t, CG_U, prev, cur, acc);
+    phaseA_batch<UNIT, XE, false, DIR>(a, c, m, r, pold, pnew, peer_lo, peer_hi, first, beta, t, CG_U, prev, cur, acc);
   for (; t < nrows; t += CG_U) {
     const int n = (nrows - t) < CG_U ? (nrows - t) : CG_U;
-    phaseA_batch<UNIT, XE, true, DIR>(a, c, m, r, pold, pnew, first, beta, t, n, prev, cur, acc);
+    phaseA_batch<UNIT, XE, true, DIR>(a, c, m, r, pold, pnew, peer_lo, peer_hi, first, beta, t, n, prev, cur, acc);
   }
   return acc;
 }
@@ -273,8 +318,8 @@ __device__ __forceinline__ double phaseA_strip(const CgArgs& a, const double* r,
 // ---- phase B -------------------------------------------------------------------
 template <bool UNIT, bool XE, bool GEN, int DIR>
 __device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, const March& m, const double* p,
-                                             double* x, double* r, double alpha, int t0, int n, Row& prev, Row& cur,
-                                             double& acc_rr, double& acc_rz) {
+                                             double* x, double* r, double* peer_lo, double* peer_hi, double alpha,
+                                             int t0, int n, Row& prev, Row& cur, double& acc_rr, double& acc_rz) {
   const Slab& s = a.s;
   const uint64_t pol = policy_evict_first();
   double2 pr[CG_U], xx[CG_U], rr[CG_U];
@@ -327,6 +372,7 @@ __device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, con
           st1(x + o, xa);
           st1(r + o, ra);
         }
+        if (GEN) peer_row_store(s, c, jc, peer_lo, peer_hi, ra, rb);
         double da = a.invd, db = a.invd;
         if (GEN || XE) {
           const bool ring_row = GEN && ((jgc == 0) || (jgc == s.nyg - 1));
@@ -349,21 +395,22 @@ __device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, con
 }
 
 template <bool UNIT, bool XE, int DIR>
-__device__ __forceinline__ void phaseB_strip(const CgArgs& a, const double* p, double* x, double* r, double alpha,
-                                             const WarpTile& w, double& acc_rr, double& acc_rz) {
+__device__ __forceinline__ void phaseB_strip(const CgArgs& a, const double* p, double* x, double* r, double* peer_lo,
+                                             double* peer_hi, double alpha, const WarpTile& w, double& acc_rr,
+                                             double& acc_rz) {
   const Cols c = strip_cols<XE>(a.s, w.i0);
   const March m = make_march<DIR>(w);
   const int nrows = m.TH + 2;
   Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
   const int head = nrows < 3 ? nrows : 3;
-  phaseB_batch<UNIT, XE, true, DIR>(a, c, m, p, x, r, alpha, 0, head, prev, cur, acc_rr, acc_rz);
+  phaseB_batch<UNIT, XE, true, DIR>(a, c, m, p, x, r, peer_lo, peer_hi, alpha, 0, head, prev, cur, acc_rr, acc_rz);
   int t = head;
   const int lean_end = m.TH;
   for (; t + CG_U <= lean_end; t += CG_U)
-    phaseB_batch<UNIT, XE, false, DIR>(a, c, m, p, x, r, alpha, t, CG_U, prev, cur, acc_rr, acc_rz);
+    phaseB_batch<UNIT, XE, false, DIR>(a, c, m, p, x, r, peer_lo, peer_hi, alpha, t, CG_U, prev, cur, acc_rr, acc_rz);
   for (; t < nrows; t += CG_U) {
     const int n = (nrows - t) < CG_U ? (nrows - t) : CG_U;
-    phaseB_batch<UNIT, XE, true, DIR>(a, c, m, p, x, r, alpha, t, n, prev, cur, acc_rr, acc_rz);
+    phaseB_batch<UNIT, XE, true, DIR>(a, c, m, p, x, r, peer_lo, peer_hi, alpha, t, n, prev, cur, acc_rr, acc_rz);
   }
 }
 
@@ -371,17 +418,19 @@ __device__ __forceinline__ void phaseB_strip(const CgArgs& a, const double* p, d
 // inside the domain) take the XE instantiation.
 template <bool UNIT, int DIR>
 __device__ __forceinline__ double phaseA_warp(const CgArgs& a, const double* r, const double* pold, double* pnew,
-                                              bool first, double beta, const WarpTile& w) {
+                                              bool first, double beta, const WarpTile& w, double* peer_lo = nullptr,
+                                              double* peer_hi = nullptr) {
   const bool xe = (w.i0 == 0) || (w.i0 + STRIP >= a.s.nx);
-  if (xe) return phaseA_strip<UNIT, true, DIR>(a, r, pold, pnew, first, beta, w);
-  return phaseA_strip<UNIT, false, DIR>(a, r, pold, pnew, first, beta, w);
+  if (xe) return phaseA_strip<UNIT, true, DIR>(a, r, pold, pnew, peer_lo, peer_hi, first, beta, w);
+  return phaseA_strip<UNIT, false, DIR>(a, r, pold, pnew, peer_lo, peer_hi, first, beta, w);
 }
 template <bool UNIT, int DIR>
 __device__ __forceinline__ void phaseB_warp(const CgArgs& a, const double* p, double* x, double* r, double alpha,
-                                            const WarpTile& w, double& acc_rr, double& acc_rz) {
+                                            const WarpTile& w, double& acc_rr, double& acc_rz,
+                                            double* peer_lo = nullptr, double* peer_hi = nullptr) {
   const bool xe = (w.i0 == 0) || (w.i0 + STRIP >= a.s.nx);
-  if (xe) phaseB_strip<UNIT, true, DIR>(a, p, x, r, alpha, w, acc_rr, acc_rz);
-  else phaseB_strip<UNIT, false, DIR>(a, p, x, r, alpha, w, acc_rr, acc_rz);
+  if (xe) phaseB_strip<UNIT, true, DIR>(a, p, x, r, peer_lo, peer_hi, alpha, w, acc_rr, acc_rz);
+  else phaseB_strip<UNIT, false, DIR>(a, p, x, r, peer_lo, peer_hi, alpha, w, acc_rr, acc_rz);
 }
 
 // Fold per-CTA partials; identical in every CTA.
@@ -461,6 +510,172 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent(CgArgs a) {
   }
 }
 
+
+// ---- multi-GPU persistent variant: compute + collective in ONE kernel ----------
+// Every rank runs the same persistent kernel on its slab.  Slab-boundary rows of
+// p (phase A) and r (phase B) are stored straight into the neighbour's halo rows
+// through NVLink peer pointers while the sweep runs.  The grid barrier that ends
+// a phase doubles as the cross-GPU collective: the last CTA to arrive on a GPU
+// folds the per-CTA partials, publishes them into every rank's mailbox (peer
+// stores + system fence + epoch flag), waits for every rank's flag, sums the
+// mailbox in RANK ORDER (so all ranks get bit-identical scalars) and releases
+// the local CTAs.  One barrier per phase covers halo visibility and the
+// all-reduce; nothing returns to the host until the solve is over.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr long long CG_SPIN_LIMIT = 20000000000LL;   // ~10 s of SM clocks: never hang the GPU
+
+// Returns false if a spin-wait timed out somewhere (error flag raised).
+template <int NV>
+__device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long long e, double (&vals)[NV],
+                                              double (&out)[NV], double* sm) {
+  __shared__ int s_last;
+  const CgSync& y = a.y;
+  const int G = gridDim.x, tid = threadIdx.x, R = y.nranks;
+  const int par = (int)(e & 1ULL);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double t = block_sum(vals[k], sm);
+    if (tid == 0) a.part[k * CG_MAX_GRID + blockIdx.x] = t;
+  }
+  __threadfence_system();            // this thread's field / partial / peer-halo stores are visible system-wide
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(y.arrive, 1ULL) == e * (unsigned long long)G - 1ULL) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double loc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) loc[k] = fold_partials(a.part + k * CG_MAX_GRID, G, sm);
+    if (tid == 0) {
+      for (int q = 0; q < R; ++q)
+        for (int k = 0; k < NV; ++k) st_sys_f64(y.peer_mbox[q] + (par * CG_MAX_RANKS + y.rank) * 4 + k, loc[k]);
+      __threadfence_system();
+      for (int q = 0; q < R; ++q) st_release_sys(y.peer_flags[q] + y.rank, e);
+    }
+    if (tid < R) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys(y.flags + tid) < e) {
+        if (clock64() - t0 > CG_SPIN_LIMIT) {
+          atomicExch(y.err, 1ULL);
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 0; k < NV; ++k) {
+        double sum = 0.0;
+        for (int q = 0; q < R; ++q) sum += ld_sys_f64(y.mbox + (par * CG_MAX_RANKS + q) * 4 + k);
+        y.gsum[par * 4 + k] = sum;
+      }
+      __threadfence();
+      st_release_gpu(y.release, e);
+    }
+  }
+  if (tid == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(y.release) < e) {
+      if (clock64() - t0 > CG_SPIN_LIMIT) {
+        atomicExch(y.err, 1ULL);
+        break;
+      }
+    }
+    __threadfence();                 // acquire side: later loads (halo rows written by peers) see fresh data
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) out[k] = ld_cg(y.gsum + par * 4 + k);
+  return ld_acquire_gpu(y.err) == 0ULL;
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent_multi(CgArgs a) {
+  __shared__ double sm[32];
+  const int G = gridDim.x;
+  const int bid = blockIdx.x;
+  const CgSync& y = a.y;
+
+  const double bb = ld_cg(a.scal + S_BB);            // already all-reduced by the host sequence
+  const double bnorm = sqrt(bb);
+  const double t0 = a.tol * bnorm;
+  const double atol = (t0 > 0.0) ? t0 : 0.0;
+  int iters = 0;
+  int info = a.maxiter;
+  double rr = bb;
+  double rho = ld_cg(a.scal + S_BZ);
+  double rho_prev = 0.0;
+  double* pcur = a.p0;
+  double* pnext = a.p1;
+  unsigned long long e = *((volatile unsigned long long*)y.epoch);   // written only by the previous launch
+  bool ok = true;
+
+  if (bnorm == 0.0) {
+    info = 0;
+  } else {
+    const int ktiles = (a.ntiles > bid) ? (a.ntiles - bid + G - 1) / G : 0;
+    for (int it = 0; it < a.maxiter; ++it) {
+      if (sqrt(rr) < atol) {
+        info = 0;
+        break;
+      }
+      const bool first = (it == 0);
+      const double beta = first ? 0.0 : rho / rho_prev;
+      double* plo = (pnext == a.p0) ? y.below_p0 : y.below_p1;
+      double* phi = (pnext == a.p0) ? y.above_p0 : y.above_p1;
+      double va[1] = {0.0}, oa[1];
+      for (int k = 0; k < ktiles; ++k) {
+        const WarpTile w = warp_tile(a, bid + k * G);
+        if (w.active) va[0] += phaseA_warp<UNIT, +1>(a, a.r, pcur, pnext, first, beta, w, plo, phi);
+      }
+      va[0] = -va[0];
+      ok = grid_exchange<1>(a, ++e, va, oa, sm);
+      if (!ok) break;
+      const double alpha = rho / oa[0];
+      double vb[2] = {0.0, 0.0}, ob[2];
+      for (int k = ktiles - 1; k >= 0; --k) {
+        const WarpTile w = warp_tile(a, bid + k * G);
+        if (w.active) phaseB_warp<UNIT, -1>(a, pnext, a.x, a.r, alpha, w, vb[0], vb[1], y.below_r, y.above_r);
+      }
+      ok = grid_exchange<2>(a, ++e, vb, ob, sm);
+      if (!ok) break;
+      rr = ob[0];
+      rho_prev = rho;
+      rho = ob[1];
+      double* tmp = pcur; pcur = pnext; pnext = tmp;
+      ++iters;
+    }
+  }
+  if (bid == 0 && threadIdx.x == 0) {
+    a.scal[S_INFO] = ok ? (double)info : -2.0;
+    a.scal[S_ITERS] = (double)iters;
+    a.scal[S_RR] = rr;
+    *y.epoch = e;                    // every rank executed the same number of exchanges
+  }
+}
 
 // ---- split-phase variant (multi-GPU slabs) -----------------------------------
 // Same tile functions, one launch per phase, so that the host can put the

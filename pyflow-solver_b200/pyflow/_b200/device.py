@@ -39,7 +39,7 @@ class DeviceSlab:
     """GPU context for an ``nx x ny_local`` slab of a ``nx x ny_global`` grid."""
 
     def __init__(self, nx: int, ny_local: int, ny_global: int | None = None, row_offset: int = 0,
-                 device: int | None = None):
+                 device: int | None = None, allocator=None):
         torch = _require_cuda()
         self._lib = _lib.load()
         self.nx, self.ny_local = int(nx), int(ny_local)
@@ -50,7 +50,11 @@ class DeviceSlab:
         nbytes = int(self._lib.pf_workspace_bytes(self.nx, self.ny_local))
         if nbytes == 0:
             raise ValueError(f"unsupported grid {nx}x{ny_local} (need nx >= 2, ny >= 2)")
-        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+        if allocator is not None:           # e.g. torch symmetric memory for peer-mapped slabs
+            self.workspace = allocator(nbytes, self.device)
+        else:
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+        self.workspace_bytes = nbytes
         base = self.workspace.data_ptr()
         if base % 256:
             raise RuntimeError("torch returned a workspace that is not 256-byte aligned")
@@ -63,6 +67,7 @@ class DeviceSlab:
         self._center = np.empty(self.ny_local, dtype=np.float64)
         self.nranks = 1
         self.rank = 0
+        self.peer_mode = False
 
     @staticmethod
     def _destroy(lib, ctx):
@@ -92,6 +97,11 @@ class DeviceSlab:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _lib.check(self._lib.pf_comm_init(self.ctx, buf, rank, nranks), self.ctx, "pf_comm_init")
         self.rank, self.nranks = rank, nranks
+
+    def set_peers(self, peer_ptrs):
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        _lib.check(self._lib.pf_comm_set_peers(self.ctx, arr, len(peer_ptrs)), self.ctx, "pf_comm_set_peers")
+        self.peer_mode = True
 
     @staticmethod
     def make_unique_id() -> bytes:

@@ -62,14 +62,51 @@ def gather_field(state: State, name: str):
     return out
 
 
+def _symmetric_allocator(nbytes: int, device: int):
+    """Workspace in torch symmetric memory: every rank allocates the same size
+    and the buffers are peer-mapped across the GPUs of the box (NVLink)."""
+    import torch
+    import torch.distributed._symmetric_memory as symm
+    return symm.empty(nbytes, dtype=torch.uint8, device=torch.device(f"cuda:{device}"))
+
+
 def make_slab(state: State) -> DeviceSlab:
-    """DeviceSlab for a slab state, with the NCCL communicator initialised."""
+    """DeviceSlab for a slab state with the NCCL communicator initialised and,
+    when the slabs are equal, the peer-memory CG path enabled
+    (PYFLOW_B200_CG_COMM=nccl forces NCCL calls per phase instead)."""
+    import os
+    import warnings
+
     import torch
     import torch.distributed as dist
     spec = state.slab
-    slab = DeviceSlab(state.nx, state.ny, spec["ny_global"], spec["row_offset"], device=torch.cuda.current_device())
-    if spec["world"] > 1:
-        box = [DeviceSlab.make_unique_id() if spec["rank"] == 0 else None]
+    world, rank = spec["world"], spec["rank"]
+    want_peer = (world > 1 and spec["ny_global"] % world == 0
+                 and os.environ.get("PYFLOW_B200_CG_COMM", "peer").lower() != "nccl")
+    slab = None
+    if want_peer:
+        try:
+            slab = DeviceSlab(state.nx, state.ny, spec["ny_global"], spec["row_offset"],
+                              device=torch.cuda.current_device(), allocator=_symmetric_allocator)
+        except Exception as exc:   # symmetric memory unavailable: stay on the GPU, use NCCL per phase
+            warnings.warn(f"symmetric memory unavailable ({exc!r}); CG falls back to NCCL halo/all-reduce per phase")
+            want_peer = False
+    if slab is None:
+        slab = DeviceSlab(state.nx, state.ny, spec["ny_global"], spec["row_offset"], device=torch.cuda.current_device())
+    if world > 1:
+        box = [DeviceSlab.make_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        slab.init_comm(box[0], spec["rank"], spec["world"])
+        slab.init_comm(box[0], rank, world)
+        # every rank must agree on the mode
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(want_peer))
+        if all(flags):
+            import torch.distributed._symmetric_memory as symm
+            hdl = symm.rendezvous(slab.workspace, dist.group.WORLD)
+            torch.cuda.synchronize()
+            dist.barrier()                     # all workspaces are zero-initialised before anyone writes remotely
+            slab.set_peers(list(hdl.buffer_ptrs))
+            slab._symm_handle = hdl
+        elif want_peer:
+            raise RuntimeError("ranks disagree on the CG communication mode")
     return slab

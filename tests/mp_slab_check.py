@@ -57,7 +57,10 @@ def main():
         dist.destroy_process_group()
         return 0
 
-    # ---- nccl: slab run vs oracle ------------------------------------------------
+    # ---- nccl / peer: slab run vs oracle -----------------------------------------
+    # MODE nccl : CG with NCCL halo + all-reduce calls per phase
+    # MODE peer : CG as one persistent kernel per rank over NVLink peer memory
+    os.environ["PYFLOW_B200_CG_COMM"] = "nccl" if mode == "nccl" else "peer"
     import pyflow_oracle as orc
     from pyflow.residuals.manager import ResidualManager
     from pyflow.solvers.solver import step
@@ -69,7 +72,9 @@ def main():
         dict(nx=96, ny=80, Re=100.0, advection_scheme="quick", lin_maxiter=10000, steps=4),   # converged regime
         dict(nx=128, ny=128, Re=100.0, advection_scheme="quick", lin_maxiter=300, steps=5),   # truncated early
         dict(nx=70, ny=61, Re=400.0, advection_scheme="upwind", lin_maxiter=100, steps=4, lx=2.0, ly=1.0),  # ragged, non-unit, truncated early
+        dict(nx=200, ny=48 * world, Re=1000.0, advection_scheme="quick", lin_maxiter=300, steps=4),           # equal slabs, several strips
     ]
+    used_peer = []
     for case in cases:
         steps = case.pop("steps")
         cfg = SimpleNamespace(lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
@@ -81,6 +86,7 @@ def main():
             _, res, diag = step(cfg, st, tr, it)
             dts.append(diag["dt"])
             iters.append(st.meta["cg_true_iterations"])
+        used_peer.append(bool(st.fields._slab.peer_mode))
         fields = {k: gather_field(st, k) for k in ("u", "v", "p")}
         if rank == 0:
             ost, od = orc.run(cfg, steps)
@@ -88,7 +94,7 @@ def main():
             same_dt = dts == [d["dt"] for d in od]
             dit = max(abs(a - d["true_iterations"]) for a, d in zip(iters, od))
             good = same_dt and all(e < 1e-8 for e in errs.values()) and dit <= 2
-            print(f"PARITY world={world} {cfg.nx}x{cfg.ny} errs={errs} dt_equal={same_dt} iters={iters} max_iter_diff={dit} "
+            print(f"PARITY mode={mode} peer_kernel={used_peer[-1]} world={world} {cfg.nx}x{cfg.ny} errs={errs} dt_equal={same_dt} iters={iters} max_iter_diff={dit} "
                   f"{'OK' if good else 'FAIL'}", flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda")

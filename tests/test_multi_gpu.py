@@ -23,12 +23,15 @@ def test_slab_host_logic_gloo(world):
 
 
 @pytest.mark.gpu
-def test_slab_parity_nccl():
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+def test_slab_parity(mode):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
-    r = _torchrun(world, "nccl", 29641)
+    r = _torchrun(world, mode, 29641 + (mode == "peer"))
     print(r.stdout[-3000:])
-    assert r.returncode == 0 and "FAIL" not in r.stdout and r.stdout.count("PARITY") == 3, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "FAIL" not in r.stdout and r.stdout.count("PARITY") == 4, r.stdout[-3000:] + r.stderr[-3000:]
+    if mode == "peer":
+        assert "peer_kernel=True" in r.stdout      # the equal-slab cases really ran the NVLink kernel
