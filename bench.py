@@ -281,6 +281,9 @@ def run_gpu_arm(args, wl, rank, world):
                        "step, per-step scalar block + centre-line D2H, 3 fields D2H after the last step, all timed"}
 
     peer_mode = bool(getattr(slab, "peer_mode", False))
+    if os.environ.get("PF_BENCH_VERBOSE"):
+        print(f"[rank {rank}] cg_ms mean {statistics.mean(cg_ms):.3f} min {min(cg_ms):.3f} max {max(cg_ms):.3f} "
+              f"step_ms mean {statistics.mean(step_ms):.3f}", file=sys.stderr, flush=True)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -150,6 +150,12 @@ int pf_comm_set_peers(pf_ctx* ctx, const void* const* peer_workspaces, int n);
 
 /* Introspection used by bench.py / tests. */
 int pf_device_info(pf_ctx* ctx, int* sm_count, int* cg_grid_blocks, int* cg_block_threads);
+/* tuning / debugging switches (key: "cg_multi_single" = run the multi-GPU
+ * persistent kernel, own barrier included, on a single-GPU context) */
+int pf_set_option(pf_ctx* ctx, const char* key, int value);
+/* debugging: copy n doubles of the CG partial-sum scratch (barrier timeline when
+ * option "cg_sync_opt" bit 4 is set) */
+int pf_debug_read_partials(pf_ctx* ctx, double* out, int offset, int n);
 /* number of kernels of this library launched on the context so far */
 int pf_launch_count(pf_ctx* ctx, int64_t* out);
 

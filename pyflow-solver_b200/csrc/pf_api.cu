@@ -8,7 +8,7 @@
 
 #include <algorithm>
 
-#include "pf_cg.cuh"
+#include "pf_cg_dyn.cuh"
 #include "pf_comm.h"
 #include "pf_kernels.cuh"
 
@@ -42,6 +42,9 @@ struct pf_ctx {
   size_t sync_off = 0;             // byte offset of the cross-GPU sync block inside the workspace
   char* peer_ws[pf::CG_MAX_RANKS] = {nullptr};   // the other ranks' workspaces mapped into this process
   bool peers = false;
+  int opt_multi_single = 0;
+  int opt_sync = 0;
+  int opt_kernel = 1;              // 1: static-tile persistent kernels (production); 0: k_cg_dyn (experimental)        // debug/tuning: run the multi-GPU persistent kernel with one rank
   char err[512] = {0};
 };
 
@@ -86,7 +89,7 @@ SmallLayout small_layout(int64_t nyl) {
   L.red_part = o;    o = align_up(o + sizeof(double) * MAX_RED_VALS * MAX_RED_BLOCKS, ALIGN);
   L.red_counter = o; o = align_up(o + sizeof(unsigned) * 4, ALIGN);
   L.scal = o;        o = align_up(o + sizeof(double) * S_COUNT, ALIGN);
-  L.cg_part = o;     o = align_up(o + sizeof(double) * 3 * CG_MAX_GRID, ALIGN);
+  L.cg_part = o;     o = align_up(o + sizeof(double) * PF_PART_DOUBLES, ALIGN);
   L.sync = o;        o = align_up(o + 1024, ALIGN);
   L.center = o;      o = align_up(o + sizeof(double) * (size_t)nyl, ALIGN);
   L.total = o;
@@ -132,16 +135,19 @@ void fill_sync(const pf_ctx* c, CgSync& y) {
   y.release = u64(mine, 1);
   y.epoch = u64(mine, 2);
   y.err = u64(mine, 3);
+  y.tickets = u64(mine, 4);
+  y.ticket_base = u64(mine, 5);
   y.flags = u64(mine, 8);
   y.mbox = (double*)(mine + 128);
   y.gsum = (double*)(mine + 128 + 64 * sizeof(double));
-  y.rank = comm_rank(c->comm);
-  y.nranks = comm_nranks(c->comm);
+  y.opt = c->opt_sync;
+  y.rank = c->comm ? comm_rank(c->comm) : 0;
+  y.nranks = c->comm ? comm_nranks(c->comm) : 1;
   for (int q = 0; q < CG_MAX_RANKS; ++q) {
     y.peer_flags[q] = nullptr;
     y.peer_mbox[q] = nullptr;
     if (q < y.nranks) {
-      char* theirs = c->peer_ws[q] + c->sync_off;
+      char* theirs = (c->comm ? c->peer_ws[q] : c->ws_base) + c->sync_off;
       y.peer_flags[q] = u64(theirs, 8);
       y.peer_mbox[q] = (double*)(theirs + 128);
     }
@@ -156,6 +162,43 @@ void fill_sync(const pf_ctx* c, CgSync& y) {
   y.above_r = has_above ? field(y.rank + 1, 6, -1) : nullptr;
   y.above_p0 = has_above ? field(y.rank + 1, 7, -1) : nullptr;
   y.above_p1 = has_above ? field(y.rank + 1, 8, -1) : nullptr;
+}
+
+int reset_trace(pf_ctx* c, cudaStream_t st) {
+  if (!(c->opt_sync & 4)) return PF_OK;   // barrier timeline: min slots start at ~0ULL, the rest at 0
+  PF_CUDA(c, cudaMemsetAsync(c->cg_part + PF_TRACE_OFFSET, 0, 64 * sizeof(double), st));
+  for (int k = 0; k < 8; ++k)
+    PF_CUDA(c, cudaMemsetAsync(c->cg_part + PF_TRACE_OFFSET + 8 * k, 0xff, sizeof(double), st));
+  return PF_OK;
+}
+
+// Tiles of the dynamically scheduled kernel: ~4 per CTA, >= 8 rows, <= CG_MAX_TILES.
+void dyn_geometry(const pf_ctx* c, CgArgs& a) {
+  const Slab& s = c->s;
+  const int nstrips = (s.nx + STRIP - 1) / STRIP;
+  int wx = 1;
+  while (wx * 2 <= CG_WARPS && wx * 2 <= nstrips) wx *= 2;
+  a.wx = wx;
+  a.wy = CG_WARPS / wx;
+  a.nchunks = (nstrips + wx - 1) / wx;
+  const int G = c->cg_grid;
+  const int rows_min = 8 * a.wy;
+  int nb = (4 * G + a.nchunks - 1) / a.nchunks;
+  nb = std::min(nb, std::max(1, s.nyl / rows_min));
+  nb = std::min(nb, std::max(1, CG_MAX_TILES / a.nchunks));
+  a.nbands = std::max(1, nb);
+  a.ntiles = a.nchunks * a.nbands;
+}
+
+int launch_dyn(pf_ctx* c, CgArgs& a, bool unit, cudaStream_t st) {
+  dyn_geometry(c, a);
+  fill_sync(c, a.y);
+  PF_TRY(reset_trace(c, st));
+  void* args[] = {&a};
+  const void* fn = unit ? (const void*)k_cg_dyn<true> : (const void*)k_cg_dyn<false>;
+  PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->cg_grid), dim3(CG_THREADS), args, 0, st));
+  c->launches++;
+  return PF_OK;
 }
 
 template <bool UNIT>
@@ -185,11 +228,20 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
   cg_geometry(c, a);
   const bool unit = is_unit(dx, dy);
-  if (c->comm && c->peers) {
-    // ONE persistent kernel per rank: halo rows and partial sums travel over NVLink peer memory
+  if (c->opt_kernel == 0 && (!c->comm || c->peers)) {
+    // production: ONE dynamically scheduled persistent kernel (per rank); with several ranks the halo
+    // rows and the dot-product partials travel over NVLink peer memory inside the kernel
+    if (c->comm) {
+      PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
+      PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
+    }
+    PF_TRY(launch_dyn(c, a, unit, st));
+  } else if (c->comm && c->peers) {
+    // static-tile persistent kernel per rank over NVLink peer memory (cross-check)
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
     PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
     fill_sync(c, a.y);
+    PF_TRY(reset_trace(c, st));
     void* args[] = {&a};
     const void* fn = unit ? (const void*)k_cg_persistent_multi<true> : (const void*)k_cg_persistent_multi<false>;
     PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->cg_grid), dim3(CG_THREADS), args, 0, st));
@@ -225,6 +277,13 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     }
     k_cg_finish<<<1, 32, 0, st>>>(c->scal, maxiter);
     PF_LAUNCHED(c);
+  } else if (c->opt_multi_single) {
+    fill_sync(c, a.y);
+    PF_TRY(reset_trace(c, st));
+    void* args[] = {&a};
+    const void* fn = unit ? (const void*)k_cg_persistent_multi<true> : (const void*)k_cg_persistent_multi<false>;
+    PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->cg_grid), dim3(CG_THREADS), args, 0, st));
+    c->launches++;
   } else {
     if (unit) PF_TRY(launch_cg<true>(c, a, st));
     else PF_TRY(launch_cg<false>(c, a, st));
@@ -365,10 +424,13 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   int occ_u = 0, occ_g = 0;
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_cg_persistent<true>, CG_THREADS, 0));
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, k_cg_persistent<false>, CG_THREADS, 0));
+  int occ_du = 0, occ_dg = 0;
+  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_du, k_cg_dyn<true>, CG_THREADS, 0));
+  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dg, k_cg_dyn<false>, CG_THREADS, 0));
   int occ_mu = 0, occ_mg = 0;
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_cg_persistent_multi<true>, CG_THREADS, 0));
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mg, k_cg_persistent_multi<false>, CG_THREADS, 0));
-  const int occ = std::min(std::min(occ_u, occ_g), std::min(occ_mu, occ_mg));
+  const int occ = std::min(std::min(std::min(occ_u, occ_g), std::min(occ_mu, occ_mg)), std::min(occ_du, occ_dg));
   if (occ < 1) {
     pf_destroy(c);
     return PF_ERR_UNSUPPORTED;
@@ -396,6 +458,20 @@ int pf_device_info(pf_ctx* c, int* sm_count, int* cg_grid_blocks, int* cg_block_
   if (sm_count) *sm_count = c->sm_count;
   if (cg_grid_blocks) *cg_grid_blocks = c->cg_grid;
   if (cg_block_threads) *cg_block_threads = CG_THREADS;
+  return PF_OK;
+}
+
+int pf_set_option(pf_ctx* c, const char* key, int value) {
+  if (!c || !key) return PF_ERR_ARG;
+  if (strcmp(key, "cg_multi_single") == 0) { c->opt_multi_single = value; return PF_OK; }
+  if (strcmp(key, "cg_sync_opt") == 0) { c->opt_sync = value; return PF_OK; }
+  if (strcmp(key, "cg_kernel") == 0) { c->opt_kernel = value; return PF_OK; }
+  return fail(c, PF_ERR_ARG, "pf_set_option", key);
+}
+
+int pf_debug_read_partials(pf_ctx* c, double* out, int offset, int n) {
+  if (!c || !out || offset < 0 || n < 0 || offset + n > PF_PART_DOUBLES) return PF_ERR_ARG;
+  PF_CUDA(c, cudaMemcpy(out, c->cg_part + offset, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
   return PF_OK;
 }
 

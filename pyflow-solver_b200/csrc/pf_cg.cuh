@@ -54,6 +54,8 @@ constexpr int CG_U = 4;       // rows fetched per batch (loads in flight per lan
 constexpr int CG_MAX_GRID = 2048;
 
 constexpr int CG_MAX_RANKS = 8;
+constexpr int PF_TRACE_OFFSET = 2 * 8192;   // doubles: behind the per-tile partials (2 x CG_MAX_TILES)
+constexpr int PF_PART_DOUBLES = 2 * 8192 + 64;
 
 // Cross-GPU exchange state of the persistent kernel (multi-GPU slabs).  The
 // `peer_*` pointers are the SAME buffers of the other ranks, mapped into this
@@ -66,6 +68,8 @@ struct CgSync {
   double* gsum;                  // local: [2][4] sums over all ranks for the local CTAs
   unsigned long long* epoch;     // local: epoch counter persisted between launches
   unsigned long long* err;       // local: != 0 after a spin-wait timeout
+  unsigned long long* tickets;   // local: monotonic tile-ticket counter (k_cg_dyn)
+  unsigned long long* ticket_base;  // local: first ticket of the next launch (persisted)
   unsigned long long* peer_flags[CG_MAX_RANKS];
   double* peer_mbox[CG_MAX_RANKS];
   // neighbour halo rows (null when there is no neighbour): my bottom row goes to
@@ -73,6 +77,7 @@ struct CgSync {
   double* below_r; double* below_p0; double* below_p1;
   double* above_r; double* above_p0; double* above_p1;
   int rank, nranks;
+  int opt;                       // experiment bits (pf_set_option "cg_sync_opt")
 };
 
 struct CgArgs {
@@ -126,13 +131,29 @@ struct Cols {
   bool ring_a, ring_b, ring_h;
 };
 
-template <bool XE>
+// Strip kinds (template XE): 0 = strictly inside the domain in x (no column
+// predicates at all); 1 = WALL strip whose 64 columns all exist (only lane 0's
+// west face / lane 31's east face and the two ring columns are special: two
+// selects per row); 2 = partially outside the domain (every predicate).
+constexpr int X_IN = 0, X_WALL = 1, X_PART = 2;
+
+template <int XE>
 __device__ __forceinline__ Cols strip_cols(const Slab& s, int i0) {
   const int lane = threadIdx.x & 31;
   Cols c;
   c.ia = i0 + 2 * lane;
   c.ih = (lane == 0) ? i0 - 1 : i0 + STRIP;
-  if (XE) {
+  if (XE == X_WALL) {         // all 64 columns exist; nx >= 64 so a lane's two columns are never both walls
+    const int ib = c.ia + 1;
+    c.va = c.vb = true;
+    c.vh = (lane == 0 || lane == 31) && c.ih >= 0 && c.ih < s.nx;
+    c.hw_a = c.ia > 0;
+    c.he_a = true;
+    c.he_b = ib < s.nx - 1;
+    c.ring_a = (c.ia == 0);
+    c.ring_b = (ib == s.nx - 1);
+    c.ring_h = (c.ih == 0) || (c.ih == s.nx - 1);
+  } else if (XE == X_PART) {
     const int ib = c.ia + 1;
     c.va = c.ia < s.nx;
     c.vb = ib < s.nx;
@@ -152,10 +173,16 @@ __device__ __forceinline__ Cols strip_cols(const Slab& s, int i0) {
   return c;
 }
 
+__device__ __forceinline__ int strip_kind(const Slab& s, int i0) {
+  if (i0 + STRIP > s.nx) return X_PART;                 // some of the 64 columns do not exist
+  if (i0 == 0 || i0 + STRIP == s.nx) return X_WALL;
+  return X_IN;
+}
+
 // laplacian_coherent (NOT negated) at the two columns of the centre row.
 // GEN: evaluate the Neumann predicates of this row / strip; otherwise every
 // neighbour exists.
-template <bool UNIT, bool XE, bool GEN>
+template <bool UNIT, int XE, bool GEN>
 __device__ __forceinline__ void lap_pair(const CgArgs& a, const Cols& c, const Row& south, const Row& cur,
                                          const Row& north, bool hs, bool hn, double& la, double& lb) {
   const int lane = threadIdx.x & 31;
@@ -163,9 +190,15 @@ __device__ __forceinline__ void lap_pair(const CgArgs& a, const Cols& c, const R
   double e_b = __shfl_down_sync(0xffffffffu, cur.a, 1);
   if (lane == 0) w_a = cur.h;
   if (lane == 31) e_b = cur.h;
-  if (XE || GEN) {
+  if (XE == X_PART || (GEN && XE != X_IN)) {
     la = -neg_lap<UNIT>(cur.a, w_a, cur.b, south.a, north.a, c.hw_a, c.he_a, hs, hn, a.dx, a.dy);
     lb = -neg_lap<UNIT>(cur.b, cur.a, e_b, south.b, north.b, true, c.he_b, hs, hn, a.dx, a.dy);
+  } else if (GEN) {           // interior strip, boundary row: only the row predicates
+    la = -neg_lap<UNIT>(cur.a, w_a, cur.b, south.a, north.a, true, true, hs, hn, a.dx, a.dy);
+    lb = -neg_lap<UNIT>(cur.b, cur.a, e_b, south.b, north.b, true, true, hs, hn, a.dx, a.dy);
+  } else if (XE == X_WALL) {  // wall strip, interior row: only lane 0's west / lane 31's east face
+    la = -neg_lap<UNIT>(cur.a, w_a, cur.b, south.a, north.a, c.hw_a, true, true, true, a.dx, a.dy);
+    lb = -neg_lap<UNIT>(cur.b, cur.a, e_b, south.b, north.b, true, c.he_b, true, true, a.dx, a.dy);
   } else {
     la = -neg_lap<UNIT>(cur.a, w_a, cur.b, south.a, north.a, true, true, true, true, a.dx, a.dy);
     lb = -neg_lap<UNIT>(cur.b, cur.a, e_b, south.b, north.b, true, true, true, true, a.dx, a.dy);
@@ -210,7 +243,7 @@ __device__ __forceinline__ void peer_row_store(const Slab& s, const Cols& c, int
   }
 }
 
-template <bool UNIT, bool XE, bool GEN, int DIR>
+template <bool UNIT, int XE, bool GEN, int DIR>
 __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, const March& m, const double* r,
                                              const double* pold, double* pnew, double* peer_lo, double* peer_hi,
                                              bool first, double beta, int t0, int n,
@@ -248,7 +281,7 @@ __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, con
       const int jl = m.jl0 + DIR * t;
       const int jg = s.row0 + jl;
       double da = a.invd, db = a.invd, dh = a.invd;
-      if (GEN || XE) {
+      if (GEN || XE != X_IN) {
         const bool ring_row = GEN && ((jg == 0) || (jg == s.nyg - 1));
         da = (ring_row || c.ring_a) ? 1.0 : a.invd;
         db = (ring_row || c.ring_b) ? 1.0 : a.invd;
@@ -277,7 +310,7 @@ __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, con
         else lap_pair<UNIT, XE, GEN>(a, c, nw, cur, prev, hs, hn, la, lb);
         if (GEN && jgc == 0 && c.ia == 0) la = -cur.a;      // pinned row: q[0] = p[0]
         // acc holds sum p*lap = -(p.q)
-        if (XE) {
+        if (XE == X_PART) {
           if (c.va) acc += cur.a * la;
           if (c.vb) acc += cur.b * lb;
         } else {
@@ -291,7 +324,7 @@ __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, con
   }
 }
 
-template <bool UNIT, bool XE, int DIR>
+template <bool UNIT, int XE, int DIR>
 __device__ __forceinline__ double phaseA_strip(const CgArgs& a, const double* r, const double* pold, double* pnew,
                                                double* peer_lo, double* peer_hi, bool first, double beta,
                                                const WarpTile& w) {
@@ -316,7 +349,7 @@ __device__ __forceinline__ double phaseA_strip(const CgArgs& a, const double* r,
 }
 
 // ---- phase B -------------------------------------------------------------------
-template <bool UNIT, bool XE, bool GEN, int DIR>
+template <bool UNIT, int XE, bool GEN, int DIR>
 __device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, const March& m, const double* p,
                                              double* x, double* r, double* peer_lo, double* peer_hi, double alpha,
                                              int t0, int n, Row& prev, Row& cur, double& acc_rr, double& acc_rz) {
@@ -374,16 +407,16 @@ __device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, con
         }
         if (GEN) peer_row_store(s, c, jc, peer_lo, peer_hi, ra, rb);
         double da = a.invd, db = a.invd;
-        if (GEN || XE) {
+        if (GEN || XE != X_IN) {
           const bool ring_row = GEN && ((jgc == 0) || (jgc == s.nyg - 1));
           da = (ring_row || c.ring_a) ? 1.0 : a.invd;
           db = (ring_row || c.ring_b) ? 1.0 : a.invd;
         }
-        if (!XE || c.va) {
+        if (XE != X_PART || c.va) {
           acc_rr += ra * ra;
           acc_rz += ra * (da * ra);
         }
-        if (!XE || c.vb) {
+        if (XE != X_PART || c.vb) {
           acc_rr += rb * rb;
           acc_rz += rb * (db * rb);
         }
@@ -394,7 +427,7 @@ __device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, con
   }
 }
 
-template <bool UNIT, bool XE, int DIR>
+template <bool UNIT, int XE, int DIR>
 __device__ __forceinline__ void phaseB_strip(const CgArgs& a, const double* p, double* x, double* r, double* peer_lo,
                                              double* peer_hi, double alpha, const WarpTile& w, double& acc_rr,
                                              double& acc_rz) {
@@ -420,17 +453,19 @@ template <bool UNIT, int DIR>
 __device__ __forceinline__ double phaseA_warp(const CgArgs& a, const double* r, const double* pold, double* pnew,
                                               bool first, double beta, const WarpTile& w, double* peer_lo = nullptr,
                                               double* peer_hi = nullptr) {
-  const bool xe = (w.i0 == 0) || (w.i0 + STRIP >= a.s.nx);
-  if (xe) return phaseA_strip<UNIT, true, DIR>(a, r, pold, pnew, peer_lo, peer_hi, first, beta, w);
-  return phaseA_strip<UNIT, false, DIR>(a, r, pold, pnew, peer_lo, peer_hi, first, beta, w);
+  const int xk = strip_kind(a.s, w.i0);
+  if (xk == X_PART) return phaseA_strip<UNIT, X_PART, DIR>(a, r, pold, pnew, peer_lo, peer_hi, first, beta, w);
+  if (xk == X_WALL) return phaseA_strip<UNIT, X_WALL, DIR>(a, r, pold, pnew, peer_lo, peer_hi, first, beta, w);
+  return phaseA_strip<UNIT, X_IN, DIR>(a, r, pold, pnew, peer_lo, peer_hi, first, beta, w);
 }
 template <bool UNIT, int DIR>
 __device__ __forceinline__ void phaseB_warp(const CgArgs& a, const double* p, double* x, double* r, double alpha,
                                             const WarpTile& w, double& acc_rr, double& acc_rz,
                                             double* peer_lo = nullptr, double* peer_hi = nullptr) {
-  const bool xe = (w.i0 == 0) || (w.i0 + STRIP >= a.s.nx);
-  if (xe) phaseB_strip<UNIT, true, DIR>(a, p, x, r, peer_lo, peer_hi, alpha, w, acc_rr, acc_rz);
-  else phaseB_strip<UNIT, false, DIR>(a, p, x, r, peer_lo, peer_hi, alpha, w, acc_rr, acc_rz);
+  const int xk = strip_kind(a.s, w.i0);
+  if (xk == X_PART) phaseB_strip<UNIT, X_PART, DIR>(a, p, x, r, peer_lo, peer_hi, alpha, w, acc_rr, acc_rz);
+  else if (xk == X_WALL) phaseB_strip<UNIT, X_WALL, DIR>(a, p, x, r, peer_lo, peer_hi, alpha, w, acc_rr, acc_rz);
+  else phaseB_strip<UNIT, X_IN, DIR>(a, p, x, r, peer_lo, peer_hi, alpha, w, acc_rr, acc_rz);
 }
 
 // Fold per-CTA partials; identical in every CTA.
@@ -548,11 +583,40 @@ __device__ __forceinline__ double ld_sys_f64(const double* p) {
 
 constexpr long long CG_SPIN_LIMIT = 20000000000LL;   // ~10 s of SM clocks: never hang the GPU
 
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Optional timeline of a few barriers (opt bit 4): 8 u64 per traced barrier in the
+// unused upper half of the first partials array.
+__device__ __forceinline__ unsigned long long* trace_slot(const CgArgs& a, unsigned long long e0, unsigned long long e) {
+  if (!(a.y.opt & 4)) return nullptr;
+  const unsigned long long k = e - e0;              // barrier index within this launch (1-based)
+  if (k < 401 || k >= 409) return nullptr;
+  return (unsigned long long*)(a.part + PF_TRACE_OFFSET) + (k - 401) * 8;
+}
+
 // Returns false if a spin-wait timed out somewhere (error flag raised).
+// Cost discipline: exactly one fence per CTA on each side of the barrier (thread 0),
+// relaxed polling loads, results handed to the other threads through shared memory.
 template <int NV>
 __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long long e, double (&vals)[NV],
-                                              double (&out)[NV], double* sm) {
+                                              double (&out)[NV], double* sm, unsigned long long e0 = 0) {
+  unsigned long long* tr = trace_slot(a, e0, e);
   __shared__ int s_last;
+  __shared__ double s_out[NV + 1];
   const CgSync& y = a.y;
   const int G = gridDim.x, tid = threadIdx.x, R = y.nranks;
   const int par = (int)(e & 1ULL);
@@ -561,55 +625,86 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
     const double t = block_sum(vals[k], sm);
     if (tid == 0) a.part[k * CG_MAX_GRID + blockIdx.x] = t;
   }
-  __threadfence_system();            // this thread's field / partial / peer-halo stores are visible system-wide
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(y.arrive, 1ULL) == e * (unsigned long long)G - 1ULL) ? 1 : 0;
+  __syncthreads();                   // CTA-scope order: every thread's stores happen-before thread 0's fence
+  if (tid == 0) {
+    // cumulative release: publishes the CTA's field / partial / peer-halo stores
+    if (R > 1 && !(y.opt & 1)) __threadfence_system(); else __threadfence();
+    if (tr) {
+      const unsigned long long t = gtime();
+      atomicMin(tr + 0, t);
+      atomicMax(tr + 1, t);
+      const unsigned long long kb = e - e0 - 401;          // per-CTA stamps of the first two traced barriers
+      if (kb < 2) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        ((unsigned long long*)(a.part + 4096))[kb * 512 + blockIdx.x] = (t << 10) | (unsigned long long)(smid & 1023u);
+      }
+    }
+    s_last = (atomicAdd(y.arrive, 1ULL) == e * (unsigned long long)G - 1ULL) ? 1 : 0;
+  }
   __syncthreads();
   if (s_last) {
-    __threadfence();
+    if (tid == 0) __threadfence();
+    __syncthreads();
     double loc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) loc[k] = fold_partials(a.part + k * CG_MAX_GRID, G, sm);
     if (tid == 0) {
-      for (int q = 0; q < R; ++q)
-        for (int k = 0; k < NV; ++k) st_sys_f64(y.peer_mbox[q] + (par * CG_MAX_RANKS + y.rank) * 4 + k, loc[k]);
-      __threadfence_system();
-      for (int q = 0; q < R; ++q) st_release_sys(y.peer_flags[q] + y.rank, e);
-    }
-    if (tid < R) {
-      const long long t0 = clock64();
-      while (ld_acquire_sys(y.flags + tid) < e) {
-        if (clock64() - t0 > CG_SPIN_LIMIT) {
-          atomicExch(y.err, 1ULL);
-          break;
-        }
+      if (tr) tr[2] = gtime();
+      if (R > 1) {
+        for (int q = 0; q < R; ++q)
+          for (int k = 0; k < NV; ++k) st_sys_f64(y.peer_mbox[q] + (par * CG_MAX_RANKS + y.rank) * 4 + k, loc[k]);
+        if (!(y.opt & 2)) __threadfence_system();
+        for (int q = 0; q < R; ++q) st_release_sys(y.peer_flags[q] + y.rank, e);
       }
+      if (tr) tr[3] = gtime();
     }
-    __syncthreads();
+    if (R > 1) {
+      if (tid < R) {
+        const long long t0 = clock64();
+        while (ld_relaxed_sys_u64(y.flags + tid) < e) {
+          if (clock64() - t0 > CG_SPIN_LIMIT) {
+            atomicExch(y.err, 1ULL);
+            break;
+          }
+        }
+        __threadfence_system();      // acquire: the peers' mailbox and halo-row stores are visible now
+      }
+      __syncthreads();
+    }
     if (tid == 0) {
+      if (tr) tr[4] = gtime();
       for (int k = 0; k < NV; ++k) {
-        double sum = 0.0;
-        for (int q = 0; q < R; ++q) sum += ld_sys_f64(y.mbox + (par * CG_MAX_RANKS + q) * 4 + k);
+        double sum = loc[k];
+        if (R > 1) {                 // rank order, identical on every GPU
+          sum = 0.0;
+          for (int q = 0; q < R; ++q) sum += ld_sys_f64(y.mbox + (par * CG_MAX_RANKS + q) * 4 + k);
+        }
         y.gsum[par * 4 + k] = sum;
       }
       __threadfence();
       st_release_gpu(y.release, e);
+      if (tr) tr[5] = gtime();
     }
   }
   if (tid == 0) {
     const long long t0 = clock64();
-    while (ld_acquire_gpu(y.release) < e) {
+    while (ld_relaxed_u64(y.release) < e) {
       if (clock64() - t0 > CG_SPIN_LIMIT) {
         atomicExch(y.err, 1ULL);
         break;
       }
     }
-    __threadfence();                 // acquire side: later loads (halo rows written by peers) see fresh data
+    __threadfence();                 // acquire side: later loads (incl. halo rows written by peers) see fresh data
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s_out[k] = ld_cg(y.gsum + par * 4 + k);
+    s_out[NV] = (ld_relaxed_u64(y.err) == 0ULL) ? 1.0 : 0.0;
+    if (tr && blockIdx.x == 0) tr[6] = gtime();
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV; ++k) out[k] = ld_cg(y.gsum + par * 4 + k);
-  return ld_acquire_gpu(y.err) == 0ULL;
+  for (int k = 0; k < NV; ++k) out[k] = s_out[k];
+  return s_out[NV] != 0.0;
 }
 
 template <bool UNIT>
@@ -631,6 +726,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent_multi(CgArgs a)
   double* pcur = a.p0;
   double* pnext = a.p1;
   unsigned long long e = *((volatile unsigned long long*)y.epoch);   // written only by the previous launch
+  const unsigned long long e0 = e;
   bool ok = true;
 
   if (bnorm == 0.0) {
@@ -652,7 +748,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent_multi(CgArgs a)
         if (w.active) va[0] += phaseA_warp<UNIT, +1>(a, a.r, pcur, pnext, first, beta, w, plo, phi);
       }
       va[0] = -va[0];
-      ok = grid_exchange<1>(a, ++e, va, oa, sm);
+      ok = grid_exchange<1>(a, ++e, va, oa, sm, e0);
       if (!ok) break;
       const double alpha = rho / oa[0];
       double vb[2] = {0.0, 0.0}, ob[2];
@@ -660,7 +756,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent_multi(CgArgs a)
         const WarpTile w = warp_tile(a, bid + k * G);
         if (w.active) phaseB_warp<UNIT, -1>(a, pnext, a.x, a.r, alpha, w, vb[0], vb[1], y.below_r, y.above_r);
       }
-      ok = grid_exchange<2>(a, ++e, vb, ob, sm);
+      ok = grid_exchange<2>(a, ++e, vb, ob, sm, e0);
       if (!ok) break;
       rr = ob[0];
       rho_prev = rho;

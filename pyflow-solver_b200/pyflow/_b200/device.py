@@ -65,6 +65,10 @@ class DeviceSlab:
         self.ctx = ctx
         self._finalizer = weakref.finalize(self, DeviceSlab._destroy, self._lib, ctx)
         self._center = np.empty(self.ny_local, dtype=np.float64)
+        import os
+        for item in filter(None, os.environ.get("PYFLOW_B200_OPTIONS", "").split(",")):   # e.g. "cg_multi_single=1"
+            k, _, v = item.partition("=")
+            self.set_option(k.strip(), int(v or 1))
         self.nranks = 1
         self.rank = 0
         self.peer_mode = False
@@ -87,6 +91,9 @@ class DeviceSlab:
         sm, grid, thr = C.c_int(), C.c_int(), C.c_int()
         _lib.check(self._lib.pf_device_info(self.ctx, C.byref(sm), C.byref(grid), C.byref(thr)), self.ctx)
         return {"sm_count": sm.value, "cg_grid_blocks": grid.value, "cg_block_threads": thr.value}
+
+    def set_option(self, key: str, value: int):
+        _lib.check(self._lib.pf_set_option(self.ctx, key.encode(), int(value)), self.ctx, "pf_set_option")
 
     def launch_count(self) -> int:
         n = C.c_int64()

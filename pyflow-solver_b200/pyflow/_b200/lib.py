@@ -21,7 +21,7 @@ EXPORTS = (
     "pf_upload", "pf_download", "pf_prestep_reduce", "pf_step", "pf_centerline",
     "pf_op_gradient_coherent", "pf_op_divergence_coherent", "pf_op_laplacian_coherent",
     "pf_op_divergence_central", "pf_op_advect", "pf_op_pcg",
-    "pf_comm_unique_id", "pf_comm_init", "pf_comm_set_peers", "pf_device_info", "pf_launch_count",
+    "pf_comm_unique_id", "pf_comm_init", "pf_comm_set_peers", "pf_device_info", "pf_launch_count", "pf_set_option", "pf_debug_read_partials",
 )
 
 
@@ -80,6 +80,8 @@ def _declare(lib):
     lib.pf_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.pf_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pf_comm_set_peers.argtypes = [vp, C.POINTER(vp), C.c_int]
+    lib.pf_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.pf_debug_read_partials.argtypes = [vp, dp, C.c_int, C.c_int]
     lib.pf_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     for name in EXPORTS:
         getattr(lib, name)       # AttributeError here == header/library drift
