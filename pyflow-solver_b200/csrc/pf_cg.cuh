@@ -608,27 +608,86 @@ __device__ __forceinline__ unsigned long long* trace_slot(const CgArgs& a, unsig
   return (unsigned long long*)(a.part + PF_TRACE_OFFSET) + (k - 401) * 8;
 }
 
-// Returns false if a spin-wait timed out somewhere (error flag raised).
-// Cost discipline: exactly one fence per CTA on each side of the barrier (thread 0),
-// relaxed polling loads, results handed to the other threads through shared memory.
+// 32-byte packets {epoch, v0, v1, v2}: written with ONE 256-bit store and polled with
+// ONE 256-bit load (LDG/STG.256 on sm_100), so a reader that sees the new epoch sees
+// the values of the same store -- no fence and no second round trip between flag
+// and payload.  Packets are 32-byte aligned (one L2 sector).
+struct Packet {
+  unsigned long long epoch;
+  double v[3];
+};
+__device__ __forceinline__ Packet ld_packet_gpu(const void* p) {
+  Packet k;
+  unsigned long long b0, b1, b2, b3;
+  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(p) : "memory");
+  k.epoch = b0;
+  k.v[0] = __longlong_as_double((long long)b1);
+  k.v[1] = __longlong_as_double((long long)b2);
+  k.v[2] = __longlong_as_double((long long)b3);
+  return k;
+}
+__device__ __forceinline__ Packet ld_packet_sys(const void* p) {
+  Packet k;
+  unsigned long long b0, b1, b2, b3;
+  asm volatile("ld.relaxed.sys.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(p) : "memory");
+  k.epoch = b0;
+  k.v[0] = __longlong_as_double((long long)b1);
+  k.v[1] = __longlong_as_double((long long)b2);
+  k.v[2] = __longlong_as_double((long long)b3);
+  return k;
+}
+__device__ __forceinline__ void st_packet_gpu(void* p, unsigned long long e, double v0, double v1, double v2) {
+  asm volatile("st.relaxed.gpu.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(e), "l"(__double_as_longlong(v0)),
+               "l"(__double_as_longlong(v1)), "l"(__double_as_longlong(v2)) : "memory");
+}
+__device__ __forceinline__ void st_packet_sys(void* p, unsigned long long e, double v0, double v1, double v2) {
+  asm volatile("st.relaxed.sys.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(e), "l"(__double_as_longlong(v0)),
+               "l"(__double_as_longlong(v1)), "l"(__double_as_longlong(v2)) : "memory");
+}
+
+// Sum of NV doubles per thread over the block with ONE pair of barriers; every thread
+// returns the totals.  sm holds >= 32*NV doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sm[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = 0.0;
+    for (int q = 0; q < nw; ++q) t += sm[k * 32 + q];
+    v[k] = t;
+  }
+}
+
+// Ends a phase on 1..8 GPUs.  Returns false if a spin-wait timed out (error flag).
+// Chain after the last CTA arrives: fold the per-CTA partials (one pass, one block
+// reduction) -> (R > 1: one system fence, one 32-byte packet per peer, wait for the
+// peers' packets, sum in RANK order) -> one 32-byte release packet -> the other CTAs
+// see epoch and sums in the same load -> one acquire fence per CTA.
 template <int NV>
 __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long long e, double (&vals)[NV],
                                               double (&out)[NV], double* sm, unsigned long long e0 = 0) {
+  static_assert(NV <= 3, "packet carries three values");
   unsigned long long* tr = trace_slot(a, e0, e);
   __shared__ int s_last;
-  __shared__ double s_out[NV + 1];
+  __shared__ double s_out[4];
   const CgSync& y = a.y;
   const int G = gridDim.x, tid = threadIdx.x, R = y.nranks;
   const int par = (int)(e & 1ULL);
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const double t = block_sum(vals[k], sm);
-    if (tid == 0) a.part[k * CG_MAX_GRID + blockIdx.x] = t;
-  }
-  __syncthreads();                   // CTA-scope order: every thread's stores happen-before thread 0's fence
+  block_sum_n<NV>(vals, sm);         // its barriers also order every thread's phase stores before thread 0's fence
   if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) a.part[k * CG_MAX_GRID + blockIdx.x] = vals[k];
     // cumulative release: publishes the CTA's field / partial / peer-halo stores
-    if (R > 1 && !(y.opt & 1)) __threadfence_system(); else __threadfence();
+    if (R > 1) __threadfence_system(); else __threadfence();
     if (tr) {
       const unsigned long long t = gtime();
       atomicMin(tr + 0, t);
@@ -644,72 +703,75 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
   }
   __syncthreads();
   if (s_last) {
-    if (tid == 0) __threadfence();
+    if (tid == 0) __threadfence();   // acquire the other CTAs' partials (read below with ld.cg)
     __syncthreads();
-    double loc[NV];
+    double loc[3] = {0.0, 0.0, 0.0};
+    for (int q = tid; q < G; q += CG_THREADS) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) loc[k] = fold_partials(a.part + k * CG_MAX_GRID, G, sm);
-    if (tid == 0) {
-      if (tr) tr[2] = gtime();
-      if (R > 1) {
-        for (int q = 0; q < R; ++q)
-          for (int k = 0; k < NV; ++k) st_sys_f64(y.peer_mbox[q] + (par * CG_MAX_RANKS + y.rank) * 4 + k, loc[k]);
-        if (!(y.opt & 2)) __threadfence_system();
-        for (int q = 0; q < R; ++q) st_release_sys(y.peer_flags[q] + y.rank, e);
-      }
-      if (tr) tr[3] = gtime();
+      for (int k = 0; k < NV; ++k) loc[k] += ld_cg(a.part + k * CG_MAX_GRID + q);
     }
+    block_sum_n<3>(loc, sm);
+    if (tid == 0 && tr) tr[2] = gtime();
     if (R > 1) {
+      char* slot_of_me = (char*)0 + (size_t)(par * CG_MAX_RANKS + y.rank) * sizeof(Packet);
+      if (tid == 0) {
+        __threadfence_system();      // the halo rows pushed by the other CTAs of this GPU go out before the packet
+        for (int q = 0; q < R; ++q) st_packet_sys((char*)y.peer_mbox[q] + (size_t)slot_of_me, e, loc[0], loc[1], loc[2]);
+        if (tr) tr[3] = gtime();
+      }
+      __shared__ double s_peer[CG_MAX_RANKS][3];
       if (tid < R) {
         const long long t0 = clock64();
-        while (ld_relaxed_sys_u64(y.flags + tid) < e) {
+        Packet k;
+        const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * sizeof(Packet);
+        while ((k = ld_packet_sys(src)).epoch != e) {
           if (clock64() - t0 > CG_SPIN_LIMIT) {
             atomicExch(y.err, 1ULL);
             break;
           }
         }
-        __threadfence_system();      // acquire: the peers' mailbox and halo-row stores are visible now
+        __threadfence_system();      // acquire: the peers' halo-row stores are visible now
+        s_peer[tid][0] = k.v[0]; s_peer[tid][1] = k.v[1]; s_peer[tid][2] = k.v[2];
       }
       __syncthreads();
+      if (tid == 0) {
+        for (int k = 0; k < 3; ++k) {   // rank order, identical on every GPU
+          double sum = 0.0;
+          for (int q = 0; q < R; ++q) sum += s_peer[q][k];
+          loc[k] = sum;
+        }
+      }
     }
     if (tid == 0) {
       if (tr) tr[4] = gtime();
-      for (int k = 0; k < NV; ++k) {
-        double sum = loc[k];
-        if (R > 1) {                 // rank order, identical on every GPU
-          sum = 0.0;
-          for (int q = 0; q < R; ++q) sum += ld_sys_f64(y.mbox + (par * CG_MAX_RANKS + q) * 4 + k);
-        }
-        y.gsum[par * 4 + k] = sum;
-      }
-      __threadfence();
-      st_release_gpu(y.release, e);
+      __threadfence();               // (R > 1) peers' halo rows, made visible to this thread, go before the release
+      st_packet_gpu(y.gsum, e, loc[0], loc[1], loc[2]);
       if (tr) tr[5] = gtime();
     }
   }
   if (tid == 0) {
     const long long t0 = clock64();
-    while (ld_relaxed_u64(y.release) < e) {
+    Packet k;
+    while ((k = ld_packet_gpu(y.gsum)).epoch != e) {
       if (clock64() - t0 > CG_SPIN_LIMIT) {
         atomicExch(y.err, 1ULL);
         break;
       }
     }
     __threadfence();                 // acquire side: later loads (incl. halo rows written by peers) see fresh data
-#pragma unroll
-    for (int k = 0; k < NV; ++k) s_out[k] = ld_cg(y.gsum + par * 4 + k);
-    s_out[NV] = (ld_relaxed_u64(y.err) == 0ULL) ? 1.0 : 0.0;
+    s_out[0] = k.v[0]; s_out[1] = k.v[1]; s_out[2] = k.v[2];
+    s_out[3] = (ld_relaxed_u64(y.err) == 0ULL) ? 1.0 : 0.0;
     if (tr && blockIdx.x == 0) tr[6] = gtime();
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < NV; ++k) out[k] = s_out[k];
-  return s_out[NV] != 0.0;
+  return s_out[3] != 0.0;
 }
 
 template <bool UNIT>
 __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent_multi(CgArgs a) {
-  __shared__ double sm[32];
+  __shared__ double sm[3 * 32];
   const int G = gridDim.x;
   const int bid = blockIdx.x;
   const CgSync& y = a.y;

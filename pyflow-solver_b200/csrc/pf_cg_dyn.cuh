@@ -262,27 +262,6 @@ __device__ __forceinline__ void dynB_strip(const CgArgs& a, const double* p, dou
 }
 
 // ---- barrier + all-reduce over tile partials ---------------------------------------
-// Sum of NV doubles per thread over the block with ONE pair of barriers.
-template <int NV>
-__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* sm /* >= 32*NV */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) sm[k * 32 + warp] = v[k];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double t = 0.0;
-    for (int q = 0; q < nw; ++q) t += sm[k * 32 + q];
-    v[k] = t;
-  }
-}
-
 // Ends a phase: every CTA arrives; the last one folds the per-TILE partials in tile
 // order, trades the sums with the other ranks (R > 1) and releases everybody.
 template <int NV>
