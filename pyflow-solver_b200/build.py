@@ -55,8 +55,8 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build_native(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    if out is None and not force and not needs_build():
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
     inc, lib = _nccl_dirs()
@@ -71,16 +71,18 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     ]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("PF_NVCC_FLAGS", "").split()      # tuning experiments, e.g. -DPF_CG_UA=6
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-o", LIB_PATH, "-L", lib, "-l:libnccl.so.2", "-Xlinker", f"-rpath={lib}"]
+    cmd += ["-o", out or LIB_PATH, "-L", lib, "-l:libnccl.so.2", "-Xlinker", f"-rpath={lib}"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libpyflow_b200.so")
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":
-    path = build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    out = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")), None)
+    path = build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out)
     print(path)

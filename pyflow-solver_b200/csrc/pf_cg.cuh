@@ -50,7 +50,18 @@ namespace cg = cooperative_groups;
 constexpr int CG_THREADS = 256;
 constexpr int CG_WARPS = CG_THREADS / 32;
 constexpr int STRIP = 64;     // columns per warp
-constexpr int CG_U = 4;       // rows fetched per batch (loads in flight per lane)
+#ifndef PF_CG_UA
+#define PF_CG_UA 6
+#endif
+#ifndef PF_CG_UB
+#define PF_CG_UB 4
+#endif
+#ifndef PF_CG_MINB
+#define PF_CG_MINB 2
+#endif
+constexpr int CG_U = 4;        // rows per batch of the experimental k_cg_dyn
+constexpr int CG_UA = PF_CG_UA;   // rows fetched per batch in phase A (loads in flight per lane: 2 arrays)
+constexpr int CG_UB = PF_CG_UB;   // ... in phase B (3 arrays)
 constexpr int CG_MAX_GRID = 2048;
 
 constexpr int CG_MAX_RANKS = 8;
@@ -222,7 +233,7 @@ __device__ __forceinline__ March make_march(const WarpTile& w) {
 }
 
 // ---- phase A -------------------------------------------------------------------
-// One batch of n (<= CG_U) consecutive visits starting at t0.  GEN rows evaluate
+// One batch of n (<= CG_UA) consecutive visits starting at t0.  GEN rows evaluate
 // existence / ring / pin predicates; lean rows are strictly inside the band.
 // Mirror a freshly written slab-boundary row into the neighbour's halo row
 // (peer memory over NVLink).  Only ever reached from GEN rows.
@@ -250,10 +261,10 @@ __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, con
                                              Row& prev, Row& cur, double& acc) {
   const Slab& s = a.s;
   const uint64_t pol = policy_evict_first();
-  double2 rr[CG_U], pp[CG_U];
-  double rh[CG_U], ph[CG_U];
+  double2 rr[CG_UA], pp[CG_UA];
+  double rh[CG_UA], ph[CG_UA];
 #pragma unroll
-  for (int u = 0; u < CG_U; ++u) {
+  for (int u = 0; u < CG_UA; ++u) {
     const int jl = m.jl0 + DIR * (t0 + u);
     const int jg = s.row0 + jl;
     rr[u] = make_double2(0.0, 0.0);
@@ -275,7 +286,7 @@ __device__ __forceinline__ void phaseA_batch(const CgArgs& a, const Cols& c, con
     }
   }
 #pragma unroll
-  for (int u = 0; u < CG_U; ++u) {
+  for (int u = 0; u < CG_UA; ++u) {
     if (!GEN || u < n) {               // warp-uniform
       const int t = t0 + u;
       const int jl = m.jl0 + DIR * t;
@@ -339,10 +350,10 @@ __device__ __forceinline__ double phaseA_strip(const CgArgs& a, const double* r,
   phaseA_batch<UNIT, XE, true, DIR>(a, c, m, r, pold, pnew, peer_lo, peer_hi, first, beta, 0, head, prev, cur, acc);
   int t = head;
   const int lean_end = m.TH;                       // lean rows are t in [3, TH)
-  for (; t + CG_U <= lean_end; t += CG_U)
-    phaseA_batch<UNIT, XE, false, DIR>(a, c, m, r, pold, pnew, peer_lo, peer_hi, first, beta, t, CG_U, prev, cur, acc);
-  for (; t < nrows; t += CG_U) {
-    const int n = (nrows - t) < CG_U ? (nrows - t) : CG_U;
+  for (; t + CG_UA <= lean_end; t += CG_UA)
+    phaseA_batch<UNIT, XE, false, DIR>(a, c, m, r, pold, pnew, peer_lo, peer_hi, first, beta, t, CG_UA, prev, cur, acc);
+  for (; t < nrows; t += CG_UA) {
+    const int n = (nrows - t) < CG_UA ? (nrows - t) : CG_UA;
     phaseA_batch<UNIT, XE, true, DIR>(a, c, m, r, pold, pnew, peer_lo, peer_hi, first, beta, t, n, prev, cur, acc);
   }
   return acc;
@@ -355,10 +366,10 @@ __device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, con
                                              int t0, int n, Row& prev, Row& cur, double& acc_rr, double& acc_rz) {
   const Slab& s = a.s;
   const uint64_t pol = policy_evict_first();
-  double2 pr[CG_U], xx[CG_U], rr[CG_U];
-  double ph[CG_U];
+  double2 pr[CG_UB], xx[CG_UB], rr[CG_UB];
+  double ph[CG_UB];
 #pragma unroll
-  for (int u = 0; u < CG_U; ++u) {
+  for (int u = 0; u < CG_UB; ++u) {
     const int t = t0 + u;
     const int jl = m.jl0 + DIR * t;
     const int jg = s.row0 + jl;
@@ -379,7 +390,7 @@ __device__ __forceinline__ void phaseB_batch(const CgArgs& a, const Cols& c, con
     }
   }
 #pragma unroll
-  for (int u = 0; u < CG_U; ++u) {
+  for (int u = 0; u < CG_UB; ++u) {
     if (!GEN || u < n) {
       const int t = t0 + u;
       const int jl = m.jl0 + DIR * t;
@@ -439,10 +450,10 @@ __device__ __forceinline__ void phaseB_strip(const CgArgs& a, const double* p, d
   phaseB_batch<UNIT, XE, true, DIR>(a, c, m, p, x, r, peer_lo, peer_hi, alpha, 0, head, prev, cur, acc_rr, acc_rz);
   int t = head;
   const int lean_end = m.TH;
-  for (; t + CG_U <= lean_end; t += CG_U)
-    phaseB_batch<UNIT, XE, false, DIR>(a, c, m, p, x, r, peer_lo, peer_hi, alpha, t, CG_U, prev, cur, acc_rr, acc_rz);
-  for (; t < nrows; t += CG_U) {
-    const int n = (nrows - t) < CG_U ? (nrows - t) : CG_U;
+  for (; t + CG_UB <= lean_end; t += CG_UB)
+    phaseB_batch<UNIT, XE, false, DIR>(a, c, m, p, x, r, peer_lo, peer_hi, alpha, t, CG_UB, prev, cur, acc_rr, acc_rz);
+  for (; t < nrows; t += CG_UB) {
+    const int n = (nrows - t) < CG_UB ? (nrows - t) : CG_UB;
     phaseB_batch<UNIT, XE, true, DIR>(a, c, m, p, x, r, peer_lo, peer_hi, alpha, t, n, prev, cur, acc_rr, acc_rz);
   }
 }
@@ -476,7 +487,7 @@ __device__ __forceinline__ double fold_partials(const double* part, int n, doubl
 }
 
 template <bool UNIT>
-__global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent(CgArgs a) {
+__global__ void __launch_bounds__(CG_THREADS, PF_CG_MINB) k_cg_persistent(CgArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[32];
   const int G = gridDim.x;
@@ -770,7 +781,7 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
 }
 
 template <bool UNIT>
-__global__ void __launch_bounds__(CG_THREADS, 2) k_cg_persistent_multi(CgArgs a) {
+__global__ void __launch_bounds__(CG_THREADS, PF_CG_MINB) k_cg_persistent_multi(CgArgs a) {
   __shared__ double sm[3 * 32];
   const int G = gridDim.x;
   const int bid = blockIdx.x;
@@ -892,7 +903,7 @@ __global__ void k_cg_begin(double* scal, double tol) {
 }
 
 template <bool UNIT>
-__global__ void __launch_bounds__(CG_THREADS, 2) k_cg_phaseA(CgArgs a, int it, unsigned* counter) {
+__global__ void __launch_bounds__(CG_THREADS, PF_CG_MINB) k_cg_phaseA(CgArgs a, int it, unsigned* counter) {
   __shared__ double sm[32];
   if (ld_cg(a.scal + S_DONE) != 0.0) return;
   const int G = gridDim.x, bid = blockIdx.x;
@@ -912,7 +923,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cg_phaseA(CgArgs a, int it, u
 }
 
 template <bool UNIT>
-__global__ void __launch_bounds__(CG_THREADS, 2) k_cg_phaseB(CgArgs a, int it, unsigned* counter) {
+__global__ void __launch_bounds__(CG_THREADS, PF_CG_MINB) k_cg_phaseB(CgArgs a, int it, unsigned* counter) {
   __shared__ double sm[32];
   if (ld_cg(a.scal + S_DONE) != 0.0) return;
   const int G = gridDim.x, bid = blockIdx.x;

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpyflow_b200.so")
+LIB_PATH = os.environ.get("PYFLOW_B200_LIB") or os.path.join(_HERE, "libpyflow_b200.so")   # override: tuning builds
 
 PF_ADV_UPWIND, PF_ADV_QUICK, PF_ADV_NONE = 0, 1, 2
 ABI_VERSION = 1
