@@ -135,6 +135,16 @@ int pf_op_pcg(pf_ctx* ctx, const double* b, double* x, double dx, double dy,
               int jacobi, double inv_diag_interior, double tol, int maxiter,
               int* info, int* true_iters, double* rnorm, void* stream);
 
+/* Straightforward device CG (q stored, one thread per cell) for the operators off
+ * the hot path.  mode 0: the pinned Neumann operator again (independent cross-check
+ * of the tuned kernels); mode 1: +laplacian_coherent with identity rows on the
+ * boundary ring = the manufactured / Dirichlet verification mode of
+ * solve_pressure_poisson (pressure_solver.py:61-93).  b, x: dense host arrays
+ * (x may be NULL); the solution also stays in the context's p field.            */
+int pf_op_cg_generic(pf_ctx* ctx, int mode, const double* b, double* x, double dx, double dy, int jacobi,
+                     double inv_diag_interior, double tol, int maxiter, int* info, int* true_iters,
+                     double* rnorm, double* bnorm, void* stream);
+
 /* Multi-GPU slabs (no reference counterpart: SURVEY.md section 8e).  One
  * process per GPU; rank 0 makes the id, the host side broadcasts the 128
  * bytes (torch.distributed), every rank calls pf_comm_init.                  */

@@ -175,6 +175,29 @@ def pressure_vectors():
         out[f"{tag}/scalars"] = np.array([_TRUE_ITERS[0], diag["Rp_iterations"], diag["Rp_residual"],
                                           diag["divergence_norm"], float(diag["Rp_converged"]),
                                           diag["divergence_norm_initial"]])
+    # tests/test_projection_method_contract.py:408-466 (manufactured Dirichlet mode, rhs_override)
+    for nx, ny in [(8, 8), (14, 11)]:
+        dx, dy = 1.0 / (nx - 1), 1.0 / (ny - 1)
+        X, Y = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 1, ny))
+        pa = np.sin(np.pi * X) * np.sin(np.pi * Y)
+        rhs_grid = np.zeros((ny, nx))
+        rhs_grid[1:-1, 1:-1] = -2.0 * np.pi ** 2 * pa[1:-1, 1:-1]
+        rhs = rhs_grid.reshape(-1)
+        cfg = SimpleNamespace(lin_tol=1e-10, lin_maxiter=500, diagnostics=False)
+        st = ref_allocate(nx, ny)
+        _TRUE_ITERS.clear()
+        p, diag = quiet(ref_ps.solve_pressure_poisson, st, 1.0, dx, dy, cfg, rhs_override=rhs.copy())
+        ost = orc.allocate_state(nx, ny)
+        op, odiag = orc.solve_manufactured(ost, dx, dy, cfg, rhs.copy())
+        tag = f"manufactured_{nx}x{ny}"
+        check(f"{tag} p", op, p)
+        check(f"{tag} true iters", odiag["true_iterations"], _TRUE_ITERS[0])
+        check(f"{tag} divergence_norm", odiag["divergence_norm"], diag["divergence_norm"])
+        check(f"{tag} Rp_iterations", odiag["Rp_iterations"], diag["Rp_iterations"])
+        out[f"{tag}/rhs"] = rhs_grid
+        out[f"{tag}/p"] = p.copy()
+        out[f"{tag}/scalars"] = np.array([_TRUE_ITERS[0], diag["Rp_iterations"], diag["Rp_residual"],
+                                          diag["divergence_norm"], float(diag["Rp_converged"])])
     np.savez_compressed(os.path.join(GOLD, "pressure.npz"), **out)
 
 

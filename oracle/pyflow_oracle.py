@@ -32,7 +32,7 @@ __all__ = [
     "gradient_coherent", "divergence_coherent", "laplacian_coherent",
     "divergence_central", "advect_upwind", "advect_quick",
     "jacobi_inverse_diagonal", "neg_laplacian_pinned", "pcg",
-    "solve_pressure_poisson", "step", "run",
+    "solve_pressure_poisson", "solve_manufactured", "step", "run",
 ]
 
 
@@ -269,6 +269,37 @@ def solve_pressure_poisson(state, dt, dx, dy, cfg, dot=np.dot):
         "true_iterations": true_iters, "info": info,
     }
     return p, diag
+
+
+def solve_manufactured(state, dx, dy, cfg, rhs_override, dot=np.dot):
+    """Manufactured / Dirichlet verification mode (pressure_solver.py:61-93):
+    A x = +laplacian_coherent(x) with identity rows on the boundary ring, no
+    automatic Jacobi, velocities untouched."""
+    ny, nx = interior(state.fields["u"]).shape
+    mask = np.zeros((ny, nx), dtype=bool)
+    mask[0, :] = mask[-1, :] = True
+    mask[:, 0] = mask[:, -1] = True
+    ring = np.flatnonzero(mask.reshape(-1))
+
+    def A(xv):
+        out = laplacian_coherent(xv.reshape(ny, nx), dx, dy).reshape(-1)
+        out[ring] = xv[ring]
+        return out
+
+    rhs = np.copy(rhs_override).reshape(-1)
+    tol = getattr(cfg, "lin_tol", 1e-10)
+    maxiter = getattr(cfg, "lin_maxiter", 500)
+    x, info, true_iters = pcg(A, rhs, tol, maxiter, None, dot)
+    res = rhs - A(x)
+    rnorm = float(np.sqrt(dot(res, res)))
+    bnorm = float(np.sqrt(dot(rhs, rhs))) or 1.0
+    p = x.reshape(ny, nx)
+    interior(state.fields["p"])[:] = p
+    iterations = info if info > 0 else 0
+    if iterations == 0 and rnorm > tol:
+        iterations = 1
+    return p, {"Rp_iterations": iterations, "Rp_residual": rnorm, "Rp_converged": (info == 0) and (rnorm <= tol * bnorm),
+               "Rp_method": "cg", "divergence_norm": rnorm, "true_iterations": true_iters, "info": info}
 
 
 # --------------------------------------------------------------------------

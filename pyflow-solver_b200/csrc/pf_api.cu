@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "pf_cg_dyn.cuh"
+#include "pf_cg_generic.cuh"
 #include "pf_comm.h"
 #include "pf_kernels.cuh"
 
@@ -33,6 +34,7 @@ struct pf_ctx {
   double* h_center = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int cg_grid = 0;
+  int gen_grid = 0;                // co-resident CTAs of k_cg_generic
   long long launches = 0;          // kernels of this library launched so far
   bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
   dim3 sgrid;                      // grid of the simple kernels
@@ -436,6 +438,10 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
     return PF_ERR_UNSUPPORTED;
   }
   c->cg_grid = std::min(c->sm_count * occ, CG_MAX_GRID);
+  int occ_gen_u = 0, occ_gen_g = 0;
+  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen_u, k_cg_generic<true>, CG_THREADS, 0));
+  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen_g, k_cg_generic<false>, CG_THREADS, 0));
+  c->gen_grid = std::min(c->sm_count * std::max(1, std::min(occ_gen_u, occ_gen_g)), CG_MAX_GRID);
 #undef PF_CREATE_CUDA
   *out = c;
   return PF_OK;
@@ -713,6 +719,32 @@ int pf_op_pcg(pf_ctx* c, const double* b, double* x, double dx, double dy, int j
   if (info) *info = (int)c->h_scal[S_INFO];
   if (true_iters) *true_iters = (int)c->h_scal[S_ITERS];
   if (rnorm) *rnorm = sqrt(c->h_scal[S_RES_SUMSQ]);
+  return PF_OK;
+}
+
+int pf_op_cg_generic(pf_ctx* c, int mode, const double* b, double* x, double dx, double dy, int jacobi,
+                     double inv_diag_interior, double tol, int maxiter, int* info, int* true_iters, double* rnorm,
+                     double* bnorm, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!b || maxiter < 0 || (mode != MODE_PINNED && mode != MODE_DIRICHLET)) return PF_ERR_ARG;
+  PF_TRY(h2d_field(c, c->b, b, nxs, st));
+  GenArgs a{};
+  a.s = s; a.b = c->b; a.x = c->x; a.r = c->r; a.p = c->p0; a.q = c->p1;
+  a.part = c->cg_part; a.scal = c->scal;
+  a.dx = dx; a.dy = dy; a.invd = jacobi ? inv_diag_interior : 1.0; a.tol = tol; a.maxiter = maxiter; a.mode = mode;
+  void* args[] = {&a};
+  const void* fn = is_unit(dx, dy) ? (const void*)k_cg_generic<true> : (const void*)k_cg_generic<false>;
+  const long long ncell = (long long)s.nx * s.nyl;
+  const int grid = (int)std::max(1LL, std::min((long long)c->gen_grid, (ncell + CG_THREADS - 1) / CG_THREADS));
+  PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CG_THREADS), args, 0, st));
+  c->launches++;
+  c->center_valid = false;
+  if (x) PF_TRY(d2h_field(c, x, c->x, nxs, st));
+  PF_TRY(read_scalars(c, st, false));
+  if (info) *info = (int)c->h_scal[S_INFO];
+  if (true_iters) *true_iters = (int)c->h_scal[S_ITERS];
+  if (rnorm) *rnorm = sqrt(c->h_scal[S_RES_SUMSQ]);
+  if (bnorm) *bnorm = sqrt(c->h_scal[S_BB]);
   return PF_OK;
 }
 

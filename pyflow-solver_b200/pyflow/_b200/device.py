@@ -211,6 +211,20 @@ class DeviceSlab:
         return x, info.value, iters.value, rnorm.value
 
 
+    def cg_generic(self, mode: str, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=1.0, want_x=True):
+        """Reference-order CG with the plain (q stored) kernel.  mode 'pinned' | 'dirichlet'.
+        The solution stays in the context's p field.  Returns (x|None, info, iters, ||b-Ax||, ||b||)."""
+        code = {"pinned": 0, "dirichlet": 1}[mode]
+        b = self._dense(b)
+        x = np.empty_like(b) if want_x else None
+        info, iters, rnorm, bnorm = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        _lib.check(self._lib.pf_op_cg_generic(self.ctx, code, _ptr(b), _ptr(x), float(dx), float(dy), int(bool(jacobi)),
+                                              float(inv_diag_interior), float(tol), int(maxiter), C.byref(info),
+                                              C.byref(iters), C.byref(rnorm), C.byref(bnorm), self._stream()),
+                   self.ctx, "pf_op_cg_generic")
+        return x, info.value, iters.value, rnorm.value, bnorm.value
+
+
 _SLAB_CACHE: dict[tuple[int, int], DeviceSlab] = {}
 
 

@@ -82,15 +82,44 @@ def _rp_diagnostics(cfg, out: _lib.StepOut) -> dict:
     }
 
 
+def _solve_manufactured(state, dx, dy, cfg, preconditioner, rhs_override):
+    """Manufactured / Dirichlet verification mode (reference :61-93): solve
+    ``laplacian_coherent(p) = rhs`` with identity rows on the boundary ring, no
+    automatic Jacobi, velocities untouched; ``divergence_norm`` is the linear
+    residual ``||A p - rhs||``.  Runs in the plain device CG (off the hot path)."""
+    if preconditioner is not None:
+        raise NotImplementedError("preconditioners in manufactured mode are not supported on the device")
+    bind = attach(state)
+    slab = bind.slab
+    rhs = np.ascontiguousarray(np.copy(rhs_override), dtype=np.float64).reshape(slab.ny_local, slab.nx)
+    lin_tol = getattr(cfg, "lin_tol", 1e-10)
+    lin_maxiter = getattr(cfg, "lin_maxiter", 500)
+    p, info, iters, rnorm, bnorm = slab.cg_generic("dirichlet", rhs, dx, dy, lin_tol, lin_maxiter)
+    bind.finish(prestep_next=None)            # the device p field holds the solution; u, v unchanged
+    converged = (info == 0) and (rnorm <= lin_tol * (bnorm or 1.0))
+    rp_iters = info if info > 0 else 0
+    if rp_iters == 0 and rnorm > lin_tol:
+        rp_iters = 1
+    rhs_norm = bnorm or 1.0
+    state.meta["cg_true_iterations"] = int(iters)
+    diag = {
+        "Rp_iterations": rp_iters, "Rp_residual": float(rnorm), "Rp_converged": bool(converged), "Rp_method": "cg",
+        "divergence_norm": float(rnorm), "lin_residual_norm": float(rnorm), "lin_residual_rel": float(rnorm) / rhs_norm,
+        "divergence_reduction_factor": None, "divergence_norm_initial": None, "divergence_norm_after_raw": None,
+        "divergence_norm_final": float(rnorm),
+    }
+    return p, diag
+
+
 def solve_pressure_poisson(state, dt: float, dx: float, dy: float, cfg, preconditioner=None, rhs_override=None):
     """Project ``state``'s (u, v) to reduce their coherent divergence.
 
     Returns ``(p, diagnostics)`` like the reference (:42-219); mutates the
-    state's u, v, p.  ``rhs_override`` (manufactured Dirichlet mode, :61-93)
-    is SURVEY.md 8f item 1 and not built yet.
+    state's u, v, p.  ``rhs_override`` selects the manufactured
+    Dirichlet verification mode (:61-93).
     """
     if rhs_override is not None:
-        raise NotImplementedError("manufactured / Dirichlet mode (rhs_override) is not on the device path yet")
+        return _solve_manufactured(state, dx, dy, cfg, preconditioner, rhs_override)
     verbose = getattr(cfg, "diagnostics", True) and not getattr(cfg, "force_quiet", False)
     bind = attach(state)
     params = _projection_params(cfg, dt, dx, dy, preconditioner)

@@ -169,6 +169,48 @@ def test_projection_coscos_vs_golden(golden, nx, ny):
     assert diag["divergence_norm"] < max(1e-10, diag["divergence_norm_initial"] * 5e-6)
 
 
+@pytest.mark.parametrize("nx,ny", [(8, 8), (14, 11)])
+def test_manufactured_dirichlet_mode_vs_golden(golden, nx, ny):
+    """rhs_override mode (reference pressure_solver.py:61-93; tests/test_projection_method_contract.py:408-466)."""
+    from pyflow.core.ghost_fields import allocate_state, interior_view
+    from pyflow.solvers.pressure_solver import solve_pressure_poisson
+    g = golden["pressure"]
+    tag = f"manufactured_{nx}x{ny}"
+    dx, dy = 1.0 / (nx - 1), 1.0 / (ny - 1)
+    cfg = SimpleNamespace(lin_tol=1e-10, lin_maxiter=500, diagnostics=False)
+    st = allocate_state(nx, ny)
+    interior_view(st.fields["u"])[:] = 0.25          # velocities must come back untouched
+    p, diag = solve_pressure_poisson(st, 1.0, dx, dy, cfg, rhs_override=g[f"{tag}/rhs"].reshape(-1).copy())
+    sc = g[f"{tag}/scalars"]            # true_iters, Rp_iterations, Rp_residual, divergence_norm, converged
+    assert rel(p, g[f"{tag}/p"]) < 1e-9
+    assert np.array_equal(interior_view(st.fields["p"]), p)
+    assert np.all(interior_view(st.fields["u"]) == 0.25) and not st.fields["v"].any()
+    assert abs(st.meta["cg_true_iterations"] - sc[0]) <= 1
+    assert diag["Rp_iterations"] == int(sc[1]) and diag["Rp_converged"] == bool(sc[4])
+    assert diag["divergence_norm"] < 1e-8 and diag["divergence_norm_initial"] is None
+    X, Y = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 1, ny))
+    assert np.allclose(p[1:-1, 1:-1], (np.sin(np.pi * X) * np.sin(np.pi * Y))[1:-1, 1:-1], atol=5e-2)
+
+
+@pytest.mark.parametrize("ny,nx,unit", [(96, 130, True), (50, 64, False), (257, 513, True)])
+def test_tuned_cg_kernel_agrees_with_plain_cg_kernel(ny, nx, unit):
+    """Two independent device implementations of the same recurrence (register-window
+    persistent kernel vs one-thread-per-cell kernel with q stored)."""
+    from pyflow._b200.device import slab_for_shape
+    slab = slab_for_shape(ny, nx)
+    rng = np.random.default_rng(ny + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.5, 0.25)
+    b = rng.standard_normal((ny, nx))
+    b -= b.mean()
+    b[0, 0] = 0.0
+    invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)
+    x1, info1, it1, rn1 = slab.pcg(b, dx, dy, 1e-10, 60, jacobi=True, inv_diag_interior=invd)
+    x2, info2, it2, rn2, bn2 = slab.cg_generic("pinned", b, dx, dy, 1e-10, 60, jacobi=True, inv_diag_interior=invd)
+    assert info1 == info2 == 60 and it1 == it2 == 60
+    assert rel(x1, x2) < 1e-12 and abs(rn1 - rn2) <= 1e-10 * rn2
+    assert abs(bn2 - np.linalg.norm(b)) <= 1e-12 * bn2
+
+
 # ---------------------------------------------------------------- full trajectories
 def _cfg(kw):
     return SimpleNamespace(lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,

@@ -49,6 +49,16 @@ def test_pressure_bump(golden, pc):
     assert abs(diag["true_iterations"] - g[f"{tag}/scalars"][0]) <= 1
 
 
+@pytest.mark.parametrize("nx,ny", [(8, 8), (14, 11)])
+def test_manufactured_mode(golden, nx, ny):
+    g = golden["pressure"]
+    tag = f"manufactured_{nx}x{ny}"
+    st = orc.allocate_state(nx, ny)
+    cfg = SimpleNamespace(lin_tol=1e-10, lin_maxiter=500)
+    p, diag = orc.solve_manufactured(st, 1.0 / (nx - 1), 1.0 / (ny - 1), cfg, g[f"{tag}/rhs"].reshape(-1).copy())
+    assert rel(p, g[f"{tag}/p"]) < 1e-9 and abs(diag["true_iterations"] - g[f"{tag}/scalars"][0]) <= 1
+
+
 @pytest.mark.parametrize("name", ["quick32_conv", "quick128_trunc", "upwind96x64_trunc", "quick40x24_spacing",
                                   "upwind17x33_nopc"])
 def test_trajectories(golden, name):
