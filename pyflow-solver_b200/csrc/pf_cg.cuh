@@ -186,7 +186,9 @@ __device__ __forceinline__ Cols strip_cols(const Slab& s, int i0) {
 
 __device__ __forceinline__ int strip_kind(const Slab& s, int i0) {
   if (i0 + STRIP > s.nx) return X_PART;                 // some of the 64 columns do not exist
-  if (i0 == 0 || i0 + STRIP == s.nx) return X_WALL;
+  // wall strips -- and the strip whose east HALO column is the wall (nx % 64 == 1): its halo
+  // value needs the ring-column Jacobi factor, which only the WALL path evaluates
+  if (i0 == 0 || i0 + STRIP >= s.nx - 1) return X_WALL;
   return X_IN;
 }
 

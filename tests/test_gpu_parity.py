@@ -111,6 +111,24 @@ def test_pcg_matches_scipy_recurrence(ny, nx, unit, jac):
     assert bits_equal(A.matvec(xo), orc.neg_laplacian_pinned(xo, nx, ny, dx, dy))
 
 
+@pytest.mark.parametrize("ny,nx", [(70, 65), (257, 513), (40, 1100), (33, 4096), (48, 577), (21, 129)])
+def test_pcg_strip_and_chunk_layouts_vs_oracle(ny, nx):
+    """Column layouts of the tuned kernel: one column beyond a strip (nx % 64 == 1, the
+    neighbour strip's halo column is then the wall), several column chunks, partial chunks."""
+    from pyflow._b200.device import slab_for_shape
+    slab = slab_for_shape(ny, nx)
+    rng = np.random.default_rng(ny * 7 + nx)
+    b = rng.standard_normal((ny, nx))
+    b -= b.mean()
+    b[0, 0] = 0.0
+    its = 25
+    x, info, iters, rnorm = slab.pcg(b, 1.0, 1.0, 1e-10, its, jacobi=True)
+    inv = orc.jacobi_inverse_diagonal(nx, ny, 1.0, 1.0)
+    xo, oinfo, oiters = orc.pcg(lambda z: orc.neg_laplacian_pinned(z, nx, ny, 1.0, 1.0), b.ravel().copy(), 1e-10, its, inv)
+    assert info == oinfo == its and iters == oiters
+    assert rel(x.ravel(), xo) < 1e-12, rel(x.ravel(), xo)
+
+
 def test_pcg_truncated_and_zero_rhs():
     from pyflow._b200.device import slab_for_shape
     ny, nx = 96, 80
@@ -207,7 +225,8 @@ def test_tuned_cg_kernel_agrees_with_plain_cg_kernel(ny, nx, unit):
     x1, info1, it1, rn1 = slab.pcg(b, dx, dy, 1e-10, 60, jacobi=True, inv_diag_interior=invd)
     x2, info2, it2, rn2, bn2 = slab.cg_generic("pinned", b, dx, dy, 1e-10, 60, jacobi=True, inv_diag_interior=invd)
     assert info1 == info2 == 60 and it1 == it2 == 60
-    assert rel(x1, x2) < 1e-12 and abs(rn1 - rn2) <= 1e-10 * rn2
+    assert rel(x1, x2) < 1e-10, rel(x1, x2)      # summation order of the dot products differs between the two
+    assert abs(rn1 - rn2) <= 1e-9 * rn2, (rn1, rn2)
     assert abs(bn2 - np.linalg.norm(b)) <= 1e-12 * bn2
 
 
