@@ -10,6 +10,7 @@
 
 #include "pf_cg_dyn.cuh"
 #include "pf_cg_generic.cuh"
+#include "pf_cg_tma.cuh"
 #include "pf_comm.h"
 #include "pf_kernels.cuh"
 
@@ -35,6 +36,7 @@ struct pf_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int cg_grid = 0;
   int gen_grid = 0;                // co-resident CTAs of k_cg_generic
+  int tma_grid = 0;                // co-resident CTAs of k_cg_tma (0: unavailable)
   long long launches = 0;          // kernels of this library launched so far
   bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
   dim3 sgrid;                      // grid of the simple kernels
@@ -46,7 +48,8 @@ struct pf_ctx {
   bool peers = false;
   int opt_multi_single = 0;
   int opt_sync = 0;
-  int opt_kernel = 1;              // 1: static-tile persistent kernels (production); 0: k_cg_dyn (experimental)        // debug/tuning: run the multi-GPU persistent kernel with one rank
+  int opt_kernel = 3;              // 3: auto = TMA-fed dynamically scheduled kernel when eligible (nx % 1024 == 0, one GPU),
+                                   //    else the register-window kernels; 2: static TMA; 1: register-window only; 0: k_cg_dyn (experimental)        // debug/tuning: run the multi-GPU persistent kernel with one rank
   char err[512] = {0};
 };
 
@@ -230,7 +233,32 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
   cg_geometry(c, a);
   const bool unit = is_unit(dx, dy);
-  if (c->opt_kernel == 0 && (!c->comm || c->peers)) {
+  if (c->opt_kernel == 3 && !c->comm && c->tma_grid > 0 && s.nx % TM_CW == 0 &&
+      (long long)(s.nx / TM_CW) * ((s.nyl + TD_ROWS - 1) / TD_ROWS) <= CG_MAX_TILES && s.nyl >= 2) {
+    // TMA-fed sweeps, dynamically scheduled 1024 x 16 tiles, one CTA per SM
+    a.nchunks = s.nx / TM_CW;
+    a.nbands = (s.nyl + TD_ROWS - 1) / TD_ROWS;
+    a.ntiles = a.nchunks * a.nbands;
+    a.wx = TM_WARPS; a.wy = 1;
+    fill_sync(c, a.y);
+    PF_CUDA(c, cudaMemsetAsync(a.y.err, 0, sizeof(unsigned long long), st));
+    void* args[] = {&a};
+    const void* fn = unit ? (const void*)k_cg_tmad<true> : (const void*)k_cg_tmad<false>;
+    PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->tma_grid), dim3(TM_THREADS), args, TM_SMEM_BYTES, st));
+    c->launches++;
+  } else if (c->opt_kernel == 2 && !c->comm && c->tma_grid > 0 && s.nx % TM_CW == 0 &&
+      s.nyl >= std::max(1, c->tma_grid / (s.nx / TM_CW))) {
+    // TMA-fed sweeps: 1024-column tiles, one CTA per SM, rows streamed through a shared-memory ring
+    a.nchunks = s.nx / TM_CW;
+    a.nbands = std::max(1, c->tma_grid / a.nchunks);
+    a.ntiles = a.nchunks * a.nbands;
+    a.wx = TM_WARPS; a.wy = 1;
+    a.y.opt = c->opt_sync;
+    void* args[] = {&a};
+    const void* fn = unit ? (const void*)k_cg_tma<true> : (const void*)k_cg_tma<false>;
+    PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->tma_grid), dim3(TM_THREADS), args, TM_SMEM_BYTES, st));
+    c->launches++;
+  } else if (c->opt_kernel == 0 && (!c->comm || c->peers)) {
     // production: ONE dynamically scheduled persistent kernel (per rank); with several ranks the halo
     // rows and the dot-product partials travel over NVLink peer memory inside the kernel
     if (c->comm) {
@@ -441,6 +469,24 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   int occ_gen_u = 0, occ_gen_g = 0;
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen_u, k_cg_generic<true>, CG_THREADS, 0));
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen_g, k_cg_generic<false>, CG_THREADS, 0));
+  {
+    cudaError_t e1 = cudaFuncSetAttribute(k_cg_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(k_cg_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_cg_tmad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_cg_tmad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+    int o1 = 0, o2 = 0;
+    if (e1 == cudaSuccess && e2 == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_cg_tma<true>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_cg_tma<false>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
+        o1 >= 1 && o2 >= 1) {
+      int o3 = 0, o4 = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_cg_tmad<true>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, k_cg_tmad<false>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
+          o3 >= 1 && o4 >= 1)
+        c->tma_grid = c->sm_count;   // one CTA per SM
+    }
+    (void)cudaGetLastError();
+  }
   c->gen_grid = std::min(c->sm_count * std::max(1, std::min(occ_gen_u, occ_gen_g)), CG_MAX_GRID);
 #undef PF_CREATE_CUDA
   *out = c;

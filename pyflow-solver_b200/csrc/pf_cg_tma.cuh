@@ -1,0 +1,859 @@
+// pf_cg_tma.cuh -- the CG sweeps fed by the TMA engine (bulk asynchronous copies)
+// through a shared-memory ring, for grids whose width is a multiple of 1024.
+//
+// Why: the register-window kernel (pf_cg.cuh) keeps at most ~100 KB of loads in
+// flight per SM and only while its warps sit in the load part of a batch; ncu
+// shows it latency-bound (long-scoreboard 12 per issue, 21 % issue slots, 5.3 TB/s
+// of DRAM traffic).  Here one producer thread per CTA streams whole 8 KB row
+// segments with cp.async.bulk (global -> shared, completion on an mbarrier) up to
+// 8 rows (~200 KB) ahead, independent of registers; 16 compute warps consume rows
+// from shared memory.  Same arithmetic, same operation order, same reductions as
+// pf_cg.cuh -- only where the operands come from changes.
+//
+//   CTA  = 16 compute warps (64 columns each, 2 per lane) + 1 producer warp, 1 CTA/SM
+//   tile = 1024 columns x band; grid = #SMs, tile = blockIdx (static)
+//   ring = 8 stages; stage = one row visit: phase A {r, p_old} (2 x 8224 B incl. 2+2
+//          halo columns), phase B {p (with halo), x, r of the centre row} (24608 B)
+//   full[s]  mbarrier: producer arrive.expect_tx + TMA complete_tx
+//   empty[s] mbarrier: one arrive per compute warp after its reads
+// Row sequence numbers run on across phases and iterations, so stage = n % 8 and the
+// mbarrier parity = (n / 8) & 1 need no per-phase reset.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "pf_cg_dyn.cuh"
+
+namespace pf {
+
+constexpr int TM_WARPS = 16;
+constexpr int TM_THREADS = (TM_WARPS + 1) * 32;
+constexpr int TM_CW = TM_WARPS * STRIP;          // 1024 columns per CTA tile
+constexpr int TM_HALO = 2;                       // halo columns kept on each side (16-byte alignment)
+constexpr int TM_ROW = TM_CW + 2 * TM_HALO;      // doubles per haloed smem row
+constexpr int TM_STAGES = 8;
+constexpr int TM_STAGE_BYTES = (TM_ROW + 2 * TM_CW) * 8;            // 24608: phase B layout is the larger one
+constexpr int TM_SMEM_BYTES = TM_STAGES * TM_STAGE_BYTES + 2 * TM_STAGES * 8 + 64;
+static_assert(TM_STAGE_BYTES % 16 == 0, "bulk copies need 16-byte aligned destinations");
+
+// ---- mbarrier / bulk-copy PTX ----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  Returns false on timeout.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                              uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+struct TmaTile {
+  int i0;            // first column of the tile
+  int j0, j1;        // local rows [j0, j1)
+  int cs, ce;        // columns actually copied [cs, ce) (halo clipped at the walls)
+  bool active;
+};
+
+__device__ __forceinline__ TmaTile tma_tile(const CgArgs& a, int t) {
+  TmaTile w;
+  const int c = t % a.nchunks, bd = t / a.nchunks;
+  w.active = t < a.ntiles;
+  w.i0 = c * TM_CW;
+  w.j0 = (int)((long long)bd * a.s.nyl / a.nbands);
+  w.j1 = (int)((long long)(bd + 1) * a.s.nyl / a.nbands);
+  w.cs = w.i0 - TM_HALO < 0 ? 0 : w.i0 - TM_HALO;
+  w.ce = w.i0 + TM_CW + TM_HALO > a.s.nx ? a.s.nx : w.i0 + TM_CW + TM_HALO;
+  return w;
+}
+
+struct Ring {
+  unsigned char* base;
+  uint64_t* full;
+  uint64_t* empty;
+  __device__ __forceinline__ double* stage(int s) const { return (double*)(base + (size_t)s * TM_STAGE_BYTES); }
+};
+
+// ---- producer: one thread streams the rows of a tile in visiting order ------------
+// Visit t of a tile (DIR = +1 top->bottom, -1 bottom->top): local row jl = jl0 + DIR*t.
+// Rows outside the global domain are not copied (the consumers mask them anyway).
+template <int DIR>
+__device__ __forceinline__ bool produce_A(const CgArgs& a, const Ring& rg, const TmaTile& w, const double* r,
+                                          const double* pold, bool first, uint64_t pol, unsigned long long& n) {
+  const Slab& s = a.s;
+  const int TH = w.j1 - w.j0, nrows = TH + 2;
+  const int jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
+  const uint32_t bytes = (uint32_t)(w.ce - w.cs) * 8u;
+  const int soff = w.cs - (w.i0 - TM_HALO);                    // where the copied segment starts inside the haloed row
+  for (int t = 0; t < nrows; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.empty + st, (uint32_t)(((n / TM_STAGES) & 1ULL) ^ 1ULL))) return false;
+    const int jl = jl0 + DIR * t;
+    const int jg = s.row0 + jl;
+    double* dst = rg.stage(st);
+    if (jg >= 0 && jg < s.nyg) {
+      mbar_expect_tx(rg.full + st, first ? bytes : 2u * bytes);
+      bulk_g2s(dst + soff, r + cell(s, jl, w.cs), bytes, rg.full + st);
+      if (!first) bulk_g2s_hint(dst + TM_ROW + soff, pold + cell(s, jl, w.cs), bytes, rg.full + st, pol);
+    } else {
+      mbar_expect_tx(rg.full + st, 0u);
+    }
+  }
+  return true;
+}
+
+template <int DIR>
+__device__ __forceinline__ bool produce_B(const CgArgs& a, const Ring& rg, const TmaTile& w, const double* p,
+                                          const double* x, const double* r, uint64_t pol, unsigned long long& n) {
+  const Slab& s = a.s;
+  const int TH = w.j1 - w.j0, nrows = TH + 2;
+  const int jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
+  const uint32_t pbytes = (uint32_t)(w.ce - w.cs) * 8u;
+  const uint32_t cbytes = (uint32_t)TM_CW * 8u;
+  const int soff = w.cs - (w.i0 - TM_HALO);
+  for (int t = 0; t < nrows; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.empty + st, (uint32_t)(((n / TM_STAGES) & 1ULL) ^ 1ULL))) return false;
+    const int jl = jl0 + DIR * t;
+    const int jg = s.row0 + jl;
+    double* dst = rg.stage(st);
+    const bool prow = jg >= 0 && jg < s.nyg;
+    const bool centre = t >= 2;                                 // x, r of the centre row jl - DIR (always a band row)
+    mbar_expect_tx(rg.full + st, (prow ? pbytes : 0u) + (centre ? 2u * cbytes : 0u));
+    if (prow) bulk_g2s(dst + soff, p + cell(s, jl, w.cs), pbytes, rg.full + st);
+    if (centre) {
+      bulk_g2s_hint(dst + TM_ROW, x + cell(s, jl - DIR, w.i0), cbytes, rg.full + st, pol);
+      bulk_g2s(dst + TM_ROW + TM_CW, r + cell(s, jl - DIR, w.i0), cbytes, rg.full + st);
+    }
+  }
+  return true;
+}
+
+// ---- consumers ------------------------------------------------------------------------
+// One compute warp = one 64-column strip of the tile.  Values come from the shared
+// ring; the 3-row window of p lives in registers as in pf_cg.cuh.
+template <bool UNIT, int XE, int DIR>
+__device__ __forceinline__ bool consume_A(const CgArgs& a, const Ring& rg, const TmaTile& w, int warp, double* pnew,
+                                          bool first, double beta, unsigned long long& n, double& acc) {
+  const Slab& s = a.s;
+  const int lane = threadIdx.x & 31;
+  const int i0 = w.i0 + warp * STRIP;
+  const Cols c = strip_cols<XE>(s, i0);
+  const int TH = w.j1 - w.j0, nrows = TH + 2;
+  const int jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
+  const int k = TM_HALO + warp * STRIP + 2 * lane;                // my first column inside the haloed smem row
+  const int kh = (lane == 0) ? k - 1 : k + 2;                    // strip halo column (lanes 0 / 31)
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  for (int t = 0; t < nrows; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+    const double* sr = rg.stage(st);
+    const double* sp = sr + TM_ROW;
+    const int jl = jl0 + DIR * t;
+    const int jg = s.row0 + jl;
+    const bool exists = jg >= 0 && jg < s.nyg;
+    double2 rr = make_double2(0.0, 0.0), pp = make_double2(0.0, 0.0);
+    double rh = 0.0, ph = 0.0;
+    if (exists) {
+      rr = *reinterpret_cast<const double2*>(sr + k);
+      if (c.vh) rh = sr[kh];
+      if (!first) {
+        pp = *reinterpret_cast<const double2*>(sp + k);
+        if (c.vh) ph = sp[kh];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(rg.empty + st);                    // this warp is done with the stage
+    // generic treatment whenever the produced row or the centre row is a global boundary row
+    // (or lies outside the domain) -- decided from global row numbers, not from the tile position:
+    // with one-row bands the halo row of an interior tile can be the Jacobi-ring row
+    const int jgc_ = jg - DIR;
+    const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc_ <= 0) || (jgc_ >= s.nyg - 1);
+    const bool ring_row = (jg == 0) || (jg == s.nyg - 1);
+    double da = a.invd, db = a.invd, dh = a.invd;
+    if (XE != X_IN || gen) {
+      da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+      db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+      dh = (ring_row || c.ring_h) ? 1.0 : a.invd;
+    }
+    const double za = da * rr.x, zb = db * rr.y, zh = dh * rh;
+    Row nw;
+    if (first) {
+      nw.a = za; nw.b = zb; nw.h = zh;
+    } else {
+      nw.a = (pp.x * beta) + za;
+      nw.b = (pp.y * beta) + zb;
+      nw.h = (ph * beta) + zh;
+    }
+    if (t >= 1 && t <= TH) st2(pnew + cell(s, jl, c.ia), nw.a, nw.b);
+    if (t >= 2) {
+      const int jgc = jg - DIR;
+      const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+      double la, lb;
+      if (gen) {
+        if (DIR > 0) lap_pair<UNIT, XE, true>(a, c, prev, cur, nw, hs, hn, la, lb);
+        else lap_pair<UNIT, XE, true>(a, c, nw, cur, prev, hs, hn, la, lb);
+        if (jgc == 0 && c.ia == 0) la = -cur.a;                   // pinned row: q[0] = p[0]
+      } else {
+        if (DIR > 0) lap_pair<UNIT, XE, false>(a, c, prev, cur, nw, hs, hn, la, lb);
+        else lap_pair<UNIT, XE, false>(a, c, nw, cur, prev, hs, hn, la, lb);
+      }
+      acc += cur.a * la;                                          // sum p*lap = -(p.q)
+      acc += cur.b * lb;
+    }
+    prev = cur;
+    cur = nw;
+  }
+  return true;
+}
+
+template <bool UNIT, int XE, int DIR>
+__device__ __forceinline__ bool consume_B(const CgArgs& a, const Ring& rg, const TmaTile& w, int warp, double* x,
+                                          double* r, double alpha, uint64_t pol, unsigned long long& n, double& acc_rr,
+                                          double& acc_rz) {
+  const Slab& s = a.s;
+  const int lane = threadIdx.x & 31;
+  const int i0 = w.i0 + warp * STRIP;
+  const Cols c = strip_cols<XE>(s, i0);
+  const int TH = w.j1 - w.j0, nrows = TH + 2;
+  const int jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
+  const int k = TM_HALO + warp * STRIP + 2 * lane;
+  const int kh = (lane == 0) ? k - 1 : k + 2;
+  const int kc = warp * STRIP + 2 * lane;                         // column inside the un-haloed x / r rows
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  for (int t = 0; t < nrows; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+    const double* sp = rg.stage(st);
+    const double* sx = sp + TM_ROW;
+    const double* sr = sx + TM_CW;
+    const int jl = jl0 + DIR * t;
+    const int jg = s.row0 + jl;
+    const bool exists = jg >= 0 && jg < s.nyg;
+    Row nw = {0.0, 0.0, 0.0};
+    if (exists) {
+      const double2 pv = *reinterpret_cast<const double2*>(sp + k);
+      nw.a = pv.x; nw.b = pv.y;
+      if (c.vh) nw.h = sp[kh];
+    }
+    double2 xx = make_double2(0.0, 0.0), rr = make_double2(0.0, 0.0);
+    if (t >= 2) {
+      xx = *reinterpret_cast<const double2*>(sx + kc);
+      rr = *reinterpret_cast<const double2*>(sr + kc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(rg.empty + st);
+    if (t >= 2) {
+      const int jc = jl - DIR;
+      const int jgc = jg - DIR;
+      const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
+      const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+      double la, lb;
+      if (gen) {
+        if (DIR > 0) lap_pair<UNIT, XE, true>(a, c, prev, cur, nw, hs, hn, la, lb);
+        else lap_pair<UNIT, XE, true>(a, c, nw, cur, prev, hs, hn, la, lb);
+        if (jgc == 0 && c.ia == 0) la = -cur.a;
+      } else {
+        if (DIR > 0) lap_pair<UNIT, XE, false>(a, c, prev, cur, nw, hs, hn, la, lb);
+        else lap_pair<UNIT, XE, false>(a, c, nw, cur, prev, hs, hn, la, lb);
+      }
+      const double xa = xx.x + alpha * cur.a;                     // x += alpha*p
+      const double xb = xx.y + alpha * cur.b;
+      const double ra = rr.x + alpha * la;                        // r -= alpha*q, q = -lap
+      const double rb = rr.y + alpha * lb;
+      const size_t o = cell(s, jc, c.ia);
+      st2_hint(x + o, xa, xb, pol);
+      st2(r + o, ra, rb);
+      const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
+      double da = a.invd, db = a.invd;
+      if (XE != X_IN || gen) {
+        da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+        db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+      }
+      acc_rr += ra * ra;
+      acc_rz += ra * (da * ra);
+      acc_rr += rb * rb;
+      acc_rz += rb * (db * rb);
+    }
+    prev = cur;
+    cur = nw;
+  }
+  return true;
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tma(CgArgs a) {
+  namespace cgr = cooperative_groups;
+  cgr::grid_group grid = cgr::this_grid();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double sm[32];
+  __shared__ int s_fail;
+  const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool producer = (warp == TM_WARPS);
+  Ring rg;
+  rg.base = smem_raw;
+  rg.full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TM_STAGES * TM_STAGE_BYTES);
+  rg.empty = rg.full + TM_STAGES;
+  if (tid == 0) {
+    for (int q = 0; q < TM_STAGES; ++q) {
+      mbar_init(rg.full + q, 1u);
+      mbar_init(rg.empty + q, (uint32_t)TM_WARPS);
+    }
+    s_fail = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const TmaTile w = tma_tile(a, bid);
+  const int xk = strip_kind(a.s, w.i0 + (warp < TM_WARPS ? warp : 0) * STRIP);
+  const uint64_t pol = policy_evict_first();
+  unsigned long long n = 0;                          // row sequence number (same in every thread of the CTA)
+
+  const double bb = ld_cg(a.scal + S_BB);
+  const double bnorm = sqrt(bb);
+  const double t0 = a.tol * bnorm;
+  const double atol = (t0 > 0.0) ? t0 : 0.0;
+  int iters = 0;
+  int info = a.maxiter;
+  double rr = bb;
+  double rho = ld_cg(a.scal + S_BZ);
+  double rho_prev = 0.0;
+  double* pcur = a.p0;
+  double* pnext = a.p1;
+  bool ok = true;
+
+  if (bnorm == 0.0) {
+    info = 0;
+  } else {
+    for (int it = 0; it < a.maxiter; ++it) {
+      if (sqrt(rr) < atol) {
+        info = 0;
+        break;
+      }
+      const bool first = (it == 0);
+      const double beta = first ? 0.0 : rho / rho_prev;
+      // ---------------- phase A: top -> bottom
+      double acc = 0.0;
+      if (w.active) {
+        bool good = true;
+        if (producer) {
+          if (lane == 0) good = produce_A<+1>(a, rg, w, a.r, pcur, first, pol, n);
+          else n += (unsigned long long)(w.j1 - w.j0 + 2);
+        } else if (xk == X_WALL) {
+          good = consume_A<UNIT, X_WALL, +1>(a, rg, w, warp, pnext, first, beta, n, acc);
+        } else {
+          good = consume_A<UNIT, X_IN, +1>(a, rg, w, warp, pnext, first, beta, n, acc);
+        }
+        if (!good) s_fail = 1;
+      }
+      acc = block_sum(acc, sm);
+      if (tid == 0) a.part[bid] = -acc;
+      if ((a.y.opt & 4) && it == 200 && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        ((unsigned long long*)(a.part + 4096))[bid] = (gtime() << 10) | (unsigned long long)(smid & 1023u);
+      }
+      grid.sync();
+      if ((a.y.opt & 4) && it == 200 && tid == 0 && bid == 0) ((unsigned long long*)(a.part + 4096))[1024] = gtime();
+      const double pq = fold_partials(a.part, G, sm);
+      const double alpha = rho / pq;
+      // ---------------- phase B: bottom -> top
+      double arr = 0.0, arz = 0.0;
+      if (w.active) {
+        bool good = true;
+        if (producer) {
+          if (lane == 0) good = produce_B<-1>(a, rg, w, pnext, a.x, a.r, pol, n);
+          else n += (unsigned long long)(w.j1 - w.j0 + 2);
+        } else if (xk == X_WALL) {
+          good = consume_B<UNIT, X_WALL, -1>(a, rg, w, warp, a.x, a.r, alpha, pol, n, arr, arz);
+        } else {
+          good = consume_B<UNIT, X_IN, -1>(a, rg, w, warp, a.x, a.r, alpha, pol, n, arr, arz);
+        }
+        if (!good) s_fail = 1;
+      }
+      arr = block_sum(arr, sm);
+      arz = block_sum(arz, sm);
+      if (tid == 0) {
+        a.part[CG_MAX_GRID + bid] = arr;
+        a.part[2 * CG_MAX_GRID + bid] = arz;
+        a.part[3 * CG_MAX_GRID + bid] = s_fail ? 1.0 : 0.0;
+        if ((a.y.opt & 4) && it == 200) {
+          unsigned smid;
+          asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+          ((unsigned long long*)(a.part + 4096))[512 + bid] = (gtime() << 10) | (unsigned long long)(smid & 1023u);
+        }
+      }
+      grid.sync();
+      if ((a.y.opt & 4) && it == 200 && tid == 0 && bid == 0) ((unsigned long long*)(a.part + 4096))[1025] = gtime();
+      if ((a.y.opt & 4) && it == 199 && tid == 0 && bid == 0) ((unsigned long long*)(a.part + 4096))[1026] = gtime();
+      rr = fold_partials(a.part + CG_MAX_GRID, G, sm);
+      const double rz = fold_partials(a.part + 2 * CG_MAX_GRID, G, sm);
+      if (fold_partials(a.part + 3 * CG_MAX_GRID, G, sm) != 0.0) {   // a pipeline wait timed out somewhere
+        ok = false;
+        break;
+      }
+      rho_prev = rho;
+      rho = rz;
+      double* tmp = pcur; pcur = pnext; pnext = tmp;
+      ++iters;
+    }
+  }
+  if (bid == 0 && tid == 0) {
+    a.scal[S_INFO] = ok ? (double)info : -2.0;
+    a.scal[S_ITERS] = (double)iters;
+    a.scal[S_RR] = rr;
+  }
+}
+
+
+// =====================================================================================
+// Dynamically scheduled variant (production for nx % 1024 == 0 on one GPU).
+//
+// The globaltimer timeline of k_cg_tma (static: one 1024 x ~110-row tile per SM)
+// showed the first CTA finishing phase B after 62 us and the last after 106 us: SMs
+// do not get equal shares of the memory system (neighbouring SM ids are slow
+// together: GPC / TPC level sharing), so equal static tiles leave a third of the
+// chip idle at the end of every sweep.  Here tiles are 1024 columns x TD_ROWS rows
+// and every CTA DRAWS its next tile from an atomic ticket counter -- ascending in
+// phase A, descending in phase B (grid-wide LIFO: what A wrote last B reads first,
+// from L2).  The producer keeps the shared-memory ring full ACROSS tile boundaries
+// (it draws the next ticket and starts streaming its rows while the compute warps
+// still work on the current tile), so a small tile costs two extra row visits, not a
+// pipeline drain.  Partial sums are kept per tile (the last compute warp to finish a
+// tile adds the 16 warp partials in warp order) and folded in tile order: the result
+// does not depend on which SM processed which tile.
+constexpr int TD_ROWS = 16;            // rows per tile
+constexpr int TD_SLOTS = 4;            // tile descriptors in flight (ring depth 8 visits < 1 tile)
+
+struct DynShared {
+  int tile[TD_SLOTS];                  // tile id of tile-sequence slot (-1: end of phase)
+  unsigned count[TD_SLOTS];            // compute warps that finished the tile
+  double wpart[TD_SLOTS][2][TM_WARPS];
+  unsigned long long n_end, seq_end;   // producer's counters at the end of a phase
+};
+
+__device__ __forceinline__ TmaTile tmad_tile(const CgArgs& a, int t) {
+  TmaTile w;
+  const int c = t % a.nchunks, bd = t / a.nchunks;
+  w.active = true;
+  w.i0 = c * TM_CW;
+  w.j0 = bd * TD_ROWS;
+  w.j1 = w.j0 + TD_ROWS > a.s.nyl ? a.s.nyl : w.j0 + TD_ROWS;
+  w.cs = w.i0 - TM_HALO < 0 ? 0 : w.i0 - TM_HALO;
+  w.ce = w.i0 + TM_CW + TM_HALO > a.s.nx ? a.s.nx : w.i0 + TM_CW + TM_HALO;
+  return w;
+}
+
+// Producer side of one phase.  PHASE_B selects the stage layout / tile order.
+template <bool PHASE_B>
+__device__ __forceinline__ bool tmad_produce(const CgArgs& a, const Ring& rg, DynShared* ds, unsigned long long tbase,
+                                             const double* f0, const double* f1, const double* f2, bool first,
+                                             uint64_t pol, unsigned long long& n, unsigned long long& seq) {
+  const Slab& s = a.s;
+  constexpr int DIR = PHASE_B ? -1 : +1;
+  for (;;) {
+    const unsigned long long tk = atomicAdd(a.y.tickets, 1ULL) - tbase;
+    const int tile = tk < (unsigned long long)a.ntiles ? (PHASE_B ? a.ntiles - 1 - (int)tk : (int)tk) : -1;
+    const int slot = (int)(seq % TD_SLOTS);
+    if (tile < 0) {                                   // end marker: an empty visit carrying tile = -1
+      const int st = (int)(n % TM_STAGES);
+      if (!mbar_wait(rg.empty + st, (uint32_t)(((n / TM_STAGES) & 1ULL) ^ 1ULL))) return false;
+      ds->tile[slot] = -1;
+      mbar_expect_tx(rg.full + st, 0u);
+      ++n;
+      ++seq;
+      return true;
+    }
+    const TmaTile w = tmad_tile(a, tile);
+    const int TH = w.j1 - w.j0, nrows = TH + 2;
+    const int jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
+    const uint32_t hbytes = (uint32_t)(w.ce - w.cs) * 8u;
+    const uint32_t cbytes = (uint32_t)TM_CW * 8u;
+    const int soff = w.cs - (w.i0 - TM_HALO);
+    for (int t = 0; t < nrows; ++t, ++n) {
+      const int st = (int)(n % TM_STAGES);
+      if (!mbar_wait(rg.empty + st, (uint32_t)(((n / TM_STAGES) & 1ULL) ^ 1ULL))) return false;
+      if (t == 0) ds->tile[slot] = tile;             // published by the release of the arrive below
+      const int jl = jl0 + DIR * t;
+      const int jg = s.row0 + jl;
+      const bool exists = jg >= 0 && jg < s.nyg;
+      double* dst = rg.stage(st);
+      if (!PHASE_B) {                                 // {r, p_old} of the visited row, with halo columns
+        if (exists) {
+          mbar_expect_tx(rg.full + st, first ? hbytes : 2u * hbytes);
+          bulk_g2s(dst + soff, f0 + cell(s, jl, w.cs), hbytes, rg.full + st);
+          if (!first) bulk_g2s_hint(dst + TM_ROW + soff, f1 + cell(s, jl, w.cs), hbytes, rg.full + st, pol);
+        } else {
+          mbar_expect_tx(rg.full + st, 0u);
+        }
+      } else {                                        // p of the visited row (haloed) + x, r of the centre row
+        const bool centre = t >= 2;
+        mbar_expect_tx(rg.full + st, (exists ? hbytes : 0u) + (centre ? 2u * cbytes : 0u));
+        if (exists) bulk_g2s(dst + soff, f0 + cell(s, jl, w.cs), hbytes, rg.full + st);
+        if (centre) {
+          bulk_g2s_hint(dst + TM_ROW, f1 + cell(s, jl - DIR, w.i0), cbytes, rg.full + st, pol);
+          bulk_g2s(dst + TM_ROW + TM_CW, f2 + cell(s, jl - DIR, w.i0), cbytes, rg.full + st);
+        }
+      }
+    }
+    ++seq;
+  }
+}
+
+// Last compute warp to finish a tile adds the warp partials in warp order.
+template <int NV>
+__device__ __forceinline__ void tmad_tile_partial(const CgArgs& a, DynShared* ds, int slot, int tile, int warp,
+                                                  double (&v)[NV], bool negate) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  unsigned prev = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) ds->wpart[slot][k][warp] = v[k];
+    __threadfence_block();
+    prev = atomicAdd(&ds->count[slot], 1u);
+  }
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev == (unsigned)TM_WARPS - 1u) {              // every warp's partial of this tile is in shared memory
+    __threadfence_block();
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+        for (int q = 0; q < TM_WARPS; ++q) t += ds->wpart[slot][k][q];
+        a.part[k * CG_MAX_TILES + tile] = negate ? -t : t;
+      }
+      ds->count[slot] = 0u;
+    }
+  }
+}
+
+template <bool UNIT, int XE>
+__device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* pnew,
+                                               bool first, double beta, unsigned long long& n,
+                                               unsigned long long& seq) {
+  const Slab& s = a.s;
+  constexpr int DIR = +1;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+    const int slot = (int)(seq % TD_SLOTS);
+    const int tile = ds->tile[slot];
+    if (tile < 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.empty + st);
+      ++n;
+      ++seq;
+      return true;
+    }
+    const TmaTile w = tmad_tile(a, tile);
+    const int i0 = w.i0 + warp * STRIP;
+    const Cols c = strip_cols<XE>(s, i0);
+    const int TH = w.j1 - w.j0, nrows = TH + 2;
+    const int jl0 = w.j0 - 1;
+    const int k = TM_HALO + warp * STRIP + 2 * lane;
+    const int kh = (lane == 0) ? k - 1 : k + 2;
+    Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+    double acc = 0.0;
+    for (int t = 0; t < nrows; ++t, ++n) {
+      st = (int)(n % TM_STAGES);
+      if (t > 0 && !mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+      const double* sr = rg.stage(st);
+      const double* sp = sr + TM_ROW;
+      const int jl = jl0 + DIR * t;
+      const int jg = s.row0 + jl;
+      const bool exists = jg >= 0 && jg < s.nyg;
+      double2 rr = make_double2(0.0, 0.0), pp = make_double2(0.0, 0.0);
+      double rh = 0.0, ph = 0.0;
+      if (exists) {
+        rr = *reinterpret_cast<const double2*>(sr + k);
+        if (c.vh) rh = sr[kh];
+        if (!first) {
+          pp = *reinterpret_cast<const double2*>(sp + k);
+          if (c.vh) ph = sp[kh];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.empty + st);
+      const int jgc = jg - DIR;
+      const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
+      const bool ring_row = (jg == 0) || (jg == s.nyg - 1);
+      double da = a.invd, db = a.invd, dh = a.invd;
+      if (XE != X_IN || gen) {
+        da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+        db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+        dh = (ring_row || c.ring_h) ? 1.0 : a.invd;
+      }
+      const double za = da * rr.x, zb = db * rr.y, zh = dh * rh;
+      Row nw;
+      if (first) {
+        nw.a = za; nw.b = zb; nw.h = zh;
+      } else {
+        nw.a = (pp.x * beta) + za;
+        nw.b = (pp.y * beta) + zb;
+        nw.h = (ph * beta) + zh;
+      }
+      if (t >= 1 && t <= TH) st2(pnew + cell(s, jl, c.ia), nw.a, nw.b);
+      if (t >= 2) {
+        const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+        double la, lb;
+        if (gen) {
+          lap_pair<UNIT, XE, true>(a, c, prev, cur, nw, hs, hn, la, lb);
+          if (jgc == 0 && c.ia == 0) la = -cur.a;
+        } else {
+          lap_pair<UNIT, XE, false>(a, c, prev, cur, nw, hs, hn, la, lb);
+        }
+        acc += cur.a * la;
+        acc += cur.b * lb;
+      }
+      prev = cur;
+      cur = nw;
+    }
+    double v[1] = {acc};
+    tmad_tile_partial<1>(a, ds, slot, tile, warp, v, /*negate=*/true);     // p.q = -(sum p*lap)
+    ++seq;
+  }
+}
+
+template <bool UNIT, int XE>
+__device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* x,
+                                               double* r, double alpha, uint64_t pol, unsigned long long& n,
+                                               unsigned long long& seq) {
+  const Slab& s = a.s;
+  constexpr int DIR = -1;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+    const int slot = (int)(seq % TD_SLOTS);
+    const int tile = ds->tile[slot];
+    if (tile < 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.empty + st);
+      ++n;
+      ++seq;
+      return true;
+    }
+    const TmaTile w = tmad_tile(a, tile);
+    const int i0 = w.i0 + warp * STRIP;
+    const Cols c = strip_cols<XE>(s, i0);
+    const int TH = w.j1 - w.j0, nrows = TH + 2;
+    const int jl0 = w.j1;
+    const int k = TM_HALO + warp * STRIP + 2 * lane;
+    const int kh = (lane == 0) ? k - 1 : k + 2;
+    const int kc = warp * STRIP + 2 * lane;
+    Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+    double v[2] = {0.0, 0.0};
+    for (int t = 0; t < nrows; ++t, ++n) {
+      st = (int)(n % TM_STAGES);
+      if (t > 0 && !mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+      const double* sp = rg.stage(st);
+      const double* sx = sp + TM_ROW;
+      const double* sr = sx + TM_CW;
+      const int jl = jl0 + DIR * t;
+      const int jg = s.row0 + jl;
+      const bool exists = jg >= 0 && jg < s.nyg;
+      Row nw = {0.0, 0.0, 0.0};
+      if (exists) {
+        const double2 pv = *reinterpret_cast<const double2*>(sp + k);
+        nw.a = pv.x; nw.b = pv.y;
+        if (c.vh) nw.h = sp[kh];
+      }
+      double2 xx = make_double2(0.0, 0.0), rr = make_double2(0.0, 0.0);
+      if (t >= 2) {
+        xx = *reinterpret_cast<const double2*>(sx + kc);
+        rr = *reinterpret_cast<const double2*>(sr + kc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.empty + st);
+      if (t >= 2) {
+        const int jc = jl - DIR;
+        const int jgc = jg - DIR;
+        const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
+        const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+        double la, lb;
+        if (gen) {
+          lap_pair<UNIT, XE, true>(a, c, nw, cur, prev, hs, hn, la, lb);
+          if (jgc == 0 && c.ia == 0) la = -cur.a;
+        } else {
+          lap_pair<UNIT, XE, false>(a, c, nw, cur, prev, hs, hn, la, lb);
+        }
+        const double xa = xx.x + alpha * cur.a;
+        const double xb = xx.y + alpha * cur.b;
+        const double ra = rr.x + alpha * la;
+        const double rb = rr.y + alpha * lb;
+        const size_t o = cell(s, jc, c.ia);
+        st2_hint(x + o, xa, xb, pol);
+        st2(r + o, ra, rb);
+        const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
+        double da = a.invd, db = a.invd;
+        if (XE != X_IN || gen) {
+          da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+          db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+        }
+        v[0] += ra * ra;
+        v[1] += ra * (da * ra);
+        v[0] += rb * rb;
+        v[1] += rb * (db * rb);
+      }
+      prev = cur;
+      cur = nw;
+    }
+    tmad_tile_partial<2>(a, ds, slot, tile, warp, v, /*negate=*/false);
+    ++seq;
+  }
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
+  namespace cgr = cooperative_groups;
+  cgr::grid_group grid = cgr::this_grid();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double sm[32];
+  __shared__ DynShared ds;
+  const int G = gridDim.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool producer = (warp == TM_WARPS);
+  Ring rg;
+  rg.base = smem_raw;
+  rg.full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TM_STAGES * TM_STAGE_BYTES);
+  rg.empty = rg.full + TM_STAGES;
+  if (tid == 0) {
+    for (int q = 0; q < TM_STAGES; ++q) {
+      mbar_init(rg.full + q, 1u);
+      mbar_init(rg.empty + q, (uint32_t)TM_WARPS);
+    }
+    for (int q = 0; q < TD_SLOTS; ++q) { ds.tile[q] = -1; ds.count[q] = 0u; }
+    ds.n_end = 0; ds.seq_end = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint64_t pol = policy_evict_first();
+  unsigned long long n = 0, seq = 0;                  // row / tile sequence numbers of this CTA
+  const unsigned long long tbase0 = *((volatile unsigned long long*)a.y.ticket_base);
+  const unsigned long long per_phase = (unsigned long long)a.ntiles + (unsigned long long)G;
+  unsigned long long phase = 0;
+  // strip kind of this warp is the same for every tile of a chunk COLUMN position, but chunks differ:
+  // it depends on the tile, so it is resolved per phase call below from the warp's column only when
+  // there is a single chunk; in general X_WALL applies to warp 0 of chunk 0 and warp 15 of the last chunk.
+
+  const double bb = ld_cg(a.scal + S_BB);
+  const double bnorm = sqrt(bb);
+  const double t0 = a.tol * bnorm;
+  const double atol = (t0 > 0.0) ? t0 : 0.0;
+  int iters = 0;
+  int info = a.maxiter;
+  double rr = bb;
+  double rho = ld_cg(a.scal + S_BZ);
+  double rho_prev = 0.0;
+  double* pcur = a.p0;
+  double* pnext = a.p1;
+  bool ok = true;
+
+  if (bnorm == 0.0) {
+    info = 0;
+  } else {
+    for (int it = 0; it < a.maxiter; ++it) {
+      if (sqrt(rr) < atol) {
+        info = 0;
+        break;
+      }
+      const bool first = (it == 0);
+      const double beta = first ? 0.0 : rho / rho_prev;
+      // ---------------- phase A
+      {
+        bool good = true;
+        const unsigned long long tbase = tbase0 + phase * per_phase;
+        if (producer) {
+          if (lane == 0) {
+            good = tmad_produce<false>(a, rg, &ds, tbase, a.r, pcur, nullptr, first, pol, n, seq);
+            ds.n_end = n; ds.seq_end = seq;
+          }
+        } else {
+          // wall strips exist only in the first / last column chunk: the generic WALL instantiation is
+          // exact for interior strips too (its predicates are all true there), so edge warps use it always
+          if (warp == 0 || warp == TM_WARPS - 1) good = tmad_consume_A<UNIT, X_WALL>(a, rg, &ds, warp, pnext, first, beta, n, seq);
+          else good = tmad_consume_A<UNIT, X_IN>(a, rg, &ds, warp, pnext, first, beta, n, seq);
+        }
+        if (!good) atomicExch(a.y.err, 1ULL);
+        ++phase;
+      }
+      __syncthreads();
+      n = ds.n_end; seq = ds.seq_end;
+      __threadfence();
+      grid.sync();
+      const double pq = fold_partials(a.part, a.ntiles, sm);
+      const double alpha = rho / pq;
+      // ---------------- phase B
+      {
+        bool good = true;
+        const unsigned long long tbase = tbase0 + phase * per_phase;
+        if (producer) {
+          if (lane == 0) {
+            good = tmad_produce<true>(a, rg, &ds, tbase, pnext, a.x, a.r, false, pol, n, seq);
+            ds.n_end = n; ds.seq_end = seq;
+          }
+        } else {
+          if (warp == 0 || warp == TM_WARPS - 1) good = tmad_consume_B<UNIT, X_WALL>(a, rg, &ds, warp, a.x, a.r, alpha, pol, n, seq);
+          else good = tmad_consume_B<UNIT, X_IN>(a, rg, &ds, warp, a.x, a.r, alpha, pol, n, seq);
+        }
+        if (!good) atomicExch(a.y.err, 1ULL);
+        ++phase;
+      }
+      __syncthreads();
+      n = ds.n_end; seq = ds.seq_end;
+      __threadfence();
+      grid.sync();
+      rr = fold_partials(a.part, a.ntiles, sm);
+      const double rz = fold_partials(a.part + CG_MAX_TILES, a.ntiles, sm);
+      if (ld_cg((const double*)a.y.err) != 0.0) {     // a pipeline wait timed out somewhere (non-zero bit pattern)
+        ok = false;
+        break;
+      }
+      rho_prev = rho;
+      rho = rz;
+      double* tmp = pcur; pcur = pnext; pnext = tmp;
+      ++iters;
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    a.scal[S_INFO] = ok ? (double)info : -2.0;
+    a.scal[S_ITERS] = (double)iters;
+    a.scal[S_RR] = rr;
+    *a.y.ticket_base = tbase0 + phase * per_phase;
+  }
+}
+
+}  // namespace pf
