@@ -233,17 +233,24 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
   cg_geometry(c, a);
   const bool unit = is_unit(dx, dy);
-  if (c->opt_kernel == 3 && !c->comm && c->tma_grid > 0 && s.nx % TM_CW == 0 &&
-      (long long)(s.nx / TM_CW) * ((s.nyl + TD_ROWS - 1) / TD_ROWS) <= CG_MAX_TILES && s.nyl >= 2) {
-    // TMA-fed sweeps, dynamically scheduled 1024 x 16 tiles, one CTA per SM
+  if (c->opt_kernel == 3 && (!c->comm || c->peers) && c->tma_grid > 0 && s.nx % TM_CW == 0 && s.nyl >= 2) {
+    // TMA-fed sweeps, dynamically scheduled 1024-column tiles (16 rows, more for huge slabs), one CTA per SM;
+    // with several ranks: halo rows + dot-product partials over NVLink peer memory inside the same kernel
     a.nchunks = s.nx / TM_CW;
-    a.nbands = (s.nyl + TD_ROWS - 1) / TD_ROWS;
+    a.tile_rows = TD_ROWS;
+    while ((long long)a.nchunks * ((s.nyl + a.tile_rows - 1) / a.tile_rows) > CG_MAX_TILES) a.tile_rows *= 2;
+    a.nbands = (s.nyl + a.tile_rows - 1) / a.tile_rows;
     a.ntiles = a.nchunks * a.nbands;
     a.wx = TM_WARPS; a.wy = 1;
+    if (c->comm) {
+      PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
+      PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
+    }
     fill_sync(c, a.y);
     PF_CUDA(c, cudaMemsetAsync(a.y.err, 0, sizeof(unsigned long long), st));
     void* args[] = {&a};
-    const void* fn = unit ? (const void*)k_cg_tmad<true> : (const void*)k_cg_tmad<false>;
+    const void* fn = c->comm ? (unit ? (const void*)k_cg_tmad<true, true> : (const void*)k_cg_tmad<false, true>)
+                             : (unit ? (const void*)k_cg_tmad<true, false> : (const void*)k_cg_tmad<false, false>);
     PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->tma_grid), dim3(TM_THREADS), args, TM_SMEM_BYTES, st));
     c->launches++;
   } else if (c->opt_kernel == 2 && !c->comm && c->tma_grid > 0 && s.nx % TM_CW == 0 &&
@@ -472,17 +479,23 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   {
     cudaError_t e1 = cudaFuncSetAttribute(k_cg_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
     cudaError_t e2 = cudaFuncSetAttribute(k_cg_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_cg_tmad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_cg_tmad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_cg_tmad<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_cg_tmad<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
     int o1 = 0, o2 = 0;
     if (e1 == cudaSuccess && e2 == cudaSuccess &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_cg_tma<true>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_cg_tma<false>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
         o1 >= 1 && o2 >= 1) {
       int o3 = 0, o4 = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_cg_tmad<true>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, k_cg_tmad<false>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
-          o3 >= 1 && o4 >= 1)
+      cudaError_t e3 = cudaFuncSetAttribute(k_cg_tmad<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+      cudaError_t e4 = cudaFuncSetAttribute(k_cg_tmad<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
+      int o5 = 0, o6 = 0;
+      if (e3 == cudaSuccess && e4 == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_cg_tmad<true, false>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, k_cg_tmad<false, false>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o5, k_cg_tmad<true, true>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o6, k_cg_tmad<false, true>, TM_THREADS, TM_SMEM_BYTES) == cudaSuccess &&
+          o3 >= 1 && o4 >= 1 && o5 >= 1 && o6 >= 1)
         c->tma_grid = c->sm_count;   // one CTA per SM
     }
     (void)cudaGetLastError();

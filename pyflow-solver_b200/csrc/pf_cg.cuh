@@ -106,6 +106,7 @@ struct CgArgs {
   int maxiter;
   int wx, wy;         // warp arrangement inside a CTA tile, wx*wy == CG_WARPS
   int nchunks, nbands, ntiles;
+  int tile_rows;      // rows per tile of the dynamically scheduled TMA kernel
   CgSync y;           // only used by the multi-GPU persistent kernel
 };
 

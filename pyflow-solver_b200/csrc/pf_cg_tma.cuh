@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tma(CgArgs a) {
 // pipeline drain.  Partial sums are kept per tile (the last compute warp to finish a
 // tile adds the 16 warp partials in warp order) and folded in tile order: the result
 // does not depend on which SM processed which tile.
-constexpr int TD_ROWS = 16;            // rows per tile
+constexpr int TD_ROWS = 16;            // default rows per tile (CgArgs::tile_rows; larger for huge slabs)
 constexpr int TD_SLOTS = 4;            // tile descriptors in flight (ring depth 8 visits < 1 tile)
 
 struct DynShared {
@@ -466,8 +466,8 @@ __device__ __forceinline__ TmaTile tmad_tile(const CgArgs& a, int t) {
   const int c = t % a.nchunks, bd = t / a.nchunks;
   w.active = true;
   w.i0 = c * TM_CW;
-  w.j0 = bd * TD_ROWS;
-  w.j1 = w.j0 + TD_ROWS > a.s.nyl ? a.s.nyl : w.j0 + TD_ROWS;
+  w.j0 = bd * a.tile_rows;
+  w.j1 = w.j0 + a.tile_rows > a.s.nyl ? a.s.nyl : w.j0 + a.tile_rows;
   w.cs = w.i0 - TM_HALO < 0 ? 0 : w.i0 - TM_HALO;
   w.ce = w.i0 + TM_CW + TM_HALO > a.s.nx ? a.s.nx : w.i0 + TM_CW + TM_HALO;
   return w;
@@ -558,10 +558,10 @@ __device__ __forceinline__ void tmad_tile_partial(const CgArgs& a, DynShared* ds
   }
 }
 
-template <bool UNIT, int XE>
+template <bool UNIT, int XE, bool MULTI>
 __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* pnew,
-                                               bool first, double beta, unsigned long long& n,
-                                               unsigned long long& seq) {
+                                               double* peer_lo, double* peer_hi, bool first, double beta,
+                                               unsigned long long& n, unsigned long long& seq) {
   const Slab& s = a.s;
   constexpr int DIR = +1;
   const int lane = threadIdx.x & 31;
@@ -624,7 +624,10 @@ __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, 
         nw.b = (pp.y * beta) + zb;
         nw.h = (ph * beta) + zh;
       }
-      if (t >= 1 && t <= TH) st2(pnew + cell(s, jl, c.ia), nw.a, nw.b);
+      if (t >= 1 && t <= TH) {
+        st2(pnew + cell(s, jl, c.ia), nw.a, nw.b);
+        if (MULTI && (jl == 0 || jl == s.nyl - 1)) peer_row_store(s, c, jl, peer_lo, peer_hi, nw.a, nw.b);
+      }
       if (t >= 2) {
         const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
         double la, lb;
@@ -646,10 +649,10 @@ __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, 
   }
 }
 
-template <bool UNIT, int XE>
+template <bool UNIT, int XE, bool MULTI>
 __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* x,
-                                               double* r, double alpha, uint64_t pol, unsigned long long& n,
-                                               unsigned long long& seq) {
+                                               double* r, double* peer_lo, double* peer_hi, double alpha, uint64_t pol,
+                                               unsigned long long& n, unsigned long long& seq) {
   const Slab& s = a.s;
   constexpr int DIR = -1;
   const int lane = threadIdx.x & 31;
@@ -716,6 +719,7 @@ __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, 
         const size_t o = cell(s, jc, c.ia);
         st2_hint(x + o, xa, xb, pol);
         st2(r + o, ra, rb);
+        if (MULTI && (jc == 0 || jc == s.nyl - 1)) peer_row_store(s, c, jc, peer_lo, peer_hi, ra, rb);
         const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
         double da = a.invd, db = a.invd;
         if (XE != X_IN || gen) {
@@ -735,12 +739,85 @@ __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, 
   }
 }
 
-template <bool UNIT>
+// Phase end for several GPUs: like grid_exchange (pf_cg.cuh) but the last CTA folds the
+// per-TILE partials; packets, fences and the rank-ordered sum are identical.
+template <int NV>
+__device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long long e, double (&out)[NV], double* sm) {
+  __shared__ int s_last;
+  __shared__ double s_out[4];
+  __shared__ double s_peer[CG_MAX_RANKS][3];
+  const CgSync& y = a.y;
+  const int G = gridDim.x, tid = threadIdx.x, R = y.nranks;
+  const int par = (int)(e & 1ULL);
+  __syncthreads();                   // every thread's stores (fields, tile partials, peer halos) before thread 0's fence
+  if (tid == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(y.arrive, 1ULL) == e * (unsigned long long)G - 1ULL) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (tid == 0) __threadfence();
+    __syncthreads();
+    double loc[3] = {0.0, 0.0, 0.0};
+    for (int q = tid; q < a.ntiles; q += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) loc[k] += ld_cg(a.part + k * CG_MAX_TILES + q);
+    }
+    block_sum_n<3>(loc, sm);
+    if (tid == 0) {
+      __threadfence_system();        // the halo rows pushed by the other CTAs of this GPU go out before the packet
+      const size_t slot = (size_t)(par * CG_MAX_RANKS + y.rank) * sizeof(Packet);
+      for (int q = 0; q < R; ++q) st_packet_sys((char*)y.peer_mbox[q] + slot, e, loc[0], loc[1], loc[2]);
+    }
+    if (tid < R) {
+      const long long t0 = clock64();
+      Packet k;
+      const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * sizeof(Packet);
+      while ((k = ld_packet_sys(src)).epoch != e) {
+        if (clock64() - t0 > CG_SPIN_LIMIT) {
+          atomicExch(y.err, 1ULL);
+          break;
+        }
+      }
+      __threadfence_system();
+      s_peer[tid][0] = k.v[0]; s_peer[tid][1] = k.v[1]; s_peer[tid][2] = k.v[2];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 0; k < 3; ++k) {  // rank order, identical on every GPU
+        double sum = 0.0;
+        for (int q = 0; q < R; ++q) sum += s_peer[q][k];
+        loc[k] = sum;
+      }
+      __threadfence();
+      st_packet_gpu(y.gsum, e, loc[0], loc[1], loc[2]);
+    }
+  }
+  if (tid == 0) {
+    const long long t0 = clock64();
+    Packet k;
+    while ((k = ld_packet_gpu(y.gsum)).epoch != e) {
+      if (clock64() - t0 > CG_SPIN_LIMIT) {
+        atomicExch(y.err, 1ULL);
+        break;
+      }
+    }
+    __threadfence();
+    s_out[0] = k.v[0]; s_out[1] = k.v[1]; s_out[2] = k.v[2];
+    s_out[3] = (ld_relaxed_u64(y.err) == 0ULL) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) out[k] = s_out[k];
+  return s_out[3] != 0.0;
+}
+
+template <bool UNIT, bool MULTI>
 __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
   namespace cgr = cooperative_groups;
   cgr::grid_group grid = cgr::this_grid();
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double sm[32];
+  __shared__ double sm[3 * 32];
   __shared__ DynShared ds;
   const int G = gridDim.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -765,6 +842,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
   const unsigned long long tbase0 = *((volatile unsigned long long*)a.y.ticket_base);
   const unsigned long long per_phase = (unsigned long long)a.ntiles + (unsigned long long)G;
   unsigned long long phase = 0;
+  unsigned long long e = *((volatile unsigned long long*)a.y.epoch);   // cross-GPU barrier epochs (MULTI)
   // strip kind of this warp is the same for every tile of a chunk COLUMN position, but chunks differ:
   // it depends on the tile, so it is resolved per phase call below from the warp's column only when
   // there is a single chunk; in general X_WALL applies to warp 0 of chunk 0 and warp 15 of the last chunk.
@@ -804,17 +882,29 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
         } else {
           // wall strips exist only in the first / last column chunk: the generic WALL instantiation is
           // exact for interior strips too (its predicates are all true there), so edge warps use it always
-          if (warp == 0 || warp == TM_WARPS - 1) good = tmad_consume_A<UNIT, X_WALL>(a, rg, &ds, warp, pnext, first, beta, n, seq);
-          else good = tmad_consume_A<UNIT, X_IN>(a, rg, &ds, warp, pnext, first, beta, n, seq);
+          double* plo = (pnext == a.p0) ? a.y.below_p0 : a.y.below_p1;
+          double* phi = (pnext == a.p0) ? a.y.above_p0 : a.y.above_p1;
+          if (warp == 0 || warp == TM_WARPS - 1)
+            good = tmad_consume_A<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq);
+          else
+            good = tmad_consume_A<UNIT, X_IN, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq);
         }
         if (!good) atomicExch(a.y.err, 1ULL);
         ++phase;
       }
       __syncthreads();
       n = ds.n_end; seq = ds.seq_end;
-      __threadfence();
-      grid.sync();
-      const double pq = fold_partials(a.part, a.ntiles, sm);
+      double pq;
+      if (MULTI) {
+        double o1[1];
+        ok = tile_exchange<1>(a, ++e, o1, sm);
+        if (!ok) break;
+        pq = o1[0];
+      } else {
+        __threadfence();
+        grid.sync();
+        pq = fold_partials(a.part, a.ntiles, sm);
+      }
       const double alpha = rho / pq;
       // ---------------- phase B
       {
@@ -826,21 +916,32 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
             ds.n_end = n; ds.seq_end = seq;
           }
         } else {
-          if (warp == 0 || warp == TM_WARPS - 1) good = tmad_consume_B<UNIT, X_WALL>(a, rg, &ds, warp, a.x, a.r, alpha, pol, n, seq);
-          else good = tmad_consume_B<UNIT, X_IN>(a, rg, &ds, warp, a.x, a.r, alpha, pol, n, seq);
+          if (warp == 0 || warp == TM_WARPS - 1)
+            good = tmad_consume_B<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq);
+          else
+            good = tmad_consume_B<UNIT, X_IN, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq);
         }
         if (!good) atomicExch(a.y.err, 1ULL);
         ++phase;
       }
       __syncthreads();
       n = ds.n_end; seq = ds.seq_end;
-      __threadfence();
-      grid.sync();
-      rr = fold_partials(a.part, a.ntiles, sm);
-      const double rz = fold_partials(a.part + CG_MAX_TILES, a.ntiles, sm);
-      if (ld_cg((const double*)a.y.err) != 0.0) {     // a pipeline wait timed out somewhere (non-zero bit pattern)
-        ok = false;
-        break;
+      double rz;
+      if (MULTI) {
+        double o2[2];
+        ok = tile_exchange<2>(a, ++e, o2, sm);
+        if (!ok) break;
+        rr = o2[0];
+        rz = o2[1];
+      } else {
+        __threadfence();
+        grid.sync();
+        rr = fold_partials(a.part, a.ntiles, sm);
+        rz = fold_partials(a.part + CG_MAX_TILES, a.ntiles, sm);
+        if (ld_cg((const double*)a.y.err) != 0.0) {   // a pipeline wait timed out somewhere (non-zero bit pattern)
+          ok = false;
+          break;
+        }
       }
       rho_prev = rho;
       rho = rz;
@@ -853,6 +954,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
     a.scal[S_ITERS] = (double)iters;
     a.scal[S_RR] = rr;
     *a.y.ticket_base = tbase0 + phase * per_phase;
+    if (MULTI) *a.y.epoch = e;
   }
 }
 

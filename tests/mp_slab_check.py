@@ -73,6 +73,8 @@ def main():
         dict(nx=128, ny=128, Re=100.0, advection_scheme="quick", lin_maxiter=300, steps=5),   # truncated early
         dict(nx=70, ny=61, Re=400.0, advection_scheme="upwind", lin_maxiter=100, steps=4, lx=2.0, ly=1.0),  # ragged, non-unit, truncated early
         dict(nx=200, ny=48 * world, Re=1000.0, advection_scheme="quick", lin_maxiter=300, steps=4),           # equal slabs, several strips
+        dict(nx=1024, ny=36 * world, Re=1000.0, advection_scheme="quick", lin_maxiter=300, steps=3),          # TMA-fed kernel (nx % 1024 == 0)
+        dict(nx=2048, ny=20 * world, Re=1000.0, advection_scheme="upwind", lin_maxiter=200, steps=3),         # TMA-fed kernel, 2 column chunks
     ]
     used_peer = []
     for case in cases:
