@@ -239,6 +239,9 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     a.nchunks = s.nx / TM_CW;
     a.tile_rows = TD_ROWS;
     while ((long long)a.nchunks * ((s.nyl + a.tile_rows - 1) / a.tile_rows) > CG_MAX_TILES) a.tile_rows *= 2;
+    // short slabs (strong scaling): keep >= ~6 tiles per CTA so the dynamic schedule can balance
+    while (a.tile_rows > 4 && (long long)a.nchunks * ((s.nyl + a.tile_rows - 1) / a.tile_rows) < 6LL * c->tma_grid)
+      a.tile_rows /= 2;
     a.nbands = (s.nyl + a.tile_rows - 1) / a.tile_rows;
     a.ntiles = a.nchunks * a.nbands;
     a.wx = TM_WARPS; a.wy = 1;
