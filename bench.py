@@ -302,7 +302,8 @@ def run_gpu_arm(args, wl, rank, world):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_cg_persistent<unit>",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "k_cg_tmad<unit> (TMA-fed persistent CG)" if nx % 1024 == 0 else "k_cg_persistent<unit>",
                 "algorithmic_bytes_per_launch": cg_bytes / max(1, len(cg_iters)),
                 "avg_launch_ms": statistics.mean(cg_ms) if cg_ms else None,
                 "frac_of_nominal_8TBs": achieved / 8000.0,

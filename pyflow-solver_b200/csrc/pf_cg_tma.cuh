@@ -936,8 +936,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
       } else {
         __threadfence();
         grid.sync();
-        rr = fold_partials(a.part, a.ntiles, sm);
-        rz = fold_partials(a.part + CG_MAX_TILES, a.ntiles, sm);
+        {                                             // both sums in one pass, one block reduction
+          double f[2] = {0.0, 0.0};
+          for (int q = tid; q < a.ntiles; q += blockDim.x) {
+            f[0] += ld_cg(a.part + q);
+            f[1] += ld_cg(a.part + CG_MAX_TILES + q);
+          }
+          block_sum_n<2>(f, sm);
+          rr = f[0];
+          rz = f[1];
+        }
         if (ld_cg((const double*)a.y.err) != 0.0) {   // a pipeline wait timed out somewhere (non-zero bit pattern)
           ok = false;
           break;
