@@ -99,6 +99,21 @@ def main():
             print(f"PARITY mode={mode} peer_kernel={used_peer[-1]} world={world} {cfg.nx}x{cfg.ny} errs={errs} dt_equal={same_dt} iters={iters} max_iter_diff={dit} "
                   f"{'OK' if good else 'FAIL'}", flush=True)
             ok = ok and good
+    # the drop-in driver on slab states: every rank yields, the centre line is the concatenation of the slabs
+    from pyflow.drivers.simulation_driver import SimulationDriver
+    cfg = SimpleNamespace(nx=64, ny=16 * world, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
+                          lin_maxiter=200, advection_scheme="quick", disable_advection=False, diagnostics=False)
+    st = allocate_slab_state(cfg.nx, cfg.ny, rank, world)
+    diags = [d for _s, _r, d in SimulationDriver(cfg, st).run(max_steps=3)]
+    full_u = gather_field(st, "u")
+    if rank == 0:
+        ost, od = orc.run(cfg, 3)
+        line = np.array(diags[-1]["u_centerline"][1])
+        good = (len(line) == cfg.ny and np.array_equal(line, full_u[1:-1, 1 + cfg.nx // 2])
+                and rel(full_u[1:-1, 1:-1], orc.interior(ost.fields["u"])) < 1e-9
+                and [d["dt"] for d in diags] == [d["dt"] for d in od])
+        print(f"PARITY driver world={world} centerline_len={len(line)} {'OK' if good else 'FAIL'}", flush=True)
+        ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

@@ -416,3 +416,51 @@ def test_large_grid_properties_4096():
         assert finals[-1][0, 0] == 0.0
         assert np.allclose(st.fields["u"][-2, 1:-1], 1.0)
     assert np.array_equal(finals[0], finals[1])
+
+
+# ---------------------------------------------------------------- CLI / checkpoint / restart on the device path
+def _run_cli(*argv, cwd=None):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "pyflow-solver_b200"))
+    return subprocess.run([sys.executable, "-m", "pyflow", *argv], capture_output=True, text=True, env=env, cwd=cwd)
+
+
+def test_cli_json_stream_checkpoint_and_restart(tmp_path):
+    """`pyflow run --json-stream` (reference cli.py:154-173 schema), periodic checkpoint with the reference's
+    npz layout, restart with hash enforcement -- all through the device-backed driver."""
+    import json
+    ck = str(tmp_path / "ck.npz")
+    common = ["--nx", "48", "--ny", "40", "--re", "100", "--lin-maxiter", "2000"]
+    r = _run_cli("run", *common, "--steps", "4", "--json-stream", "--checkpoint", ck, "--checkpoint-interval", "3",
+                 cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.strip()]
+    assert [l["iteration"] for l in lines] == [0, 1, 2, 3] and all(l["type"] == "step" for l in lines)
+    for l in lines:
+        assert set(l) == {"type", "iteration", "dt", "CFL", "continuity", "wall_time", "residuals", "diagnostics"}
+        assert set(l["residuals"]) == {"Ru", "Rv", "Rp", "continuity"}
+        assert {"plateau_Ru", "max_residual", "residual_drop_Ru_orders", "nu", "Rp_iterations", "Rp_residual",
+                "Rp_converged", "Rp_method", "divergence_norm", "nan_detected", "u_centerline"} <= set(l["diagnostics"])
+        assert len(l["diagnostics"]["u_centerline"][1]) == 40
+    assert lines[0]["dt"] == 0.0105 and lines[1]["dt"] == 0.011025000000000002      # reference dt sequence from rest
+    # oracle agreement of the streamed scalars
+    cfg = _cfg(dict(nx=48, ny=40, Re=100.0, advection_scheme="quick", lin_maxiter=2000))
+    ost, od = orc.run(cfg, 4)
+    for l, d in zip(lines, od):
+        assert l["dt"] == d["dt"] and abs(l["residuals"]["Ru"] - d["Ru"]) <= 1e-9 * d["Ru"]
+    # checkpoint written after the yield of iteration 3 (3 % 3 == 0) with the reference layout
+    with np.load(ck) as z:
+        meta = json.loads(str(z["meta"]))
+        assert meta["iteration"] == 3 and z["field_u"].shape == (42, 50)
+        assert rel(z["field_u"][1:-1, 1:-1], orc.interior(ost.fields["u"])) < 1e-9
+    # restart: hash mismatch refused (exit 3), matching config resumes at iteration 4
+    bad = _run_cli("run", "--nx", "48", "--ny", "40", "--re", "200", "--steps", "6", "--restart", ck, cwd=str(tmp_path))
+    assert bad.returncode == 3
+    # (checkpoint_interval is part of the hashed config, as in the reference: it must match too)
+    ok = _run_cli("run", *common, "--steps", "6", "--json-stream", "--restart", ck, "--checkpoint-interval", "3",
+                  cwd=str(tmp_path))
+    assert ok.returncode == 0, ok.stdout[-500:] + ok.stderr[-500:]
+    assert [json.loads(l)["iteration"] for l in ok.stdout.splitlines() if l.strip()] == [4, 5]

@@ -32,6 +32,6 @@ def test_slab_parity(mode):
     world = 2 if n < 4 else 4
     r = _torchrun(world, mode, 29641 + (mode == "peer"))
     print(r.stdout[-3000:])
-    assert r.returncode == 0 and "FAIL" not in r.stdout and r.stdout.count("PARITY") == 6, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "FAIL" not in r.stdout and r.stdout.count("PARITY") == 7, r.stdout[-3000:] + r.stderr[-3000:]
     if mode == "peer":
         assert "peer_kernel=True" in r.stdout      # the equal-slab cases really ran the NVLink kernel
