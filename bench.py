@@ -277,7 +277,7 @@ def run_gpu_arm(args, wl, rank, world):
         e2e = {"value": cells * args.steps / e2e_s / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": int(field_bytes / args.steps + 96),
                "d2h_bytes_per_step": int(field_bytes / args.steps + per_step_scalars),
-               "note": "SimulationDriver.run from host State arrays (pageable numpy): 3 fields H2D before the first "
+               "note": "SimulationDriver.run from host State arrays (page-locked numpy from allocate_state): 3 fields H2D before the first "
                        "step, per-step scalar block + centre-line D2H, 3 fields D2H after the last step, all timed"}
 
     peer_mode = bool(getattr(slab, "peer_mode", False))

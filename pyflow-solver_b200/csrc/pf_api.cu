@@ -209,7 +209,10 @@ int launch_dyn(pf_ctx* c, CgArgs& a, bool unit, cudaStream_t st) {
 template <bool UNIT>
 int launch_cg(pf_ctx* c, CgArgs& a, cudaStream_t st) {
   void* args[] = {&a};
-  PF_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_cg_persistent<UNIT>, dim3(c->cg_grid), dim3(CG_THREADS),
+  // small grids have fewer tiles than co-resident CTAs: launch only as many CTAs as there are tiles, so
+  // that the two grid barriers and partial folds per iteration involve no idle CTAs
+  const int grid = std::max(1, std::min(c->cg_grid, a.ntiles));
+  PF_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_cg_persistent<UNIT>, dim3(grid), dim3(CG_THREADS),
                                          args, 0, st));
   c->launches++;
   return PF_OK;
