@@ -258,27 +258,31 @@ def run_gpu_arm(args, wl, rank, world):
     value = cells * args.steps / (elapsed_ms * 1e-3) / 1e6
 
     # ---- e2e: host arrays -> driver.run K steps -> host arrays -------------------
-    e2e = None
-    if world == 1:
-        for name in ("u", "v", "p"):
-            state.fields[name]                      # D2H now (untimed); marks the fields host-owned
-        drv = SimulationDriver(cfg, state, tracker)
-        barrier()
-        t0 = time.perf_counter()
-        last = None
-        for st, res, diag in drv.run(max_steps=it + args.steps, start_iteration=it):
-            last = (res["continuity"], diag["u_centerline"][1][0])
-        fields_back = [state.fields[name] for name in ("u", "v", "p")]       # D2H inside the timed region
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        it += args.steps
-        field_bytes = sum(a[1:-1, 1:-1].nbytes for a in fields_back)
-        per_step_scalars = 32 * 8 + ny_global * 8
-        e2e = {"value": cells * args.steps / e2e_s / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": int(field_bytes / args.steps + 96),
-               "d2h_bytes_per_step": int(field_bytes / args.steps + per_step_scalars),
-               "note": "SimulationDriver.run from host State arrays (page-locked numpy from allocate_state): 3 fields H2D before the first "
-                       "step, per-step scalar block + centre-line D2H, 3 fields D2H after the last step, all timed"}
+    # (with several GPUs every rank moves its own slab; time = max over ranks)
+    for name in ("u", "v", "p"):
+        state.fields[name]                      # D2H now (untimed); marks the fields host-owned
+    drv = SimulationDriver(cfg, state, tracker)
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for st, res, diag in drv.run(max_steps=it + args.steps, start_iteration=it):
+        last = (res["continuity"], diag["u_centerline"][1][0])
+    fields_back = [state.fields[name] for name in ("u", "v", "p")]       # D2H inside the timed region
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    it += args.steps
+    field_bytes = sum(a[1:-1, 1:-1].nbytes for a in fields_back) * world
+    per_step_scalars = (32 * 8) * world + ny_global * 8
+    e2e = {"value": cells * args.steps / e2e_s / 1e6, "unit": "MLUPS",
+           "h2d_bytes_per_step": int(field_bytes / args.steps + 96 * world),
+           "d2h_bytes_per_step": int(field_bytes / args.steps + per_step_scalars),
+           "note": "SimulationDriver.run from host State arrays (page-locked numpy from allocate_state): 3 fields H2D "
+                   "before the first step, per-step scalar block + centre-line D2H, 3 fields D2H after the last step, "
+                   "all timed; bytes are totals over all ranks"}
 
     peer_mode = bool(getattr(slab, "peer_mode", False))
     if os.environ.get("PF_BENCH_VERBOSE"):

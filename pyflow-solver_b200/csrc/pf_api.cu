@@ -48,6 +48,7 @@ struct pf_ctx {
   bool peers = false;
   int opt_multi_single = 0;
   int opt_sync = 0;
+  int opt_rows_min = 4;            // minimum rows per warp tile of the register-window kernel
   int opt_kernel = 3;              // 3: auto = TMA-fed dynamically scheduled kernel when eligible (nx % 1024 == 0, one GPU),
                                    //    else the register-window kernels; 2: static TMA; 1: register-window only; 0: k_cg_dyn (experimental)        // debug/tuning: run the multi-GPU persistent kernel with one rank
   char err[512] = {0};
@@ -124,7 +125,7 @@ void cg_geometry(const pf_ctx* c, CgArgs& a) {
   const int G = c->cg_grid;
   // Bands: aim for one tile per CTA (a multiple of the grid when the slab is
   // tall enough), at least ~4 rows per warp so halo rows stay a small share.
-  const int rows_min = 4 * a.wy;
+  const int rows_min = c->opt_rows_min * a.wy;
   const int max_bands = std::max(1, s.nyl / rows_min);
   int want = std::max(1, G / a.nchunks);
   a.nbands = std::min(want, max_bands);
@@ -537,6 +538,7 @@ int pf_set_option(pf_ctx* c, const char* key, int value) {
   if (strcmp(key, "cg_multi_single") == 0) { c->opt_multi_single = value; return PF_OK; }
   if (strcmp(key, "cg_sync_opt") == 0) { c->opt_sync = value; return PF_OK; }
   if (strcmp(key, "cg_kernel") == 0) { c->opt_kernel = value; return PF_OK; }
+  if (strcmp(key, "cg_rows_min") == 0 && value >= 1) { c->opt_rows_min = value; return PF_OK; }
   return fail(c, PF_ERR_ARG, "pf_set_option", key);
 }
 

@@ -33,7 +33,8 @@ def allocate_slab_state(nx: int, ny_global: int, rank: int, world: int) -> State
     row0, nyl = slab_rows(ny_global, rank, world)
     if nyl < 2:
         raise ValueError(f"slab of rank {rank} has {nyl} rows; need at least 2 per GPU")
-    st = State(nx=nx, ny=nyl, fields={k: np.zeros((nyl + 2, nx + 2)) for k in ("u", "v", "p")})
+    from ..core.ghost_fields import _zeros
+    st = State(nx=nx, ny=nyl, fields={k: _zeros((nyl + 2, nx + 2)) for k in ("u", "v", "p")})
     st.slab = {"ny_global": int(ny_global), "row_offset": int(row0), "rank": int(rank), "world": int(world)}
     return st
 
