@@ -8,7 +8,7 @@
 
 #include <algorithm>
 
-#include "pf_cg_dyn.cuh"
+#include "pf_cg.cuh"
 #include "pf_cg_generic.cuh"
 #include "pf_cg_tma.cuh"
 #include "pf_comm.h"
@@ -50,7 +50,7 @@ struct pf_ctx {
   int opt_sync = 0;
   int opt_rows_min = 4;            // minimum rows per warp tile of the register-window kernel
   int opt_kernel = 3;              // 3: auto = TMA-fed dynamically scheduled kernel when eligible (nx % 1024 == 0, one GPU),
-                                   //    else the register-window kernels; 2: static TMA; 1: register-window only; 0: k_cg_dyn (experimental)        // debug/tuning: run the multi-GPU persistent kernel with one rank
+                                   //    else the register-window kernels; 2: static TMA tiles; 1: register-window only        // debug/tuning: run the multi-GPU persistent kernel with one rank
   char err[512] = {0};
 };
 
@@ -178,35 +178,6 @@ int reset_trace(pf_ctx* c, cudaStream_t st) {
   return PF_OK;
 }
 
-// Tiles of the dynamically scheduled kernel: ~4 per CTA, >= 8 rows, <= CG_MAX_TILES.
-void dyn_geometry(const pf_ctx* c, CgArgs& a) {
-  const Slab& s = c->s;
-  const int nstrips = (s.nx + STRIP - 1) / STRIP;
-  int wx = 1;
-  while (wx * 2 <= CG_WARPS && wx * 2 <= nstrips) wx *= 2;
-  a.wx = wx;
-  a.wy = CG_WARPS / wx;
-  a.nchunks = (nstrips + wx - 1) / wx;
-  const int G = c->cg_grid;
-  const int rows_min = 8 * a.wy;
-  int nb = (4 * G + a.nchunks - 1) / a.nchunks;
-  nb = std::min(nb, std::max(1, s.nyl / rows_min));
-  nb = std::min(nb, std::max(1, CG_MAX_TILES / a.nchunks));
-  a.nbands = std::max(1, nb);
-  a.ntiles = a.nchunks * a.nbands;
-}
-
-int launch_dyn(pf_ctx* c, CgArgs& a, bool unit, cudaStream_t st) {
-  dyn_geometry(c, a);
-  fill_sync(c, a.y);
-  PF_TRY(reset_trace(c, st));
-  void* args[] = {&a};
-  const void* fn = unit ? (const void*)k_cg_dyn<true> : (const void*)k_cg_dyn<false>;
-  PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->cg_grid), dim3(CG_THREADS), args, 0, st));
-  c->launches++;
-  return PF_OK;
-}
-
 template <bool UNIT>
 int launch_cg(pf_ctx* c, CgArgs& a, cudaStream_t st) {
   void* args[] = {&a};
@@ -272,14 +243,6 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     const void* fn = unit ? (const void*)k_cg_tma<true> : (const void*)k_cg_tma<false>;
     PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(c->tma_grid), dim3(TM_THREADS), args, TM_SMEM_BYTES, st));
     c->launches++;
-  } else if (c->opt_kernel == 0 && (!c->comm || c->peers)) {
-    // production: ONE dynamically scheduled persistent kernel (per rank); with several ranks the halo
-    // rows and the dot-product partials travel over NVLink peer memory inside the kernel
-    if (c->comm) {
-      PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
-      PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
-    }
-    PF_TRY(launch_dyn(c, a, unit, st));
   } else if (c->comm && c->peers) {
     // static-tile persistent kernel per rank over NVLink peer memory (cross-check)
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
@@ -468,13 +431,10 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   int occ_u = 0, occ_g = 0;
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_cg_persistent<true>, CG_THREADS, 0));
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, k_cg_persistent<false>, CG_THREADS, 0));
-  int occ_du = 0, occ_dg = 0;
-  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_du, k_cg_dyn<true>, CG_THREADS, 0));
-  PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dg, k_cg_dyn<false>, CG_THREADS, 0));
   int occ_mu = 0, occ_mg = 0;
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_cg_persistent_multi<true>, CG_THREADS, 0));
   PF_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mg, k_cg_persistent_multi<false>, CG_THREADS, 0));
-  const int occ = std::min(std::min(std::min(occ_u, occ_g), std::min(occ_mu, occ_mg)), std::min(occ_du, occ_dg));
+  const int occ = std::min(std::min(occ_u, occ_g), std::min(occ_mu, occ_mg));
   if (occ < 1) {
     pf_destroy(c);
     return PF_ERR_UNSUPPORTED;

@@ -29,7 +29,7 @@
 // x and the old search direction, which nobody re-reads soon, are streamed
 // with evict-first hints so they do not displace r and p in L2.
 //
-// Rows are processed in batches of CG_U: all loads of a batch are issued, then
+// Rows are processed in batches (CG_UA / CG_UB rows): all loads of a batch are issued, then
 // consumed.  Rows strictly inside a band (the vast majority) take a LEAN path
 // with no boundary masks; only the first/last rows of a band (which may touch
 // the domain boundary, the Jacobi ring or the pinned cell) and strips on the
@@ -59,7 +59,6 @@ constexpr int STRIP = 64;     // columns per warp
 #ifndef PF_CG_MINB
 #define PF_CG_MINB 2
 #endif
-constexpr int CG_U = 4;        // rows per batch of the experimental k_cg_dyn
 constexpr int CG_UA = PF_CG_UA;   // rows fetched per batch in phase A (loads in flight per lane: 2 arrays)
 constexpr int CG_UB = PF_CG_UB;   // ... in phase B (3 arrays)
 constexpr int CG_MAX_GRID = 2048;
@@ -79,7 +78,7 @@ struct CgSync {
   double* gsum;                  // local: [2][4] sums over all ranks for the local CTAs
   unsigned long long* epoch;     // local: epoch counter persisted between launches
   unsigned long long* err;       // local: != 0 after a spin-wait timeout
-  unsigned long long* tickets;   // local: monotonic tile-ticket counter (k_cg_dyn)
+  unsigned long long* tickets;   // local: monotonic tile-ticket counter (k_cg_tmad)
   unsigned long long* ticket_base;  // local: first ticket of the next launch (persisted)
   unsigned long long* peer_flags[CG_MAX_RANKS];
   double* peer_mbox[CG_MAX_RANKS];

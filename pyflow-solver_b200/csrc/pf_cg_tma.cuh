@@ -22,9 +22,12 @@
 
 #include <cooperative_groups.h>
 
-#include "pf_cg_dyn.cuh"
+#include "pf_cg.cuh"
 
 namespace pf {
+
+constexpr int CG_MAX_TILES = 8192;           // per-tile partial sums of the dynamically scheduled kernel
+static_assert(PF_TRACE_OFFSET == 2 * CG_MAX_TILES, "trace region sits behind the tile partials");
 
 constexpr int TM_WARPS = 16;
 constexpr int TM_THREADS = (TM_WARPS + 1) * 32;

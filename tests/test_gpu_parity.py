@@ -290,6 +290,26 @@ def test_default_config_trajectory_within_reference_noise(golden):
         assert rel(st.fields[f], golden["trajectories"][f"{name}/{f}"]) < 100 * meta["noise_floor"][f]
 
 
+def test_trajectory_tma_kernel_vs_live_oracle():
+    """A 1024-wide grid takes the TMA-fed, dynamically scheduled CG kernel (nx % 1024 == 0):
+    whole steps against the oracle, QUICK, truncated solves."""
+    from pyflow.core.ghost_fields import allocate_state
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    cfg = _cfg(dict(nx=1024, ny=96, Re=1000.0, advection_scheme="quick", lin_maxiter=150))
+    steps = 4
+    ost, odiags = orc.run(cfg, steps)
+    st = allocate_state(1024, 96)
+    tr = ResidualManager()
+    for it in range(steps):
+        _, res, diag = step(cfg, st, tr, it)
+        assert diag["dt"] == odiags[it]["dt"]
+        assert st.meta["cg_true_iterations"] == odiags[it]["true_iterations"]
+    for f in ("u", "v", "p"):
+        e = rel(st.fields[f][1:-1, 1:-1], orc.interior(ost.fields[f]))
+        assert e < 1e-9, (f, e)
+
+
 def test_trajectory_vs_live_oracle_512():
     """Config 2 grid (512^2, Re=1000, quick, 300 its), first steps, against the
     oracle run on the host in this very test."""
