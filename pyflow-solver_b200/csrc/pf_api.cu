@@ -226,6 +226,7 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     }
     fill_sync(c, a.y);
     PF_CUDA(c, cudaMemsetAsync(a.y.err, 0, sizeof(unsigned long long), st));
+    PF_TRY(reset_trace(c, st));
     void* args[] = {&a};
     const void* fn = c->comm ? (unit ? (const void*)k_cg_tmad<true, true> : (const void*)k_cg_tmad<false, true>)
                              : (unit ? (const void*)k_cg_tmad<true, false> : (const void*)k_cg_tmad<false, false>);

@@ -743,7 +743,7 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
             break;
           }
         }
-        __threadfence_system();      // acquire: the peers' halo-row stores are visible now
+        (void)ld_acquire_sys((const unsigned long long*)src);   // acquire: the peers' halo-row stores are visible now
         s_peer[tid][0] = k.v[0]; s_peer[tid][1] = k.v[1]; s_peer[tid][2] = k.v[2];
       }
       __syncthreads();
@@ -771,7 +771,7 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
         break;
       }
     }
-    __threadfence();                 // acquire side: later loads (incl. halo rows written by peers) see fresh data
+    (void)ld_acquire_gpu((const unsigned long long*)y.gsum);   // acquire: later loads (incl. halo rows written by peers) see fresh data
     s_out[0] = k.v[0]; s_out[1] = k.v[1]; s_out[2] = k.v[2];
     s_out[3] = (ld_relaxed_u64(y.err) == 0ULL) ? 1.0 : 0.0;
     if (tr && blockIdx.x == 0) tr[6] = gtime();

@@ -747,10 +747,16 @@ __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, 
   }
 }
 
-// Phase end for several GPUs: like grid_exchange (pf_cg.cuh) but the last CTA folds the
-// per-TILE partials; packets, fences and the rank-ordered sum are identical.
+// Phase end for several GPUs.  Every CTA arrives (gpu-scope release: its stores, peer halo rows
+// included, become visible to the CTA that arrives last); the last CTA folds the per-TILE partials,
+// issues ONE system fence (cumulative: it also publishes the halo rows pushed by the other CTAs) and
+// writes one 32-byte packet {epoch, v0, v1, v2} into the mailbox of EVERY rank, its own included.
+// All CTAs of all ranks then poll their local mailbox directly -- no separate local release hop --
+// and add the packets in rank order, so every CTA of every GPU holds bit-identical sums.
 template <int NV>
-__device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long long e, double (&out)[NV], double* sm) {
+__device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long long e, double (&out)[NV], double* sm,
+                                              unsigned long long e0 = 0) {
+  unsigned long long* tr = trace_slot(a, e0, e);
   __shared__ int s_last;
   __shared__ double s_out[4];
   __shared__ double s_peer[CG_MAX_RANKS][3];
@@ -759,7 +765,8 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
   const int par = (int)(e & 1ULL);
   __syncthreads();                   // every thread's stores (fields, tile partials, peer halos) before thread 0's fence
   if (tid == 0) {
-    __threadfence_system();
+    __threadfence();
+    if (tr) { const unsigned long long t = gtime(); atomicMin(tr + 0, t); atomicMax(tr + 1, t); }
     s_last = (atomicAdd(y.arrive, 1ULL) == e * (unsigned long long)G - 1ULL) ? 1 : 0;
   }
   __syncthreads();
@@ -773,46 +780,38 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
     }
     block_sum_n<3>(loc, sm);
     if (tid == 0) {
-      __threadfence_system();        // the halo rows pushed by the other CTAs of this GPU go out before the packet
+      if (tr) tr[2] = gtime();
+      __threadfence_system();
       const size_t slot = (size_t)(par * CG_MAX_RANKS + y.rank) * sizeof(Packet);
       for (int q = 0; q < R; ++q) st_packet_sys((char*)y.peer_mbox[q] + slot, e, loc[0], loc[1], loc[2]);
-    }
-    if (tid < R) {
-      const long long t0 = clock64();
-      Packet k;
-      const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * sizeof(Packet);
-      while ((k = ld_packet_sys(src)).epoch != e) {
-        if (clock64() - t0 > CG_SPIN_LIMIT) {
-          atomicExch(y.err, 1ULL);
-          break;
-        }
-      }
-      __threadfence_system();
-      s_peer[tid][0] = k.v[0]; s_peer[tid][1] = k.v[1]; s_peer[tid][2] = k.v[2];
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int k = 0; k < 3; ++k) {  // rank order, identical on every GPU
-        double sum = 0.0;
-        for (int q = 0; q < R; ++q) sum += s_peer[q][k];
-        loc[k] = sum;
-      }
-      __threadfence();
-      st_packet_gpu(y.gsum, e, loc[0], loc[1], loc[2]);
+      if (tr) tr[3] = gtime();
     }
   }
-  if (tid == 0) {
+  if (tid < R) {
     const long long t0 = clock64();
     Packet k;
-    while ((k = ld_packet_gpu(y.gsum)).epoch != e) {
+    const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * sizeof(Packet);
+    while ((k = ld_packet_sys(src)).epoch != e) {
       if (clock64() - t0 > CG_SPIN_LIMIT) {
         atomicExch(y.err, 1ULL);
         break;
       }
     }
-    __threadfence();
-    s_out[0] = k.v[0]; s_out[1] = k.v[1]; s_out[2] = k.v[2];
+    if (tr && blockIdx.x == 0) tr[4 + (tid & 1)] = gtime();      // when block 0 saw rank tid's packet
+    // acquire (LDG.STRONG.SYS + L1 invalidate; a full fence.sys = MEMBAR.ALL.SYS cost ~4 us here): the
+    // field data of this GPU's other CTAs and the peers' halo rows are visible to what follows
+    (void)ld_acquire_sys((const unsigned long long*)src);
+    s_peer[tid][0] = k.v[0]; s_peer[tid][1] = k.v[1]; s_peer[tid][2] = k.v[2];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < 3; ++k) {    // rank order, identical everywhere
+      double sum = 0.0;
+      for (int q = 0; q < R; ++q) sum += s_peer[q][k];
+      s_out[k] = sum;
+    }
     s_out[3] = (ld_relaxed_u64(y.err) == 0ULL) ? 1.0 : 0.0;
+    if (tr && blockIdx.x == 0) tr[6] = gtime();
   }
   __syncthreads();
 #pragma unroll
@@ -851,6 +850,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
   const unsigned long long per_phase = (unsigned long long)a.ntiles + (unsigned long long)G;
   unsigned long long phase = 0;
   unsigned long long e = *((volatile unsigned long long*)a.y.epoch);   // cross-GPU barrier epochs (MULTI)
+  const unsigned long long e0 = e;
   // strip kind of this warp is the same for every tile of a chunk COLUMN position, but chunks differ:
   // it depends on the tile, so it is resolved per phase call below from the warp's column only when
   // there is a single chunk; in general X_WALL applies to warp 0 of chunk 0 and warp 15 of the last chunk.
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
       double pq;
       if (MULTI) {
         double o1[1];
-        ok = tile_exchange<1>(a, ++e, o1, sm);
+        ok = tile_exchange<1>(a, ++e, o1, sm, e0);
         if (!ok) break;
         pq = o1[0];
       } else {
@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
       double rz;
       if (MULTI) {
         double o2[2];
-        ok = tile_exchange<2>(a, ++e, o2, sm);
+        ok = tile_exchange<2>(a, ++e, o2, sm, e0);
         if (!ok) break;
         rr = o2[0];
         rz = o2[1];

@@ -22,7 +22,7 @@ for r in range(world):
         print(f"rank {rank} cg_ms {st.meta['cg_ms']:.2f}")
         prev_exit = None
         for k in range(8):
-            first, last, fold, pub, seen, rel, b0 = t[k][:7]
-            print(f"  barrier {k}: spread first->last arrival {(last-first)/1e3:7.2f} us | fold {(fold-last)/1e3:6.2f} | publish {(pub-fold)/1e3:6.2f} | peers seen {(seen-pub)/1e3:6.2f} | release {(rel-seen)/1e3:6.2f} | blk0 out {(b0-rel)/1e3:6.2f} | phase since prev exit {((first-prev_exit)/1e3 if prev_exit else 0):7.2f}", flush=True)
+            first, last, fold, pub, seen0, seen1, b0 = t[k][:7]
+            print(f"  barrier {k}: spread first->last arrival {(last-first)/1e3:7.2f} us | fold {(fold-last)/1e3:6.2f} | publish {(pub-fold)/1e3:6.2f} | blk0 saw rank0 pkt {(seen0-pub)/1e3:6.2f} rank1 pkt {(seen1-pub)/1e3:6.2f} | blk0 out {(b0-max(seen0,seen1))/1e3:6.2f} | total last-arrival->out {(b0-last)/1e3:6.2f} | phase since prev exit {((first-prev_exit)/1e3 if prev_exit else 0):7.2f}", flush=True)
             prev_exit = b0
 dist.destroy_process_group()
