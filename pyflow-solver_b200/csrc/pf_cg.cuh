@@ -481,6 +481,28 @@ __device__ __forceinline__ void phaseB_warp(const CgArgs& a, const double* p, do
   else phaseB_strip<UNIT, X_IN, DIR>(a, p, x, r, peer_lo, peer_hi, alpha, w, acc_rr, acc_rz);
 }
 
+// Sum of NV doubles per thread over the block with ONE pair of barriers; every thread
+// returns the totals.  sm holds >= 32*NV doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sm[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = 0.0;
+    for (int q = 0; q < nw; ++q) t += sm[k * 32 + q];
+    v[k] = t;
+  }
+}
+
 // Fold per-CTA partials; identical in every CTA.
 __device__ __forceinline__ double fold_partials(const double* part, int n, double* sm) {
   double acc = 0.0;
@@ -491,7 +513,7 @@ __device__ __forceinline__ double fold_partials(const double* part, int n, doubl
 template <bool UNIT>
 __global__ void __launch_bounds__(CG_THREADS, PF_CG_MINB) k_cg_persistent(CgArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sm[32];
+  __shared__ double sm[2 * 32];
   const int G = gridDim.x;
   const int bid = blockIdx.x;
 
@@ -536,15 +558,28 @@ __global__ void __launch_bounds__(CG_THREADS, PF_CG_MINB) k_cg_persistent(CgArgs
         const WarpTile w = warp_tile(a, bid + k * G);
         if (w.active) phaseB_warp<UNIT, -1>(a, pnext, a.x, a.r, alpha, w, arr, arz);
       }
-      arr = block_sum(arr, sm);
-      arz = block_sum(arz, sm);
+      {                                              // both partials with one block reduction
+        double v2[2] = {arr, arz};
+        block_sum_n<2>(v2, sm);
+        arr = v2[0];
+        arz = v2[1];
+      }
       if (threadIdx.x == 0) {
         a.part[CG_MAX_GRID + bid] = arr;
         a.part[2 * CG_MAX_GRID + bid] = arz;
       }
       grid.sync();
-      rr = fold_partials(a.part + CG_MAX_GRID, G, sm);
-      const double rz = fold_partials(a.part + 2 * CG_MAX_GRID, G, sm);
+      double rz;
+      {                                              // both folds in one pass, one block reduction
+        double f[2] = {0.0, 0.0};
+        for (int q = threadIdx.x; q < G; q += blockDim.x) {
+          f[0] += ld_cg(a.part + CG_MAX_GRID + q);
+          f[1] += ld_cg(a.part + 2 * CG_MAX_GRID + q);
+        }
+        block_sum_n<2>(f, sm);
+        rr = f[0];
+        rz = f[1];
+      }
       rho_prev = rho;
       rho = rz;
       double* tmp = pcur; pcur = pnext; pnext = tmp;
@@ -656,28 +691,6 @@ __device__ __forceinline__ void st_packet_gpu(void* p, unsigned long long e, dou
 __device__ __forceinline__ void st_packet_sys(void* p, unsigned long long e, double v0, double v1, double v2) {
   asm volatile("st.relaxed.sys.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(e), "l"(__double_as_longlong(v0)),
                "l"(__double_as_longlong(v1)), "l"(__double_as_longlong(v2)) : "memory");
-}
-
-// Sum of NV doubles per thread over the block with ONE pair of barriers; every thread
-// returns the totals.  sm holds >= 32*NV doubles.
-template <int NV>
-__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* sm) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) sm[k * 32 + warp] = v[k];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double t = 0.0;
-    for (int q = 0; q < nw; ++q) t += sm[k * 32 + q];
-    v[k] = t;
-  }
 }
 
 // Ends a phase on 1..8 GPUs.  Returns false if a spin-wait timed out (error flag).
