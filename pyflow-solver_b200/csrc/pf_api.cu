@@ -10,6 +10,7 @@
 
 #include "pf_cg.cuh"
 #include "pf_cg_generic.cuh"
+#include "pf_cg_small.cuh"
 #include "pf_cg_tma.cuh"
 #include "pf_comm.h"
 #include "pf_kernels.cuh"
@@ -37,6 +38,9 @@ struct pf_ctx {
   int cg_grid = 0;
   int gen_grid = 0;                // co-resident CTAs of k_cg_generic
   int tma_grid = 0;                // co-resident CTAs of k_cg_tma (0: unavailable)
+  bool small_ok = false;           // k_cg_small usable (dynamic shared memory attribute set)
+  double* small_halo = nullptr;    // [sm_count][2][pitch] boundary rows of r (k_cg_small)
+  double* small_part = nullptr;    // [2][sm_count][4]
   long long launches = 0;          // kernels of this library launched so far
   bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
   dim3 sgrid;                      // grid of the simple kernels
@@ -87,9 +91,9 @@ int pitch_of(int64_t nx) { return (int)align_up((size_t)nx, PITCH_ALIGN); }
 size_t field_elems_of(int64_t nx, int64_t nyl) { return (size_t)(nyl + 2 * HALO) * (size_t)pitch_of(nx); }
 
 struct SmallLayout {
-  size_t red_part, red_counter, scal, cg_part, sync, center, total;
+  size_t red_part, red_counter, scal, cg_part, sync, center, small_halo, small_part, total;
 };
-SmallLayout small_layout(int64_t nyl) {
+SmallLayout small_layout(int64_t nyl, int64_t nx = 0) {
   SmallLayout L{};
   size_t o = 0;
   L.red_part = o;    o = align_up(o + sizeof(double) * MAX_RED_VALS * MAX_RED_BLOCKS, ALIGN);
@@ -98,6 +102,8 @@ SmallLayout small_layout(int64_t nyl) {
   L.cg_part = o;     o = align_up(o + sizeof(double) * PF_PART_DOUBLES, ALIGN);
   L.sync = o;        o = align_up(o + 1024, ALIGN);
   L.center = o;      o = align_up(o + sizeof(double) * (size_t)nyl, ALIGN);
+  L.small_halo = o;  o = align_up(o + sizeof(double) * 2 * 256 * (size_t)(nx <= 2048 ? align_up((size_t)nx, PITCH_ALIGN) : 0), ALIGN);
+  L.small_part = o;  o = align_up(o + sizeof(double) * 2 * 256 * 4, ALIGN);
   L.total = o;
   return L;
 }
@@ -208,7 +214,24 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
   cg_geometry(c, a);
   const bool unit = is_unit(dx, dy);
-  if (c->opt_kernel == 3 && (!c->comm || c->peers) && c->tma_grid > 0 && s.nx % TM_CW == 0 && s.nyl >= 2) {
+  const int small_rows = (s.nyl + c->sm_count - 1) / c->sm_count;
+  const size_t small_smem = sizeof(double) * (size_t)s.nx * ((size_t)(small_rows + 2) * 2 + small_rows);
+  if (c->opt_kernel == 3 && !c->comm && c->small_ok && s.nx % 2 == 0 && s.nx <= 2048 && c->sm_count <= 256 &&
+      (long long)small_rows * (s.nx / 2) <= (long long)SM_PAIRS * SM_THREADS && small_smem <= (size_t)SM_MAX_SMEM) {
+    // shared-memory-resident solve for small grids (config 2): x, r, p never leave the SMs
+    SmallArgs sa{};
+    sa.s = s; sa.b = c->b; sa.x = c->x; sa.rhalo = c->small_halo; sa.part = c->small_part; sa.scal = c->scal;
+    sa.arrive = (unsigned long long*)(c->ws_base + c->sync_off) + 6;     // own counter / epoch words of the sync block
+    sa.epoch = (unsigned long long*)(c->ws_base + c->sync_off) + 7;
+    sa.err = (unsigned long long*)(c->ws_base + c->sync_off) + 3;
+    sa.dx = dx; sa.dy = dy; sa.invd = invd; sa.tol = tol; sa.maxiter = maxiter; sa.rows = small_rows;
+    PF_CUDA(c, cudaMemsetAsync(sa.err, 0, sizeof(unsigned long long), st));
+    const int grid = (s.nyl + small_rows - 1) / small_rows;
+    void* args[] = {&sa};
+    const void* fn = unit ? (const void*)k_cg_small<true> : (const void*)k_cg_small<false>;
+    PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SM_THREADS), args, small_smem, st));
+    c->launches++;
+  } else if (c->opt_kernel == 3 && (!c->comm || c->peers) && c->tma_grid > 0 && s.nx % TM_CW == 0 && s.nyl >= 2) {
     // TMA-fed sweeps, dynamically scheduled 1024-column tiles (16 rows, more for huge slabs), one CTA per SM;
     // with several ranks: halo rows + dot-product partials over NVLink peer memory inside the same kernel
     a.nchunks = s.nx / TM_CW;
@@ -372,7 +395,7 @@ const char* pf_last_error(const pf_ctx* ctx) { return ctx ? ctx->err : ""; }
 size_t pf_workspace_bytes(int64_t nx, int64_t ny_local) {
   if (nx < 2 || ny_local < 1) return 0;
   const size_t fb = align_up(field_elems_of(nx, ny_local) * sizeof(double), ALIGN);
-  return NFIELDS * fb + small_layout(ny_local).total + ALIGN;
+  return NFIELDS * fb + small_layout(ny_local, nx).total + ALIGN;
 }
 
 int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int64_t row_offset, int device,
@@ -408,12 +431,14 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   c->ws_base = base;
   c->field_stride = fb;
   char* small = base + (size_t)NFIELDS * fb;
-  const SmallLayout L = small_layout(ny_local);
+  const SmallLayout L = small_layout(ny_local, nx);
   c->red_part = (double*)(small + L.red_part);
   c->red_counter = (unsigned*)(small + L.red_counter);
   c->scal = (double*)(small + L.scal);
   c->cg_part = (double*)(small + L.cg_part);
   c->center = (double*)(small + L.center);
+  c->small_halo = (double*)(small + L.small_halo);
+  c->small_part = (double*)(small + L.small_part);
   c->sync_off = (size_t)NFIELDS * fb + L.sync;
   c->sgrid = simple_grid(c->s);
 #define PF_CREATE_CUDA(call)                                  \
@@ -468,6 +493,9 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
     }
     (void)cudaGetLastError();
   }
+  c->small_ok = cudaFuncSetAttribute(k_cg_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_SMEM) == cudaSuccess &&
+                cudaFuncSetAttribute(k_cg_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_SMEM) == cudaSuccess;
+  (void)cudaGetLastError();
   c->gen_grid = std::min(c->sm_count * std::max(1, std::min(occ_gen_u, occ_gen_g)), CG_MAX_GRID);
 #undef PF_CREATE_CUDA
   *out = c;

@@ -1,0 +1,243 @@
+// pf_cg_small.cuh -- CG for grids small enough to LIVE IN SHARED MEMORY (config 2: 512^2).
+//
+// At 512^2 a vector is 2 MiB: the streaming kernels run out of L2 and an iteration is
+// two grid barriers plus two latency-bound sweeps (10.8 us).  Here x, r and p stay in
+// the shared memory of the CTA that owns their rows for the WHOLE solve (1 CTA per SM,
+// a band of rows x all columns each); A p is a pure shared-memory stencil; q stays in
+// registers between the two phases; only the two boundary rows of r travel through
+// global memory (L2) per iteration -- the halo rows of p are recomputed redundantly
+// from them with the owner's exact arithmetic, so no third barrier is needed.  The
+// two reductions per iteration (classical CG) use a lean arrive / poll barrier whose
+// release is folded into the reduction: every CTA's warp 0 adds the per-CTA partials in
+// CTA order (bit-identical everywhere).  Same operation order as pf_cg.cuh / scipy.
+#pragma once
+
+#include "pf_cg.cuh"
+
+namespace pf {
+
+constexpr int SM_THREADS = 512;
+constexpr int SM_PAIRS = 8;                       // column pairs per thread, at most
+constexpr int SM_MAX_SMEM = 200 * 1024;
+
+struct SmallArgs {
+  Slab s;
+  const double* b;          // rhs (= initial r), device field layout
+  double* x;                // solution out (field layout)
+  double* rhalo;            // [G][2][pitch]: first / last row of r of every CTA
+  double* part;             // [2][G][4] per-CTA partials, double-buffered by barrier parity
+  double* scal;
+  unsigned long long* arrive;   // monotonic arrival counter (sync block)
+  unsigned long long* epoch;    // persisted barrier epoch
+  unsigned long long* err;      // != 0 after a spin-wait timeout
+  double dx, dy, invd, tol;
+  int maxiter;
+  int rows;                 // rows per CTA (last CTA may own fewer)
+};
+
+__device__ __forceinline__ int small_smem_bytes(int nx, int rows) {
+  return (int)sizeof(double) * nx * ((rows + 2) * 2 + rows);
+}
+
+// All-reduce of NV doubles over the grid; barrier included.  Every thread returns the sums.
+template <int NV>
+__device__ __forceinline__ void small_allreduce(const SmallArgs& a, unsigned long long e, double (&v)[NV], double* sm,
+                                                double* s_res) {
+  const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // partials are double-buffered by parity: a fast CTA may already write its e+1 partial while a slow
+  // one still reads the e partials; it cannot reach e+2 before the slow one arrived at e+1
+  double* part = a.part + (size_t)(e & 1ULL) * (size_t)G * 4;
+  block_sum_n<NV>(v, sm);
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) part[blockIdx.x * 4 + k] = v[k];
+    __threadfence();                                   // release: partials + this CTA's halo rows
+    atomicAdd(a.arrive, 1ULL);
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      const unsigned long long target = e * (unsigned long long)G;
+      const long long t0 = clock64();
+      while (ld_relaxed_u64(a.arrive) < target) {
+        if (clock64() - t0 > CG_SPIN_LIMIT) {            // never hang the GPU
+          atomicExch(a.err, 1ULL);
+          break;
+        }
+      }
+      (void)ld_acquire_gpu(a.arrive);
+    }
+    __syncwarp();
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (int q = lane; q < G; q += 32) {               // CTA order within a lane, fixed xor tree across lanes
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc[k] += ld_cg(part + q * 4 + k);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      acc[k] = warp_sum(acc[k]);
+      if (lane == 0) s_res[k] = acc[k];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = s_res[k];
+  __syncthreads();
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(SM_THREADS, 1) k_cg_small(SmallArgs a) {
+  extern __shared__ __align__(16) double smem_d[];
+  __shared__ double sm[3 * 32];
+  __shared__ double s_res[4];
+  const Slab& s = a.s;
+  const int nx = s.nx, G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+  const int j0 = bid * a.rows;
+  const int j1 = (j0 + a.rows > s.nyl) ? s.nyl : j0 + a.rows;
+  const int R = j1 - j0;                              // >= 1 by construction
+  // shared layout: r_s[(rows+2)][nx], p_s[(rows+2)][nx] (row 0 / R+1 = halo), x_s[rows][nx]
+  double* r_s = smem_d;
+  double* p_s = r_s + (size_t)(a.rows + 2) * nx;
+  double* x_s = p_s + (size_t)(a.rows + 2) * nx;
+  const int hp = nx / 2;                              // column pairs per row
+  const int npairs = R * hp;                          // own cells, in pairs
+  const int hpairs = (R + 2) * hp;                    // incl. the two halo rows
+
+  auto invd_of = [&](int jg, int i) {
+    const bool ring = (i == 0) || (i == nx - 1) || (jg == 0) || (jg == s.nyg - 1);
+    return ring ? 1.0 : a.invd;
+  };
+
+  // ---- load r = b (own rows + halo rows), x = 0, p = 0
+  for (int idx = tid; idx < hpairs; idx += SM_THREADS) {
+    const int lr = idx / hp, c = (idx % hp) * 2;      // lr: 0 = halo below, 1..R own, R+1 = halo above
+    const int jl = j0 + lr - 1;
+    double2 v = make_double2(0.0, 0.0);
+    if (jl >= 0 && jl < s.nyl) v = ld2(a.b + cell(s, jl, c));
+    *reinterpret_cast<double2*>(r_s + (size_t)lr * nx + c) = v;
+    *reinterpret_cast<double2*>(p_s + (size_t)lr * nx + c) = make_double2(0.0, 0.0);
+  }
+  for (int idx = tid; idx < npairs; idx += SM_THREADS)
+    *reinterpret_cast<double2*>(x_s + (size_t)(idx / hp) * nx + (idx % hp) * 2) = make_double2(0.0, 0.0);
+  __syncthreads();
+
+  const double bb = ld_cg(a.scal + S_BB);
+  const double bnorm = sqrt(bb);
+  const double t0 = a.tol * bnorm;
+  const double atol = (t0 > 0.0) ? t0 : 0.0;
+  int iters = 0, info = a.maxiter;
+  double rr = bb, rho = ld_cg(a.scal + S_BZ), rho_prev = 0.0;
+  unsigned long long e = *((volatile unsigned long long*)a.epoch);
+
+  if (bnorm == 0.0) {
+    info = 0;
+  } else {
+    for (int it = 0; it < a.maxiter; ++it) {
+      if (sqrt(rr) < atol) { info = 0; break; }
+      const bool first = (it == 0);
+      const double beta = first ? 0.0 : rho / rho_prev;
+      // ---- phase A.1: p = (p*beta) + M r on own rows AND the two halo rows
+      for (int idx = tid; idx < hpairs; idx += SM_THREADS) {
+        const int lr = idx / hp, c = (idx % hp) * 2;
+        const int jg = s.row0 + j0 + lr - 1;
+        if (jg < 0 || jg >= s.nyg) continue;
+        const size_t o = (size_t)lr * nx + c;
+        const double2 rv = *reinterpret_cast<const double2*>(r_s + o);
+        const double za = invd_of(jg, c) * rv.x, zb = invd_of(jg, c + 1) * rv.y;
+        double2 pv;
+        if (first) {
+          pv = make_double2(za, zb);
+        } else {
+          const double2 po = *reinterpret_cast<const double2*>(p_s + o);
+          pv = make_double2((po.x * beta) + za, (po.y * beta) + zb);
+        }
+        *reinterpret_cast<double2*>(p_s + o) = pv;
+      }
+      __syncthreads();
+      // ---- phase A.2: q = A p on own rows (kept in registers), p.q
+      double qa[SM_PAIRS], qb[SM_PAIRS];
+      double v1[1] = {0.0};
+#pragma unroll
+      for (int k = 0; k < SM_PAIRS; ++k) {
+        const int idx = tid + k * SM_THREADS;
+        qa[k] = 0.0; qb[k] = 0.0;
+        if (idx < npairs) {
+          const int lr = idx / hp + 1, c = (idx % hp) * 2;
+          const int jg = s.row0 + j0 + lr - 1;
+          const double* pc = p_s + (size_t)lr * nx + c;
+          const bool hs = jg > 0, hn = jg < s.nyg - 1;
+          const bool hw = c > 0, he_b = c + 1 < nx - 1;
+          const double pa = pc[0], pb = pc[1];
+          const double w = hw ? pc[-1] : 0.0, ee = he_b ? pc[2] : 0.0;
+          const double sa = hs ? pc[-nx] : 0.0, sb = hs ? pc[-nx + 1] : 0.0;
+          const double na = hn ? pc[nx] : 0.0, nb = hn ? pc[nx + 1] : 0.0;
+          double q0 = neg_lap<UNIT>(pa, w, pb, sa, na, hw, true, hs, hn, a.dx, a.dy);
+          double q1 = neg_lap<UNIT>(pb, pa, ee, sb, nb, true, he_b, hs, hn, a.dx, a.dy);
+          if (jg == 0 && c == 0) q0 = pa;               // pinned row
+          qa[k] = q0; qb[k] = q1;
+          v1[0] += pa * q0;
+          v1[0] += pb * q1;
+        }
+      }
+      small_allreduce<1>(a, ++e, v1, sm, s_res);
+      const double alpha = rho / v1[0];
+      // ---- phase B: x += alpha p ; r -= alpha q ; publish the boundary rows of r
+      double v2[2] = {0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < SM_PAIRS; ++k) {
+        const int idx = tid + k * SM_THREADS;
+        if (idx < npairs) {
+          const int lr = idx / hp + 1, c = (idx % hp) * 2;
+          const int jg = s.row0 + j0 + lr - 1;
+          const size_t o = (size_t)lr * nx + c;
+          const double2 pv = *reinterpret_cast<const double2*>(p_s + o);
+          double2 xv = *reinterpret_cast<double2*>(x_s + (size_t)(lr - 1) * nx + c);
+          double2 rv = *reinterpret_cast<double2*>(r_s + o);
+          xv.x = xv.x + alpha * pv.x;
+          xv.y = xv.y + alpha * pv.y;
+          rv.x = rv.x - alpha * qa[k];
+          rv.y = rv.y - alpha * qb[k];
+          *reinterpret_cast<double2*>(x_s + (size_t)(lr - 1) * nx + c) = xv;
+          *reinterpret_cast<double2*>(r_s + o) = rv;
+          if (lr == 1) st2(a.rhalo + ((size_t)bid * 2 + 0) * s.pitch + c, rv.x, rv.y);
+          if (lr == R) st2(a.rhalo + ((size_t)bid * 2 + 1) * s.pitch + c, rv.x, rv.y);
+          v2[0] += rv.x * rv.x;
+          v2[1] += rv.x * (invd_of(jg, c) * rv.x);
+          v2[0] += rv.y * rv.y;
+          v2[1] += rv.y * (invd_of(jg, c + 1) * rv.y);
+        }
+      }
+      small_allreduce<2>(a, ++e, v2, sm, s_res);
+      rr = v2[0];
+      rho_prev = rho;
+      rho = v2[1];
+      ++iters;
+      // ---- fetch the neighbours' boundary rows of r into the halo rows (visible after the barrier)
+      for (int idx = tid; idx < 2 * hp; idx += SM_THREADS) {
+        const int side = idx / hp, c = (idx % hp) * 2;
+        const int nb = side == 0 ? bid - 1 : bid + 1;
+        if (nb >= 0 && nb < G) {
+          const double* src = a.rhalo + ((size_t)nb * 2 + (side == 0 ? 1 : 0)) * s.pitch + c;
+          const double2 v = make_double2(ld_cg(src), ld_cg(src + 1));   // L2: written by another SM this iteration
+          *reinterpret_cast<double2*>(r_s + (size_t)(side == 0 ? 0 : R + 1) * nx + c) = v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- write x back
+  for (int idx = tid; idx < npairs; idx += SM_THREADS) {
+    const int lr = idx / hp, c = (idx % hp) * 2;
+    const double2 xv = *reinterpret_cast<const double2*>(x_s + (size_t)lr * nx + c);
+    st2(a.x + cell(s, j0 + lr, c), xv.x, xv.y);
+  }
+  if (bid == 0 && tid == 0) {
+    a.scal[S_INFO] = (ld_relaxed_u64(a.err) == 0ULL) ? (double)info : -2.0;
+    a.scal[S_ITERS] = (double)iters;
+    a.scal[S_RR] = rr;
+    *a.epoch = e;
+  }
+}
+
+}  // namespace pf

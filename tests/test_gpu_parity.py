@@ -272,6 +272,28 @@ def test_trajectory_vs_golden(golden, name):
     assert not rows[:, 9].any()
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("name", ["quick128_trunc", "quick40x24_spacing", "upwind17x33_nopc"])
+def test_trajectory_with_forced_cg_kernel(golden, monkeypatch, name, kernel):
+    """Small grids default to the shared-memory-resident kernel; the register-window kernel
+    (cg_kernel=1) and the static TMA path selector (cg_kernel=2, falls back to register-window for
+    these widths) must give the same physics."""
+    from pyflow.core.ghost_fields import allocate_state
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    monkeypatch.setenv("PYFLOW_B200_OPTIONS", f"cg_kernel={kernel}")
+    meta = golden["trajectories_meta"][name]
+    g = golden["trajectories"]
+    cfg = _cfg(meta["cfg"])
+    st = allocate_state(cfg.nx, cfg.ny)
+    tr = ResidualManager()
+    for it in range(meta["steps"]):
+        step(cfg, st, tr, it)
+    for f in ("u", "v", "p"):
+        tol = max(1e-9, 100 * meta["noise_floor"][f])
+        assert rel(st.fields[f][1:-1, 1:-1], g[f"{name}/{f}"][1:-1, 1:-1]) < tol
+
+
 def test_default_config_trajectory_within_reference_noise(golden):
     """Config 1 (64^2, 300 its) is truncated midway: even reference-vs-reference
     differs by 1e-5..1e-3; the GPU must stay inside that band."""
