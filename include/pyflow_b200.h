@@ -117,6 +117,11 @@ int pf_step(pf_ctx* ctx, const pf_step_params* params, pf_step_out* out, void* s
  * (ny_local doubles) as of the last pf_step / pf_upload.                     */
 int pf_centerline(pf_ctx* ctx, double* host_out, void* stream);
 
+/* driver/simulation_driver.py:126-130 (the alternate, dict-payload driver): mean and
+ * mean-free 2-norm of fluid_ops.divergence(u, v, dx, dy) of the device fields:
+ * out = { mean(div), ||div - mean(div)|| }.                                       */
+int pf_divergence_stats(pf_ctx* ctx, double dx, double dy, double out[2], void* stream);
+
 /* Operator-level seams on dense host arrays (row stride nx, ny_local rows):
  * numerics/core_ops_coherent.py:45,63,81; numerics/fluid_ops.py:30;
  * numerics/operators/advection.py:17,45; linear_solvers/interface.py:23 with

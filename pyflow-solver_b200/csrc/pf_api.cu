@@ -272,6 +272,7 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
     PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
     fill_sync(c, a.y);
+    PF_CUDA(c, cudaMemsetAsync(a.y.err, 0, sizeof(unsigned long long), st));
     PF_TRY(reset_trace(c, st));
     void* args[] = {&a};
     const void* fn = unit ? (const void*)k_cg_persistent_multi<true> : (const void*)k_cg_persistent_multi<false>;
@@ -648,7 +649,7 @@ int pf_step(pf_ctx* c, const pf_step_params* P, pf_step_out* out, void* stream) 
   out->rnorm = sqrt(h[S_RES_SUMSQ]);
   out->div_after_norm = sqrt(h[S_DIVA_SUMSQ]);
   out->p00 = h[S_X0] - h[S_X0];   /* p -= p.flat[0] (pressure_solver.py:148) */
-  if (h[S_INFO] == -2.0) return fail(c, PF_ERR_STATE, "pf_step", "cross-GPU exchange timed out inside the CG kernel");
+  if (h[S_INFO] == -2.0) return fail(c, PF_ERR_STATE, "pf_step", "a bounded wait inside the CG kernel timed out (pipeline or cross-GPU exchange)");
   out->info = (int32_t)h[S_INFO];
   out->true_iters = (int32_t)h[S_ITERS];
   if (!P->projection_only) {
@@ -664,6 +665,25 @@ int pf_step(pf_ctx* c, const pf_step_params* P, pf_step_out* out, void* stream) 
   out->cg_ms = ms;
   PF_CUDA(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]));
   out->step_ms = ms;
+  return PF_OK;
+}
+
+int pf_divergence_stats(pf_ctx* c, double dx, double dy, double out[2], void* stream) {
+  if (!c || !out) return PF_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Slab& s = c->s;
+  const Red red{c->red_part, c->red_counter, c->scal};
+  const double ncells = (double)s.nx * (double)s.nyg;
+  if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 1, st, c->err));
+  for (int pass = 0; pass < 2; ++pass) {
+    if (is_unit(dx, dy)) k_divc_stats<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, pass, ncells, red);
+    else k_divc_stats<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, pass, ncells, red);
+    PF_LAUNCHED(c);
+    if (c->comm) PF_TRY(comm_allreduce_scalars(c->comm, c->scal + (pass ? S_TMP1 : S_TMP0), 1, 0, st, c->err));
+  }
+  PF_TRY(read_scalars(c, st, false));
+  out[0] = c->h_scal[S_TMP0] / ncells;
+  out[1] = sqrt(c->h_scal[S_TMP1]);
   return PF_OK;
 }
 
@@ -772,6 +792,7 @@ int pf_op_pcg(pf_ctx* c, const double* b, double* x, double dx, double dy, int j
   PF_TRY(solve_on_device(c, dx, dy, jacobi, inv_diag_interior, tol, maxiter, 0, 0, st, nullptr, nullptr));
   PF_TRY(d2h_field(c, x, c->x, nxs, st));
   PF_TRY(read_scalars(c, st, false));
+  if (c->h_scal[S_INFO] == -2.0) return fail(c, PF_ERR_STATE, "pf_op_pcg", "a bounded wait inside the CG kernel timed out");
   if (info) *info = (int)c->h_scal[S_INFO];
   if (true_iters) *true_iters = (int)c->h_scal[S_ITERS];
   if (rnorm) *rnorm = sqrt(c->h_scal[S_RES_SUMSQ]);

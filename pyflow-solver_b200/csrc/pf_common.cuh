@@ -46,6 +46,7 @@ enum Scalar {
   S_PQ,                                       // split-phase CG (multi-GPU) state
   S_RR_NEW, S_RZ_NEW,
   S_RHO, S_RHO_PREV, S_DONE, S_ATOL,
+  S_TMP0, S_TMP1,                             // divergence statistics of the alternate driver
   S_COUNT = 32
 };
 

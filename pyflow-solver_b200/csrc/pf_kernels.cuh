@@ -339,6 +339,24 @@ __global__ void __launch_bounds__(KT) k_post(Slab s, const double* u, const doub
   grid_reduce_store<8, 0x3u>(vals, red, slots);
 }
 
+// ---- divergence statistics of the alternate driver (driver/simulation_driver.py:126-130, :78-81):
+// pass 0: sum of div_central(u,v;dx,dy);  pass 1: sum of (div - mean)^2 with mean = S_TMP0 / ncells
+template <bool UNIT>
+__global__ void __launch_bounds__(KT) k_divc_stats(Slab s, const double* u, const double* v, double dx, double dy,
+                                                   int pass, double ncells, Red red) {
+  double vals[1] = {0.0};
+  const double mean = pass ? ld_cg(red.scal + S_TMP0) / ncells : 0.0;
+  const int i = blockIdx.x * KT + threadIdx.x;
+  if (i < s.nx) {
+    for (int jl = blockIdx.y; jl < s.nyl; jl += gridDim.y) {
+      const double d = div_central<UNIT>(s, u, v, jl, i, dx, dy);
+      vals[0] += pass ? (d - mean) * (d - mean) : d;
+    }
+  }
+  const int slots[1] = {pass ? S_TMP1 : S_TMP0};
+  grid_reduce_store<1, 0u>(vals, red, slots);
+}
+
 __global__ void __launch_bounds__(KT) k_centerline(Slab s, const double* u, double* center) {
   const int jl = blockIdx.x * KT + threadIdx.x;
   if (jl < s.nyl) center[jl] = u[cell(s, jl, s.nx / 2)];

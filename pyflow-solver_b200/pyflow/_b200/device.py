@@ -150,6 +150,13 @@ class DeviceSlab:
         _lib.check(self._lib.pf_step(self.ctx, C.byref(params), C.byref(out), self._stream()), self.ctx, "pf_step")
         return out
 
+    def divergence_stats(self, dx: float, dy: float) -> tuple[float, float]:
+        """(mean, mean-free 2-norm) of the central divergence of the device u, v."""
+        out = (C.c_double * 2)()
+        _lib.check(self._lib.pf_divergence_stats(self.ctx, float(dx), float(dy), out, self._stream()), self.ctx,
+                   "pf_divergence_stats")
+        return float(out[0]), float(out[1])
+
     def centerline(self) -> np.ndarray:
         _lib.check(self._lib.pf_centerline(self.ctx, _ptr(self._center), self._stream()), self.ctx, "pf_centerline")
         return self._center.copy()

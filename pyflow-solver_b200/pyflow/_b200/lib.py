@@ -18,7 +18,7 @@ ABI_VERSION = 1
 # every symbol include/pyflow_b200.h declares (checked by the CPU test-suite)
 EXPORTS = (
     "pf_abi_version", "pf_strerror", "pf_last_error", "pf_workspace_bytes", "pf_create", "pf_destroy",
-    "pf_upload", "pf_download", "pf_prestep_reduce", "pf_step", "pf_centerline",
+    "pf_upload", "pf_download", "pf_prestep_reduce", "pf_step", "pf_centerline", "pf_divergence_stats",
     "pf_op_gradient_coherent", "pf_op_divergence_coherent", "pf_op_laplacian_coherent",
     "pf_op_divergence_central", "pf_op_advect", "pf_op_pcg", "pf_op_cg_generic",
     "pf_comm_unique_id", "pf_comm_init", "pf_comm_set_peers", "pf_device_info", "pf_launch_count", "pf_set_option", "pf_debug_read_partials",
@@ -69,6 +69,7 @@ def _declare(lib):
     lib.pf_prestep_reduce.argtypes = [vp, dp, vp]
     lib.pf_step.argtypes = [vp, C.POINTER(StepParams), C.POINTER(StepOut), vp]
     lib.pf_centerline.argtypes = [vp, vp, vp]
+    lib.pf_divergence_stats.argtypes = [vp, C.c_double, C.c_double, dp, vp]
     lib.pf_op_gradient_coherent.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp]
     lib.pf_op_divergence_coherent.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp]
     lib.pf_op_laplacian_coherent.argtypes = [vp, vp, vp, C.c_double, C.c_double, vp]

@@ -460,6 +460,24 @@ def test_large_grid_properties_4096():
     assert np.array_equal(finals[0], finals[1])
 
 
+def test_alternate_driver_divergence_stats_on_device():
+    """driver/simulation_driver.py (singular): mean / mean-free norm of the central divergence come from
+    device reductions; compare with numpy on the downloaded fields and with the oracle trajectory."""
+    from pyflow.driver.simulation_driver import DriverConfig, PhysicsConfig, SimulationDriver
+    phys = PhysicsConfig(lin_maxiter=3000, lx=32.0, ly=20.0)          # non-unit spacing: dx = 32/39, dy = 20/23
+    drv = SimulationDriver(DriverConfig(nx=40, ny=24, max_steps=4, report_interval=1000), phys)
+    payloads = list(drv.run())
+    assert len(payloads) == 4 and payloads[-1]["state"] is drv.state
+    ost, od = orc.run(SimpleNamespace(nx=40, ny=24, **phys.__dict__), 4)
+    st = drv.state
+    assert rel(st.fields["u"][1:-1, 1:-1], orc.interior(ost.fields["u"])) < 1e-9
+    d = orc.divergence_central(orc.interior(ost.fields["u"]), orc.interior(ost.fields["v"]), st.meta["dx"], st.meta["dy"])
+    mean, mf = float(d.mean()), float(np.linalg.norm(d - d.mean()))
+    assert abs(payloads[-1]["divergence_mean"] - mean) <= 1e-9 * max(abs(mean), 1e-12) + 1e-15
+    assert abs(payloads[-1]["divergence_mean_free_norm"] - mf) <= 1e-9 * mf
+    assert payloads[-1]["diagnostics"]["dt"] == od[-1]["dt"]
+
+
 # ---------------------------------------------------------------- CLI / checkpoint / restart on the device path
 def _run_cli(*argv, cwd=None):
     import os

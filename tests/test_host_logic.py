@@ -300,3 +300,36 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "MLUPS" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["config"]["nx"] == 4096 and line["higher_is_better"] is True
+
+
+# ------------------------------------------------------------------ alternate (dict-payload) driver, host logic
+def test_alternate_driver_steady_detection_and_hooks(monkeypatch):
+    """Reference driver/simulation_driver.py:113-176 semantics with the solver step mocked out."""
+    import pyflow.driver.simulation_driver as alt
+    calls = {"pre": 0, "post": 0}
+
+    def fake_step(cfg, state, tracker, it):
+        ru = 1e-3 * (0.5 ** it) if it < 6 else 1e-5          # decays, then flat => slope ~ 0
+        tracker.add("Ru", ru)
+        state.meta.update(dx=1.0, dy=1.0)
+        return state, {"Ru": ru, "Rv": ru, "Rp": 0.0, "continuity": 0.0}, {"dt": 0.01, "CFL": 0.5}
+
+    monkeypatch.setattr(alt, "core_step", fake_step)
+    monkeypatch.setattr(alt.SimulationDriver, "_divergence_stats", lambda self, st: (0.25, 0.5))
+    cfg = alt.DriverConfig(nx=8, ny=8, max_steps=40, steady_window=5, steady_slope_tol=1e-3, report_interval=1000,
+                           pre_step=lambda d, it, st: calls.__setitem__("pre", calls["pre"] + 1),
+                           post_step=lambda d, it, st: calls.__setitem__("post", calls["post"] + 1))
+    drv = alt.SimulationDriver(cfg, alt.PhysicsConfig())
+    payloads = list(drv.run())
+    last = payloads[-1]
+    assert set(last) == {"iteration", "state", "residuals", "diagnostics", "divergence_mean",
+                         "divergence_mean_free_norm", "steady", "steady_slope", "elapsed"}
+    assert last["steady"] is True and drv.steady_detected and drv.steady_iteration == last["iteration"] < 39
+    assert all(p["state"] is drv.state for p in payloads) and not any(p["steady"] for p in payloads[:-1])
+    assert calls["pre"] == len(payloads) and calls["post"] == len(payloads) - 1     # no post hook on the final steady yield
+    assert last["divergence_mean"] == 0.25 and last["divergence_mean_free_norm"] == 0.5
+    # without stop_on_steady the loop runs to max_steps
+    cfg2 = alt.DriverConfig(nx=8, ny=8, max_steps=12, steady_window=5, steady_slope_tol=1e-3, stop_on_steady=False,
+                            report_interval=1000)
+    assert len(list(alt.SimulationDriver(cfg2).run())) == 12
+    assert alt.create_default_driver().driver_cfg.nx == 65 and alt.PhysicsConfig().lin_maxiter == 800
