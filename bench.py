@@ -22,8 +22,10 @@ through the public `step()`; `e2e` is the same metric through
 `SimulationDriver.run` starting from HOST arrays and ending with the fields
 back on the host, copies inside the timed region.  `roofline` is the CG kernel:
 algorithmic bytes (64 B per cell per CG iteration) / its CUDA-event
-duration, against MEASURED_PEAKS.json.  `cpu_baseline` is the numpy oracle
-(bit-exact port of the reference) on a bounded sample on this box's host cores.
+duration, against MEASURED_PEAKS.json.  `cpu_baseline` (and `--impl reference`)
+is the C / OpenMP restatement of the reference algorithm (oracle/pyflow_oracle.c)
+on a bounded sample on all of this box's host cores; the single-threaded numpy
+oracle is reported beside it.
 """
 from __future__ import annotations
 
@@ -119,20 +121,26 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------ CPU legs (oracle)
-def oracle_sample(n: int, Re: float, lin_maxiter: int, steps: int, warmup: int):
+def oracle_sample(n: int, Re: float, lin_maxiter: int, steps: int, warmup: int, impl: str = "c"):
     """Times `steps` oracle steps (after `warmup`) of an n x n cavity from rest.
+    impl "c": oracle/pyflow_oracle.c on every host core (OpenMP); "numpy": oracle/pyflow_oracle.py.
     Returns (mlups, seconds_per_step, true CG iterations per step)."""
     import pyflow_oracle as orc
+    stepper = orc.step
+    if impl == "c":
+        import pyflow_oracle_c as orc_c
+        ws = orc_c.Workspace(n, n)
+        stepper = lambda cfg, st, it: orc_c.step(cfg, st, it, ws)          # noqa: E731
     cfg = make_cfg(n, n, Re, lin_maxiter)
     st = orc.allocate_state(n, n)
     it = 0
     for _ in range(max(1, warmup)):          # step 0 from rest has b = 0 (no CG work): never timed
-        orc.step(cfg, st, it)
+        stepper(cfg, st, it)
         it += 1
     t0 = time.perf_counter()
     iters = []
     for _ in range(steps):
-        _, _, d = orc.step(cfg, st, it)
+        _, _, d = stepper(cfg, st, it)
         iters.append(d["true_iterations"])
         it += 1
     dt = time.perf_counter() - t0
@@ -140,34 +148,36 @@ def oracle_sample(n: int, Re: float, lin_maxiter: int, steps: int, warmup: int):
 
 
 def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-        return int(n)
-    except Exception:
-        return os.cpu_count() or 1
+    """Host threads the C / OpenMP oracle runs on."""
+    import pyflow_oracle_c as orc_c
+    return orc_c.threads()
+
+
+def sized_oracle_grid(n_max: int, total_steps: int, budget_s: float):
+    """Largest power-of-two-scaled grid <= n_max whose `total_steps` C-oracle steps fit the time budget, from a
+    calibration step at 512^2 (cost scales with cells x CG iterations; large grids leave the caches, hence x2)."""
+    _m, sps, _it = oracle_sample(512, 1000.0, 300, 1, 1)
+    per_cell = sps / (512 * 512) * 2.0
+    n = n_max
+    while n > 512 and n * n * per_cell * total_steps > budget_s:
+        n //= 2
+    return n
 
 
 def run_reference_arm(args, wl, rank):
-    """`--impl reference`: the reference's CPU path (its bit-exact numpy port,
-    oracle/pyflow_oracle.py -- the reference itself is Python and cannot travel
-    to the box) on this box's host cores, same metric / config keys."""
+    """`--impl reference`: the reference's CPU algorithm for the path on this box's host cores.  The reference
+    itself is Python and cannot travel to the box; its restatement oracle/pyflow_oracle.c (pinned through the
+    numpy oracle and the golden vectors) runs on all host threads, same metric / config keys."""
     if rank != 0:
         return
-    budget_s = 150.0
-    per_cell_iter = 60e-9                                  # numpy CG iteration cost per cell (SURVEY section 6)
     total_steps = args.steps + max(1, args.warmup)
-    n = 2048
-    while n > 128 and n * n * 300 * per_cell_iter * total_steps > budget_s:
-        n //= 2
-    if args.ref_grid:
-        n = args.ref_grid
+    n = args.ref_grid or sized_oracle_grid(min(wl["nx"], 4096), total_steps, 150.0)
     mlups, sps, iters = oracle_sample(n, wl["Re"], 300, args.steps, args.warmup)
     cores = cpu_threads()
     sample = (f"{args.steps} steps (after {max(1, args.warmup)} warm-up) of a {n}x{n} cavity from rest, Re={wl['Re']}, "
-              f"QUICK, lin_maxiter=300 ({int(statistics.mean(iters))} true CG iterations/step); numpy oracle = "
-              "vectorised bit-exact port of the reference (element-wise numpy single-threaded, BLAS ddot/dnrm2 "
-              f"on {cores} threads)")
+              f"QUICK, lin_maxiter=300 ({int(statistics.mean(iters))} true CG iterations/step); C/OpenMP restatement "
+              f"of the reference algorithm on {cores} threads (the unmodified reference is single-threaded "
+              "Python/numpy/scipy and far slower)")
     line = {
         "impl": "reference", "metric": "MLUPS per projection step", "value": mlups, "unit": "MLUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
@@ -316,13 +326,16 @@ def run_gpu_arm(args, wl, rank, world):
     # ---- CPU baseline: bounded oracle sample on this box ---------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        n = 1024 if wl["nx"] >= 1024 else wl["nx"]
-        mlups, sps, iters = oracle_sample(n, wl["Re"], 300, 1, 1)
+        n = sized_oracle_grid(min(wl["nx"], 4096), 3, 25.0)
+        mlups, sps, iters = oracle_sample(n, wl["Re"], 300, 2, 1)
+        np_mlups, np_sps, _ = oracle_sample(min(n, 512), wl["Re"], 300, 1, 1, impl="numpy")
         cpu = {"value": mlups, "unit": "MLUPS", "cores": cpu_threads(), "kind": "port",
-               "sample": f"1 step (#1 from rest, {iters[0]} true CG iterations) of a {n}x{n} cavity, same Re/scheme/"
-                         f"solver settings, {sps:.1f} s; numpy oracle = vectorised bit-exact port of the reference "
-                         "(the unmodified reference is ~50x slower: Python loops for advection and the Jacobi "
-                         "assembly, SURVEY section 6)"}
+               "sample": f"2 steps (#1-#2 from rest, {int(statistics.mean(iters))} true CG iterations each) of a {n}x{n} "
+                         f"cavity, same Re/scheme/solver settings, {sps:.2f} s/step; C/OpenMP restatement of the "
+                         "reference algorithm (oracle/pyflow_oracle.c) on all host threads",
+               "numpy_port_mlups": np_mlups,
+               "numpy_port_sample": f"1 step of a {min(n, 512)}x{min(n, 512)} cavity with the single-threaded numpy "
+                                    "oracle (the unmodified reference is slower still: Python loops for advection)"}
     # ---- BASELINE config 2 (512^2, L2-resident, latency-bound) beside the headline, N = 1 only -------
     other = None
     if world == 1 and args.workload == "cavity4096":

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import pyflow_oracle as orc
+import pyflow_oracle_c as orc_c          # C / OpenMP restatement (bench.py's CPU baseline); built on first use
 
 OP_TAGS = ["8x8", "16x12", "5x9", "11x7", "33x17", "70x66"]
 
@@ -89,3 +90,53 @@ def test_survey_kats():
     assert abs(np.linalg.norm(orc.interior(st.fields["u"])) - 5.738896948423326) < 1e-9
     assert abs(np.linalg.norm(orc.interior(st.fields["p"])) - 1.970969104493264e+01) < 1e-7
     assert diags[-1]["Rp_iterations"] == 1
+
+
+# ---------------------------------------------------------------- the C / OpenMP restatement (oracle/pyflow_oracle.c)
+@pytest.mark.parametrize("tag", OP_TAGS)
+def test_c_oracle_operators_bit_exact(golden, tag):
+    g = {k.split("/", 1)[1]: v for k, v in golden["operators"].items() if k.startswith(tag + "/")}
+    dx, dy = (float(t) for t in g["dxdy"])
+    gx, gy = orc_c.gradient_coherent(g["p"], dx, dy)
+    assert np.array_equal(gx, g["gx"]) and np.array_equal(gy, g["gy"])
+    assert np.array_equal(orc_c.divergence_coherent(g["u"], g["v"], dx, dy), g["div"])
+    assert np.array_equal(orc_c.laplacian_coherent(g["p"], dx, dy), g["lap"])
+    assert np.array_equal(orc_c.divergence_central(g["u"], g["v"], dx, dy), g["divc"])
+    assert np.array_equal(orc_c.divergence_central(g["u"], g["v"], 1.0, 1.0), g["divc1"])
+    assert np.array_equal(orc_c.advect_upwind(g["u"], g["v"], g["f"], dx, dy), g["upwind"])
+    assert np.array_equal(orc_c.advect_quick(g["u"], g["v"], g["f"], dx, dy), g["quick"])
+
+
+@pytest.mark.parametrize("name", ["quick32_conv", "quick128_trunc", "upwind96x64_trunc", "quick40x24_spacing",
+                                  "upwind17x33_nopc"])
+def test_c_oracle_trajectories(golden, name):
+    meta = golden["trajectories_meta"][name]
+    cfg = SimpleNamespace(lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
+                          disable_advection=False, diagnostics=False, **meta["cfg"])
+    st, diags = orc_c.run(cfg, meta["steps"])
+    g = golden["trajectories"]
+    floor = meta["noise_floor"]
+    for f in ("u", "v", "p"):
+        tol = max(1e-9, 100 * floor[f])
+        assert rel(orc.interior(st.fields[f]), g[f"{name}/{f}"][1:-1, 1:-1]) < tol
+    assert np.array_equal([d["dt"] for d in diags], g[f"{name}/scalars"][:, 0])
+    it_tol = max(1, 2 * floor["iters_maxdiff"])
+    assert max(abs(a["true_iterations"] - b) for a, b in zip(diags, g[f"{name}/true_iters"])) <= it_tol
+
+
+def test_c_oracle_cg_matches_numpy_oracle():
+    rng = np.random.default_rng(5)
+    nx, ny, dx, dy = 37, 29, 0.7, 1.3
+    b = rng.standard_normal(nx * ny)
+    b -= b.mean()
+    b[0] = 0.0
+    for pc in (True, False):
+        inv = orc.jacobi_inverse_diagonal(nx, ny, dx, dy) if pc else None
+        x0, info0, it0 = orc.pcg(lambda t: orc.neg_laplacian_pinned(t, nx, ny, dx, dy), b, 1e-10, 5000, inv)
+        x1, info1, it1 = orc_c.pcg_pinned(b, nx, ny, dx, dy, 1e-10, 5000, jacobi=pc)
+        assert info0 == info1 == 0 and abs(it0 - it1) <= 1 and rel(x1, x0) < 1e-9
+    # truncated solve: same iterate after exactly 7 iterations (up to summation order)
+    x0, info0, _ = orc.pcg(lambda t: orc.neg_laplacian_pinned(t, nx, ny, dx, dy), b, 1e-10, 7,
+                           orc.jacobi_inverse_diagonal(nx, ny, dx, dy))
+    x1, info1, it1 = orc_c.pcg_pinned(b, nx, ny, dx, dy, 1e-10, 7)
+    assert info0 == info1 == 7 and it1 == 7 and rel(x1, x0) < 1e-12
