@@ -102,7 +102,7 @@ SmallLayout small_layout(int64_t nyl, int64_t nx = 0) {
   L.cg_part = o;     o = align_up(o + sizeof(double) * PF_PART_DOUBLES, ALIGN);
   L.sync = o;        o = align_up(o + 1024, ALIGN);
   L.center = o;      o = align_up(o + sizeof(double) * (size_t)nyl, ALIGN);
-  L.small_halo = o;  o = align_up(o + sizeof(double) * 2 * 256 * (size_t)(nx <= 2048 ? align_up((size_t)nx, PITCH_ALIGN) : 0), ALIGN);
+  L.small_halo = o;  o = align_up(o + sizeof(double) * 2 * SM_MAX_GRID * (size_t)(nx <= 2048 ? 4 * small_row_packets((int)nx) : 0), ALIGN);
   L.small_part = o;  o = align_up(o + sizeof(double) * 2 * 256 * 4, ALIGN);
   L.total = o;
   return L;
@@ -216,12 +216,11 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   const bool unit = is_unit(dx, dy);
   const int small_rows = (s.nyl + c->sm_count - 1) / c->sm_count;
   const size_t small_smem = sizeof(double) * (size_t)s.nx * ((size_t)(small_rows + 2) * 2 + small_rows);
-  if (c->opt_kernel == 3 && !c->comm && c->small_ok && s.nx % 2 == 0 && s.nx <= 2048 && c->sm_count <= 256 &&
+  if (c->opt_kernel == 3 && !c->comm && c->small_ok && s.nx % 2 == 0 && s.nx <= 2048 && c->sm_count <= SM_MAX_GRID &&
       (long long)small_rows * (s.nx / 2) <= (long long)SM_PAIRS * SM_THREADS && small_smem <= (size_t)SM_MAX_SMEM) {
     // shared-memory-resident solve for small grids (config 2): x, r, p never leave the SMs
     SmallArgs sa{};
     sa.s = s; sa.b = c->b; sa.x = c->x; sa.rhalo = c->small_halo; sa.part = c->small_part; sa.scal = c->scal;
-    sa.arrive = (unsigned long long*)(c->ws_base + c->sync_off) + 6;     // own counter / epoch words of the sync block
     sa.epoch = (unsigned long long*)(c->ws_base + c->sync_off) + 7;
     sa.err = (unsigned long long*)(c->ws_base + c->sync_off) + 3;
     sa.dx = dx; sa.dy = dy; sa.invd = invd; sa.tol = tol; sa.maxiter = maxiter; sa.rows = small_rows;

@@ -7,9 +7,10 @@
 // registers between the two phases; only the two boundary rows of r travel through
 // global memory (L2) per iteration -- the halo rows of p are recomputed redundantly
 // from them with the owner's exact arithmetic, so no third barrier is needed.  The
-// two reductions per iteration (classical CG) use a lean arrive / poll barrier whose
-// release is folded into the reduction: every CTA's warp 0 adds the per-CTA partials in
-// CTA order (bit-identical everywhere).  Same operation order as pf_cg.cuh / scipy.
+// two reductions per iteration (classical CG) are fence-free: every CTA posts one
+// self-validating 32-byte packet {epoch, partials}, every CTA's warp 0 polls all of
+// them and adds them in CTA order (bit-identical everywhere); the boundary rows of r
+// travel as the same kind of tagged packets.  Same operation order as pf_cg.cuh / scipy.
 #pragma once
 
 #include "pf_cg.cuh"
@@ -24,10 +25,9 @@ struct SmallArgs {
   Slab s;
   const double* b;          // rhs (= initial r), device field layout
   double* x;                // solution out (field layout)
-  double* rhalo;            // [G][2][pitch]: first / last row of r of every CTA
-  double* part;             // [2][G][4] per-CTA partials, double-buffered by barrier parity
+  double* rhalo;            // [G][2][packets per row][4]: first / last row of r of every CTA as tagged packets
+  double* part;             // [2][G][4] per-CTA reduction packets, double-buffered by barrier parity
   double* scal;
-  unsigned long long* arrive;   // monotonic arrival counter (sync block)
   unsigned long long* epoch;    // persisted barrier epoch
   unsigned long long* err;      // != 0 after a spin-wait timeout
   double dx, dy, invd, tol;
@@ -39,58 +39,119 @@ __device__ __forceinline__ int small_smem_bytes(int nx, int rows) {
   return (int)sizeof(double) * nx * ((rows + 2) * 2 + rows);
 }
 
-// All-reduce of NV doubles over the grid; barrier included.  Every thread returns the sums.
-template <int NV>
+constexpr int SM_POLL = 5;                        // reduce packets per lane of warp 0
+constexpr int SM_MAX_GRID = 32 * SM_POLL;         // => at most 160 CTAs (B200: 148 SMs)
+
+// packets per boundary row: {epoch, 3 doubles} each
+__host__ __device__ __forceinline__ int small_row_packets(int nx) { return (nx + 2) / 3; }
+
+// All-reduce of NV doubles over the grid; barrier included; every thread returns the sums.
+//
+// No counter, no fence: every CTA publishes ONE self-validating 32-byte packet {epoch, partials}
+// (a single 256-bit store) into its slot, warp 0 of every CTA polls all slots -- its loads are in
+// flight together -- and adds them in CTA order (same order everywhere => identical sums).
+// Slots are double-buffered by epoch parity: a fast CTA can post e+1 while a slow one still reads
+// e, but cannot reach e+2 before the slow one posted e+1.
+//
+// HALO: the CTA also publishes its first / last row of r (a.r_s rows 1 and R) as tagged packets, and
+// warps 1.. fetch the neighbours' rows into the halo rows of r_s while warp 0 runs the reduction.
+// A packet is complete or absent, so no release / acquire fence is needed for the rows either; a
+// neighbour overwrites its row packets only after the NEXT reduction, which needs this CTA's packet,
+// which is posted after these reads.
+template <int NV, bool HALO>
 __device__ __forceinline__ void small_allreduce(const SmallArgs& a, unsigned long long e, double (&v)[NV], double* sm,
-                                                double* s_res) {
-  const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // partials are double-buffered by parity: a fast CTA may already write its e+1 partial while a slow
-  // one still reads the e partials; it cannot reach e+2 before the slow one arrived at e+1
-  double* part = a.part + (size_t)(e & 1ULL) * (size_t)G * 4;
-  block_sum_n<NV>(v, sm);
-  if (tid == 0) {
+                                                double* s_res2, double* r_s, int R) {
+  const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bid = blockIdx.x;
+  const int nx = a.s.nx;
+  double* slots = a.part + (size_t)(e & 1ULL) * (size_t)G * 4;
+  double* s_res = s_res2 + (e & 1ULL) * 4;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) part[blockIdx.x * 4 + k] = v[k];
-    __threadfence();                                   // release: partials + this CTA's halo rows
-    atomicAdd(a.arrive, 1ULL);
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sm[k * 32 + warp] = v[k];
   }
+  __syncthreads();                                     // warp partials and (HALO) the CTA's new r rows are in shared memory
   if (warp == 0) {
     if (lane == 0) {
-      const unsigned long long target = e * (unsigned long long)G;
-      const long long t0 = clock64();
-      while (ld_relaxed_u64(a.arrive) < target) {
-        if (clock64() - t0 > CG_SPIN_LIMIT) {            // never hang the GPU
-          atomicExch(a.err, 1ULL);
-          break;
+      double t[2] = {0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        for (int q = 0; q < SM_THREADS / 32; ++q) t[k] += sm[k * 32 + q];
+      st_packet_gpu(slots + (size_t)bid * 4, e, t[0], t[1], 0.0);
+    }
+    Packet pk[SM_POLL];
+    const long long t0 = clock64();
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int j = 0; j < SM_POLL; ++j) {
+        const int q = lane + 32 * j;
+        if (q < G) {
+          pk[j] = ld_packet_gpu(slots + (size_t)q * 4);
+          ok = ok && (pk[j].epoch == e);
         }
       }
-      (void)ld_acquire_gpu(a.arrive);
-    }
-    __syncwarp();
+      if (!ok && clock64() - t0 > CG_SPIN_LIMIT) {       // never hang the GPU
+        atomicExch(a.err, 1ULL);
+        break;
+      }
+    } while (!ok);
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    for (int q = lane; q < G; q += 32) {               // CTA order within a lane, fixed xor tree across lanes
 #pragma unroll
-      for (int k = 0; k < NV; ++k) acc[k] += ld_cg(part + q * 4 + k);
+    for (int j = 0; j < SM_POLL; ++j) {                  // CTA order within a lane, fixed xor tree across lanes
+      if (lane + 32 * j < G) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] += pk[j].v[k];
+      }
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       acc[k] = warp_sum(acc[k]);
       if (lane == 0) s_res[k] = acc[k];
     }
+  } else if (HALO) {
+    const int npk = small_row_packets(nx);
+    const size_t hstride = (size_t)npk * 4;
+    for (int idx = tid - 32; idx < 2 * npk; idx += SM_THREADS - 32) {          // publish own boundary rows
+      const int side = idx / npk, k = idx - side * npk, c = 3 * k;
+      const double* row = r_s + (size_t)(side == 0 ? 1 : R) * nx;
+      st_packet_gpu(a.rhalo + ((size_t)bid * 2 + side) * hstride + (size_t)k * 4, e, row[c],
+                    c + 1 < nx ? row[c + 1] : 0.0, c + 2 < nx ? row[c + 2] : 0.0);
+    }
+    for (int idx = tid - 32; idx < 2 * npk; idx += SM_THREADS - 32) {          // fetch the neighbours' rows
+      const int side = idx / npk, k = idx - side * npk, c = 3 * k;
+      const int nb = side == 0 ? bid - 1 : bid + 1;
+      if (nb < 0 || nb >= G) continue;
+      const double* src = a.rhalo + ((size_t)nb * 2 + (side == 0 ? 1 : 0)) * hstride + (size_t)k * 4;
+      Packet h = ld_packet_gpu(src);
+      const long long t0 = clock64();
+      while (h.epoch != e) {
+        if (clock64() - t0 > CG_SPIN_LIMIT) {
+          atomicExch(a.err, 1ULL);
+          break;
+        }
+        h = ld_packet_gpu(src);
+      }
+      double* dst = r_s + (size_t)(side == 0 ? 0 : R + 1) * nx + c;
+      dst[0] = h.v[0];
+      if (c + 1 < nx) dst[1] = h.v[1];
+      if (c + 2 < nx) dst[2] = h.v[2];
+    }
   }
-  __syncthreads();
+  __syncthreads();                                     // sums (and halo rows) are in shared memory
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = s_res[k];
-  __syncthreads();
 }
 
 template <bool UNIT>
 __global__ void __launch_bounds__(SM_THREADS, 1) k_cg_small(SmallArgs a) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ double sm[3 * 32];
-  __shared__ double s_res[4];
+  __shared__ double s_res[8];                       // sums, double-buffered by barrier parity
   const Slab& s = a.s;
   const int nx = s.nx, G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
   const int j0 = bid * a.rows;
@@ -180,7 +241,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_cg_small(SmallArgs a) {
           v1[0] += pb * q1;
         }
       }
-      small_allreduce<1>(a, ++e, v1, sm, s_res);
+      small_allreduce<1, false>(a, ++e, v1, sm, s_res, r_s, R);
       const double alpha = rho / v1[0];
       // ---- phase B: x += alpha p ; r -= alpha q ; publish the boundary rows of r
       double v2[2] = {0.0, 0.0};
@@ -200,30 +261,17 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_cg_small(SmallArgs a) {
           rv.y = rv.y - alpha * qb[k];
           *reinterpret_cast<double2*>(x_s + (size_t)(lr - 1) * nx + c) = xv;
           *reinterpret_cast<double2*>(r_s + o) = rv;
-          if (lr == 1) st2(a.rhalo + ((size_t)bid * 2 + 0) * s.pitch + c, rv.x, rv.y);
-          if (lr == R) st2(a.rhalo + ((size_t)bid * 2 + 1) * s.pitch + c, rv.x, rv.y);
           v2[0] += rv.x * rv.x;
           v2[1] += rv.x * (invd_of(jg, c) * rv.x);
           v2[0] += rv.y * rv.y;
           v2[1] += rv.y * (invd_of(jg, c + 1) * rv.y);
         }
       }
-      small_allreduce<2>(a, ++e, v2, sm, s_res);
+      small_allreduce<2, true>(a, ++e, v2, sm, s_res, r_s, R);   // also exchanges the boundary rows of r
       rr = v2[0];
       rho_prev = rho;
       rho = v2[1];
       ++iters;
-      // ---- fetch the neighbours' boundary rows of r into the halo rows (visible after the barrier)
-      for (int idx = tid; idx < 2 * hp; idx += SM_THREADS) {
-        const int side = idx / hp, c = (idx % hp) * 2;
-        const int nb = side == 0 ? bid - 1 : bid + 1;
-        if (nb >= 0 && nb < G) {
-          const double* src = a.rhalo + ((size_t)nb * 2 + (side == 0 ? 1 : 0)) * s.pitch + c;
-          const double2 v = make_double2(ld_cg(src), ld_cg(src + 1));   // L2: written by another SM this iteration
-          *reinterpret_cast<double2*>(r_s + (size_t)(side == 0 ? 0 : R + 1) * nx + c) = v;
-        }
-      }
-      __syncthreads();
     }
   }
   // ---- write x back
