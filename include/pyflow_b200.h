@@ -134,6 +134,17 @@ int pf_op_laplacian_coherent(pf_ctx* ctx, const double* p, double* out,
                              double dx, double dy, void* stream);
 int pf_op_divergence_central(pf_ctx* ctx, const double* u, const double* v, double* out,
                              double dx, double dy, void* stream);
+/* Legacy central operators of the same module as pf_op_divergence_central, off the
+ * time-step path but imported by the reference's own projection tests:
+ * numerics/fluid_ops.py:43-67 (gradient), :69-91 (laplacian), :108-125
+ * (apply_pressure_correction: u_out = u - dt*dp/dx, v_out = v - dt*dp/dy).      */
+int pf_op_gradient_central(pf_ctx* ctx, const double* p, double* gx, double* gy,
+                           double dx, double dy, void* stream);
+int pf_op_laplacian_central(pf_ctx* ctx, const double* p, double* out,
+                            double dx, double dy, void* stream);
+int pf_op_pressure_correction_central(pf_ctx* ctx, const double* u, const double* v, const double* p,
+                                      double dt, double dx, double dy,
+                                      double* u_out, double* v_out, void* stream);
 int pf_op_advect(pf_ctx* ctx, int scheme, const double* u, const double* v, const double* f,
                  double* out, double dx, double dy, void* stream);
 int pf_op_pcg(pf_ctx* ctx, const double* b, double* x, double dx, double dy,

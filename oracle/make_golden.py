@@ -8,7 +8,8 @@ Runs only where ``/root/reference`` exists (the build container).  It
   3. writes small fixtures to ``tests/golden/`` (inputs + reference outputs),
      which travel to the GPU box where the reference itself cannot.
 
-Usage:  python oracle/make_golden.py          (exit code != 0 on any mismatch)
+Usage:  python oracle/make_golden.py [part ...]   (exit code != 0 on any mismatch; parts: operators,
+        legacy_ops, pressure, trajectories, config -- default all)
 """
 from __future__ import annotations
 
@@ -116,6 +117,41 @@ def operator_vectors():
             cases[f"{tag}/{nm}"] = arr
         cases[f"{tag}/dxdy"] = np.array([dx, dy])
     np.savez_compressed(os.path.join(GOLD, "operators.npz"), **cases)
+
+
+def legacy_ops_vectors():
+    """fluid_ops.gradient / laplacian / apply_pressure_correction (numerics/fluid_ops.py:43-125): off the
+    time-step path but imported by the reference's own projection tests."""
+    print("legacy central operators")
+    cases = {}
+    for k, (nx, ny, unit) in enumerate([(8, 8, False), (16, 12, False), (5, 9, True), (2, 2, False), (3, 3, True),
+                                        (2, 7, False), (9, 2, True), (33, 17, True), (70, 66, False)]):
+        rng = np.random.default_rng(100 + k)
+        dx, dy = (1.0, 1.0) if unit else (1.3 / max(nx - 1, 1), 0.7 / max(ny - 1, 1))
+        dt = 0.0137
+        p = rng.standard_normal((ny, nx))
+        u = rng.standard_normal((ny, nx))
+        v = rng.standard_normal((ny, nx))
+        gx, gy = ref_fluid.gradient(p, dx, dy)
+        lp = ref_fluid.laplacian(p, dx, dy)
+        st = ref_allocate(nx, ny)
+        interior_view(st.fields["u"])[:] = u
+        interior_view(st.fields["v"])[:] = v
+        ref_fluid.apply_pressure_correction(st, p, dt, dx, dy)
+        uc, vc = interior_view(st.fields["u"]).copy(), interior_view(st.fields["v"]).copy()
+        tag = f"{nx}x{ny}"
+        ogx, ogy = orc.gradient_central(p, dx, dy)
+        ouc, ovc = orc.pressure_correction_central(u, v, p, dt, dx, dy)
+        check(f"gradient_central x {tag}", ogx, gx)
+        check(f"gradient_central y {tag}", ogy, gy)
+        check(f"laplacian_central {tag}", orc.laplacian_central(p, dx, dy), lp)
+        check(f"pressure_correction u {tag}", ouc, uc)
+        check(f"pressure_correction v {tag}", ovc, vc)
+        check(f"pressure_correction p {tag}", interior_view(st.fields["p"]), p)
+        for nm, arr in dict(p=p, u=u, v=v, gx=gx, gy=gy, lap=lp, ucorr=uc, vcorr=vc).items():
+            cases[f"{tag}/{nm}"] = arr
+        cases[f"{tag}/dxdydt"] = np.array([dx, dy, dt])
+    np.savez_compressed(os.path.join(GOLD, "legacy_ops.npz"), **cases)
 
 
 def pressure_vectors():
@@ -288,10 +324,12 @@ def config_vectors():
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    operator_vectors()
-    pressure_vectors()
-    trajectory_vectors()
-    config_vectors()
+    parts = {"operators": operator_vectors, "legacy_ops": legacy_ops_vectors, "pressure": pressure_vectors,
+             "trajectories": trajectory_vectors, "config": config_vectors}
+    only = sys.argv[1:]                      # e.g. `make_golden.py legacy_ops` regenerates one fixture file
+    for name, fn in parts.items():
+        if not only or name in only:
+            fn()
     if FAILS:
         print(f"\n{len(FAILS)} MISMATCHES: {FAILS}")
         return 1

@@ -30,7 +30,8 @@ import numpy as np
 __all__ = [
     "OracleState", "allocate_state", "interior",
     "gradient_coherent", "divergence_coherent", "laplacian_coherent",
-    "divergence_central", "advect_upwind", "advect_quick",
+    "divergence_central", "gradient_central", "laplacian_central", "pressure_correction_central",
+    "advect_upwind", "advect_quick",
     "jacobi_inverse_diagonal", "neg_laplacian_pinned", "pcg",
     "solve_pressure_poisson", "solve_manufactured", "step", "run",
 ]
@@ -118,6 +119,46 @@ def divergence_central(u, v, dx, dy):
     # NOTE (fluid_ops.py:16-27): the right column excluding corners is never
     # written by the reference and stays zero.  Reproduced here on purpose.
     return d
+
+
+# --------------------------------------------------------------------------
+# Legacy central gradient / Laplacian / correction of the same module
+# src/pyflow/numerics/fluid_ops.py:43-67, 69-91, 108-125 -- off the time-step
+# path, but imported by the reference's own projection tests
+# (tests/test_projection_method_contract.py:304,337,409)
+# --------------------------------------------------------------------------
+def gradient_central(p, dx, dy):
+    """fluid_ops.gradient (:43-67): difference of the two clamped neighbours over
+    ``2*spacing`` inside and over ``spacing`` in the first / last column or row."""
+    ny, nx = p.shape
+    ii = np.arange(nx)
+    jj = np.arange(ny)
+    span_x = np.where((ii > 0) & (ii < nx - 1), 2.0 * dx, dx)
+    span_y = np.where((jj > 0) & (jj < ny - 1), 2.0 * dy, dy)
+    gx = (p[:, np.minimum(ii + 1, nx - 1)] - p[:, np.maximum(ii - 1, 0)]) / span_x[None, :]
+    gy = (p[np.minimum(jj + 1, ny - 1), :] - p[np.maximum(jj - 1, 0), :]) / span_y[:, None]
+    return gx, gy
+
+
+def laplacian_central(p, dx, dy):
+    """fluid_ops.laplacian (:69-91): 5-point second differences inside; every wall
+    cell copies the value of its nearest interior cell (rows first, then columns,
+    so corners take the diagonal neighbour); all zero unless nx > 2 and ny > 2."""
+    ny, nx = p.shape
+    if nx <= 2 or ny <= 2:
+        return np.zeros_like(p)
+    c = p[1:-1, 1:-1]
+    core = (p[1:-1, 2:] - 2.0 * c + p[1:-1, :-2]) / (dx * dx) + (p[2:, 1:-1] - 2.0 * c + p[:-2, 1:-1]) / (dy * dy)
+    jj = np.clip(np.arange(ny), 1, ny - 2) - 1
+    ii = np.clip(np.arange(nx), 1, nx - 2) - 1
+    return core[np.ix_(jj, ii)]
+
+
+def pressure_correction_central(u, v, p, dt, dx, dy):
+    """fluid_ops.apply_pressure_correction (:108-125) on interior arrays:
+    returns (u - dt*dp/dx, v - dt*dp/dy) with the central gradient above."""
+    gx, gy = gradient_central(p, dx, dy)
+    return u - dt * gx, v - dt * gy
 
 
 # --------------------------------------------------------------------------

@@ -760,6 +760,52 @@ int pf_op_laplacian_coherent(pf_ctx* c, const double* p, double* out, double dx,
   return PF_OK;
 }
 
+int pf_op_gradient_central(pf_ctx* c, const double* p, double* gx, double* gy, double dx, double dy, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!p || !gx || !gy) return PF_ERR_ARG;
+  PF_TRY(h2d_field(c, c->b, p, nxs, st));
+  if (is_unit(dx, dy)) k_op_grad_central<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, c->p1, dx, dy);
+  else k_op_grad_central<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, c->p1, dx, dy);
+  PF_LAUNCHED(c);
+  PF_TRY(d2h_field(c, gx, c->p0, nxs, st));
+  PF_TRY(d2h_field(c, gy, c->p1, nxs, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+int pf_op_laplacian_central(pf_ctx* c, const double* p, double* out, double dx, double dy, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!p || !out) return PF_ERR_ARG;
+  PF_TRY(h2d_field(c, c->b, p, nxs, st));
+  if (is_unit(dx, dy)) k_op_lap_central<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, dx, dy);
+  else k_op_lap_central<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, dx, dy);
+  PF_LAUNCHED(c);
+  PF_TRY(d2h_field(c, out, c->p0, nxs, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
+int pf_op_pressure_correction_central(pf_ctx* c, const double* u, const double* v, const double* p, double dt,
+                                      double dx, double dy, double* u_out, double* v_out, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!u || !v || !p || !u_out || !v_out) return PF_ERR_ARG;
+  const bool unit = is_unit(dx, dy);
+  PF_TRY(h2d_field(c, c->b, p, nxs, st));
+  PF_TRY(h2d_field(c, c->r, u, nxs, st));
+  PF_TRY(h2d_field(c, c->p0, v, nxs, st));
+  if (unit) k_op_correct_central<true, 0><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p1, dt, dx);
+  else k_op_correct_central<false, 0><<<c->sgrid, KT, 0, st>>>(s, c->b, c->r, c->p1, dt, dx);
+  PF_LAUNCHED(c);
+  PF_TRY(d2h_field(c, u_out, c->p1, nxs, st));
+  // stream order: the copy of p1 above completes before the next kernel overwrites it
+  if (unit) k_op_correct_central<true, 1><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, c->p1, dt, dy);
+  else k_op_correct_central<false, 1><<<c->sgrid, KT, 0, st>>>(s, c->b, c->p0, c->p1, dt, dy);
+  PF_LAUNCHED(c);
+  PF_TRY(d2h_field(c, v_out, c->p1, nxs, st));
+  PF_CUDA(c, cudaStreamSynchronize(st));
+  return PF_OK;
+}
+
 int pf_op_advect(pf_ctx* c, int scheme, const double* u, const double* v, const double* f, double* out, double dx,
                  double dy, void* stream) {
   PF_OP_PROLOGUE();

@@ -400,6 +400,72 @@ __global__ void __launch_bounds__(KT) k_op_lap(Slab s, const double* p, double* 
   }
 }
 
+// ---- legacy central operators of fluid_ops.py (off the time-step path; the
+// reference's own projection tests import them) ------------------------------
+// fluid_ops.gradient at one cell (numerics/fluid_ops.py:43-67): the two clamped
+// neighbours' difference over 2*h inside, over h in the first / last column (row).
+// DIR 0: d/dx, DIR 1: d/dy.
+template <bool UNIT, int DIR>
+__device__ __forceinline__ double grad_central(const Slab& s, const double* p, int jl, int i, double h) {
+  double d;
+  bool inner;
+  if (DIR == 0) {
+    inner = (i > 0) && (i < s.nx - 1);
+    d = p[cell(s, jl, clampi(i + 1, 0, s.nx - 1))] - p[cell(s, jl, clampi(i - 1, 0, s.nx - 1))];
+  } else {
+    const int jg = s.row0 + jl;
+    inner = (jg > 0) && (jg < s.nyg - 1);
+    d = p[cell(s, clampi(jg + 1, 0, s.nyg - 1) - s.row0, i)] - p[cell(s, clampi(jg - 1, 0, s.nyg - 1) - s.row0, i)];
+  }
+  if (inner) return UNIT ? d * 0.5 : d / (2.0 * h);      // d/2.0 == d*0.5 exactly
+  return dv<UNIT>(d, h);
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(KT) k_op_grad_central(Slab s, const double* p, double* gx, double* gy,
+                                                        double dx, double dy) {
+  const int i = blockIdx.x * KT + threadIdx.x;
+  if (i >= s.nx) return;
+  for (int jl = blockIdx.y; jl < s.nyl; jl += gridDim.y) {
+    gx[cell(s, jl, i)] = grad_central<UNIT, 0>(s, p, jl, i, dx);
+    gy[cell(s, jl, i)] = grad_central<UNIT, 1>(s, p, jl, i, dy);
+  }
+}
+
+// fluid_ops.laplacian (numerics/fluid_ops.py:69-91): 5-point second differences inside;
+// every wall cell copies its nearest interior cell (rows are copied first, then columns,
+// so a corner takes its diagonal neighbour); all zero unless nx > 2 and ny > 2.
+template <bool UNIT>
+__global__ void __launch_bounds__(KT) k_op_lap_central(Slab s, const double* p, double* out, double dx, double dy) {
+  const int i = blockIdx.x * KT + threadIdx.x;
+  if (i >= s.nx) return;
+  const bool any = (s.nx > 2) && (s.nyg > 2);
+  const double dx2 = dx * dx, dy2 = dy * dy;
+  for (int jl = blockIdx.y; jl < s.nyl; jl += gridDim.y) {
+    double r = 0.0;
+    if (any) {
+      const int ic = clampi(i, 1, s.nx - 2);
+      const int jc = clampi(s.row0 + jl, 1, s.nyg - 2) - s.row0;
+      const double tc = 2.0 * p[cell(s, jc, ic)];
+      const double xt = dv<UNIT>((p[cell(s, jc, ic + 1)] - tc) + p[cell(s, jc, ic - 1)], dx2);
+      const double yt = dv<UNIT>((p[cell(s, jc + 1, ic)] - tc) + p[cell(s, jc - 1, ic)], dy2);
+      r = xt + yt;
+    }
+    out[cell(s, jl, i)] = r;
+  }
+}
+
+// one component of fluid_ops.apply_pressure_correction (numerics/fluid_ops.py:108-125):
+// out = f - dt * d(p)/d(DIR) with the central gradient above.
+template <bool UNIT, int DIR>
+__global__ void __launch_bounds__(KT) k_op_correct_central(Slab s, const double* p, const double* f, double* out,
+                                                           double dt, double h) {
+  const int i = blockIdx.x * KT + threadIdx.x;
+  if (i >= s.nx) return;
+  for (int jl = blockIdx.y; jl < s.nyl; jl += gridDim.y)
+    out[cell(s, jl, i)] = f[cell(s, jl, i)] - dt * grad_central<UNIT, DIR>(s, p, jl, i, h);
+}
+
 template <bool UNIT, int SCHEME>
 __global__ void __launch_bounds__(KT) k_op_advect(Slab s, const double* u, const double* v, const double* f,
                                                   double* out, double dx, double dy) {

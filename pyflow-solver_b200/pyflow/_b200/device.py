@@ -196,6 +196,32 @@ class DeviceSlab:
                                                       self._stream()), self.ctx, "pf_op_laplacian_coherent")
         return out
 
+    def gradient_central(self, p, dx, dy):
+        """fluid_ops.gradient (reference numerics/fluid_ops.py:43-67)."""
+        p = self._dense(p)
+        gx, gy = np.empty_like(p), np.empty_like(p)
+        _lib.check(self._lib.pf_op_gradient_central(self.ctx, _ptr(p), _ptr(gx), _ptr(gy), float(dx), float(dy),
+                                                    self._stream()), self.ctx, "pf_op_gradient_central")
+        return gx, gy
+
+    def laplacian_central(self, p, dx, dy):
+        """fluid_ops.laplacian (reference numerics/fluid_ops.py:69-91)."""
+        p = self._dense(p)
+        out = np.empty_like(p)
+        _lib.check(self._lib.pf_op_laplacian_central(self.ctx, _ptr(p), _ptr(out), float(dx), float(dy),
+                                                     self._stream()), self.ctx, "pf_op_laplacian_central")
+        return out
+
+    def pressure_correction_central(self, u, v, p, dt, dx, dy):
+        """(u - dt*dp/dx, v - dt*dp/dy) with the central gradient (reference numerics/fluid_ops.py:108-125)."""
+        u, v, p = self._dense(u), self._dense(v), self._dense(p)
+        uo, vo = np.empty_like(u), np.empty_like(v)
+        _lib.check(self._lib.pf_op_pressure_correction_central(self.ctx, _ptr(u), _ptr(v), _ptr(p), float(dt),
+                                                               float(dx), float(dy), _ptr(uo), _ptr(vo),
+                                                               self._stream()),
+                   self.ctx, "pf_op_pressure_correction_central")
+        return uo, vo
+
     def advect(self, scheme: str, u, v, f, dx, dy):
         code = {"upwind": _lib.PF_ADV_UPWIND, "quick": _lib.PF_ADV_QUICK}[scheme]
         u, v, f = self._dense(u), self._dense(v), self._dense(f)
@@ -216,7 +242,6 @@ class DeviceSlab:
                                        float(inv_diag_interior), float(tol), int(maxiter), C.byref(info),
                                        C.byref(iters), C.byref(rnorm), self._stream()), self.ctx, "pf_op_pcg")
         return x, info.value, iters.value, rnorm.value
-
 
     def cg_generic(self, mode: str, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=1.0, want_x=True):
         """Reference-order CG with the plain (q stored) kernel.  mode 'pinned' | 'dirichlet'.

@@ -63,7 +63,7 @@ def golden():
     import json
     import numpy as np
     out = {}
-    for name in ("operators", "pressure", "trajectories"):
+    for name in ("operators", "legacy_ops", "pressure", "trajectories"):
         with np.load(os.path.join(GOLDEN, f"{name}.npz")) as z:
             out[name] = {k: z[k] for k in z.files}
     with open(os.path.join(GOLDEN, "trajectories.json")) as fh:

@@ -1,0 +1,325 @@
+"""Host side of the drop-in exercised END TO END on a machine without a GPU.
+
+The GPU context is replaced by the oracle-backed stand-in (``tests/cpu_slab.py``), so what
+these tests check is everything the product does on the HOST around the ``pf_step`` call:
+the dt / safeguard floats, the residual and diagnostics dictionaries, the lazy State
+synchronisation protocol (which fields are uploaded / downloaded and when), the generator
+driver, checkpoints of device-resident fields, the CLI run loop and its JSON stream, the
+alternate dict-payload driver, the array-level operator seams.  The kernels themselves are
+checked by the ``-m gpu`` suite.
+"""
+import io
+import json
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import cpu_slab
+import pyflow_oracle as orc
+
+
+@pytest.fixture()
+def slab_cls(monkeypatch):
+    return cpu_slab.install(monkeypatch)
+
+
+def make_cfg(**kw):
+    base = dict(nx=24, ny=20, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
+                lin_maxiter=300, advection_scheme="quick", disable_advection=False, diagnostics=False)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+# ------------------------------------------------------------------ whole trajectories through step()
+@pytest.mark.parametrize("kw,steps", [
+    (dict(nx=32, ny=32, lin_maxiter=2000), 6),
+    (dict(nx=40, ny=24, Re=400.0, lx=2.0, ly=1.0, lin_maxiter=3000), 6),
+    (dict(nx=17, ny=33, Re=50.0, advection_scheme="upwind", enable_jacobi_pc=False, lin_maxiter=2000), 5),
+    (dict(nx=24, ny=20, disable_advection=True), 4),
+    (dict(nx=24, ny=20, lid_velocity=None, advection_scheme="anything-else-is-upwind"), 3),
+])
+def test_step_matches_the_oracle_step_for_step(slab_cls, kw, steps):
+    """Same floats as the reference: dt, CFL, residuals, Rp_* and the fields, every step."""
+    from pyflow.core.ghost_fields import allocate_state
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    cfg = make_cfg(**kw)
+    st, tr = allocate_state(cfg.nx, cfg.ny), ResidualManager()
+    ost = orc.allocate_state(cfg.nx, cfg.ny)
+    if cfg.lid_velocity is None:                           # nothing drives the flow: seed a vortex
+        yy, xx = np.mgrid[0:cfg.ny, 0:cfg.nx]
+        for s in (st, ost):
+            s.fields["u"][1:-1, 1:-1] = np.sin(0.3 * xx) * np.cos(0.2 * yy)
+            s.fields["v"][1:-1, 1:-1] = -np.cos(0.3 * xx) * np.sin(0.2 * yy)
+    for it in range(steps):
+        same, res, diag = step(cfg, st, tr, it)
+        _, ores, odiag = orc.step(cfg, ost, it)
+        assert same is st
+        assert diag["dt"] == odiag["dt"] and diag["CFL"] == odiag["CFL"] and diag["iteration"] == it
+        for k in ("Ru", "Rv", "Rp", "continuity"):
+            assert res[k] == ores[k], (it, k)
+        for k in ("Rp_iterations", "Rp_residual", "Rp_converged", "Rp_method", "divergence_norm", "nan_detected",
+                  "max_residual", "nu"):
+            assert diag[k] == odiag[k], (it, k)
+        assert st.meta["cg_true_iterations"] == odiag["true_iterations"]
+        assert st.meta["dt_prev"] == ost.meta["dt_prev"]
+        assert st.meta["divergence_history"] == ost.meta["divergence_history"]
+        assert st.meta["prev_div_norm"] == ost.meta["prev_div_norm"]
+    for f in ("u", "v", "p"):
+        assert np.array_equal(st.fields[f], ost.fields[f]), f
+    assert tr.series["Ru"].values[0] == 1.0 and len(tr.series["Ru"].values) == steps + 1
+    assert set(tr.series) == {"Ru"}                        # the reference's tracker is a stub that keeps Ru only
+
+
+def test_dt_sequence_known_answers_from_rest(slab_cls):
+    """SURVEY 8c KAT: growth-limited dt from rest, then the divergence safeguard halves it."""
+    from pyflow.core.ghost_fields import allocate_state
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    cfg = make_cfg(nx=32, ny=32, lin_maxiter=10000)
+    st, tr = allocate_state(32, 32), ResidualManager()
+    dts = [step(cfg, st, tr, it)[2]["dt"] for it in range(5)]
+    assert dts == [0.0105, 0.011025000000000002, 0.011576250000000003, 0.012155062500000004, 0.006381407812500003]
+
+
+# ------------------------------------------------------------------ lazy State protocol around step()
+def test_fields_stay_on_the_device_between_steps(slab_cls):
+    from pyflow.core.ghost_fields import allocate_state, interior_view
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    cfg = make_cfg()
+    st, tr = allocate_state(cfg.nx, cfg.ny), ResidualManager()
+    for it in range(3):
+        step(cfg, st, tr, it)
+    slab = st.fields._slab
+    assert isinstance(slab, slab_cls) and slab.steps == 3
+    assert slab.uploads == [("u", "v", "p")] and slab.downloads == []      # one upload, nothing pulled back
+    # the pre-step reductions of step k+1 come from step k's post pass: no extra device call is needed,
+    # and a host write invalidates that cache
+    assert st.fields._prestep is not None
+    u = st.fields["u"]                                                     # materialise: one D2H of u only
+    assert slab.downloads == [("u",)] and st.fields.host_touched() == {"u"}
+    interior_view(u)[3, 4] += 0.25                                         # host mutation between steps ...
+    step(cfg, st, tr, 3)
+    assert slab.uploads[-1] == ("u",)                                      # ... is uploaded (u only) before the step
+    ost = orc.allocate_state(cfg.nx, cfg.ny)
+    for it in range(3):
+        orc.step(cfg, ost, it)
+    orc.interior(ost.fields["u"])[3, 4] += 0.25
+    orc.step(cfg, ost, 3)
+    for f in ("u", "v", "p"):
+        assert np.array_equal(st.fields[f], ost.fields[f])
+
+
+def test_foreign_state_objects_are_synchronised_eagerly(slab_cls):
+    """A state that is not ours (plain dict fields, e.g. the reference's dataclass): upload before and
+    download after every call, into the caller's own arrays."""
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    cfg = make_cfg(nx=16, ny=12)
+    foreign = SimpleNamespace(nx=16, ny=12, fields={k: np.zeros((14, 18)) for k in "uvp"}, meta={})
+    u_arr = foreign.fields["u"]
+    ost = orc.allocate_state(16, 12)
+    for it in range(3):
+        step(cfg, foreign, ResidualManager(), it)
+        orc.step(cfg, ost, it)
+        assert foreign.fields["u"] is u_arr and np.array_equal(u_arr, ost.fields["u"])
+    assert len(foreign._pf_slab.uploads) == 3 and len(foreign._pf_slab.downloads) == 3
+    with pytest.raises(TypeError):
+        bad = SimpleNamespace(nx=16, ny=12, fields={k: np.zeros((14, 18), dtype=np.float32) for k in "uvp"}, meta={})
+        step(cfg, bad, ResidualManager(), 0)
+
+
+# ------------------------------------------------------------------ solve_pressure_poisson seam
+def test_solve_pressure_poisson_diagnostics_and_modes(slab_cls):
+    from pyflow.core.ghost_fields import allocate_state, interior_view
+    from pyflow.linear_solvers.interface import NegLaplacianPinned
+    from pyflow.linear_solvers.preconditioners import jacobi_preconditioner
+    from pyflow.solvers.pressure_solver import solve_pressure_poisson
+    nx, ny = 24, 20
+    cfg = SimpleNamespace(lin_tol=1e-10, lin_maxiter=300, diagnostics=False)
+    results = {}
+    for tag, kw, cfgkw in (("auto", {}, {}), ("none", {}, dict(enable_jacobi_pc=False)),
+                           ("explicit", dict(preconditioner=jacobi_preconditioner(NegLaplacianPinned(nx, ny, 1.0, 1.0))),
+                            dict(enable_jacobi_pc=False))):
+        st = allocate_state(nx, ny)
+        interior_view(st.fields["u"])[ny // 3, nx // 3] = 1.0
+        c = SimpleNamespace(**{**vars(cfg), **cfgkw})
+        p, diag = solve_pressure_poisson(st, 0.01, 1.0, 1.0, c, **kw)
+        ost = orc.allocate_state(nx, ny)
+        orc.interior(ost.fields["u"])[ny // 3, nx // 3] = 1.0
+        oc = SimpleNamespace(**{**vars(cfg), "enable_jacobi_pc": tag != "none"})
+        op, odiag = orc.solve_pressure_poisson(ost, 0.01, 1.0, 1.0, oc)
+        assert np.array_equal(p, op) and p.shape == (ny, nx)
+        for k in ("Rp_iterations", "Rp_residual", "Rp_converged", "Rp_method", "divergence_norm",
+                  "divergence_norm_initial"):
+            assert diag[k] == odiag[k], (tag, k)
+        assert set(diag) >= {"lin_residual_norm", "lin_residual_rel", "divergence_reduction_factor",
+                             "divergence_norm_after_raw", "divergence_norm_final"}
+        assert np.array_equal(st.fields["u"], ost.fields["u"]) and np.array_equal(st.fields["p"], ost.fields["p"])
+        results[tag] = p
+    assert np.array_equal(results["auto"], results["explicit"])
+    # reference tests/test_preconditioner_effect.py:23: preconditioned and plain solves agree to 1e-9
+    assert np.max(np.abs(results["auto"] - results["none"])) <= 1e-9 * max(1.0, np.max(np.abs(results["none"])))
+    with pytest.raises(NotImplementedError):
+        solve_pressure_poisson(allocate_state(nx, ny), 0.01, 1.0, 1.0, cfg, preconditioner=object())
+    # manufactured / Dirichlet mode (rhs_override): velocities untouched, p solves lap(p) = rhs
+    X, Y = np.meshgrid(np.linspace(0, 1, 14), np.linspace(0, 1, 11))
+    rhs = np.zeros((11, 14))
+    rhs[1:-1, 1:-1] = (-2.0 * np.pi ** 2 * np.sin(np.pi * X) * np.sin(np.pi * Y))[1:-1, 1:-1]
+    st = allocate_state(14, 11)
+    interior_view(st.fields["u"])[:] = 3.0
+    mcfg = SimpleNamespace(lin_tol=1e-10, lin_maxiter=500, diagnostics=False)
+    p, diag = solve_pressure_poisson(st, 1.0, 1 / 13, 1 / 10, mcfg, rhs_override=rhs.reshape(-1))
+    op, odiag = orc.solve_manufactured(orc.allocate_state(14, 11), 1 / 13, 1 / 10, mcfg, rhs.reshape(-1))
+    assert np.array_equal(p, op) and diag["Rp_iterations"] == odiag["Rp_iterations"]
+    assert diag["divergence_norm"] == odiag["divergence_norm"] and diag["divergence_norm_initial"] is None
+    assert np.all(interior_view(st.fields["u"]) == 3.0) and np.array_equal(interior_view(st.fields["p"]), op)
+
+
+# ------------------------------------------------------------------ driver, checkpoint, restart
+def test_driver_protocol_checkpoint_and_restart(slab_cls, tmp_path):
+    from pyflow.config.model import SimulationConfig
+    from pyflow.drivers.simulation_driver import SimulationDriver
+    from pyflow.io.checkpoint import load_checkpoint
+    cfg = SimulationConfig(nx=20, ny=16, Re=100.0, advection_scheme="quick", lin_maxiter=300, diagnostics=False)
+    ck = str(tmp_path / "ck.npz")
+    drv = SimulationDriver(cfg)
+    seen, states = [], []
+    for st, res, diag in drv.run(max_steps=5, checkpoint_path=ck, checkpoint_interval=2):
+        seen.append((diag["iteration"], diag["dt"], res["continuity"], diag.get("checkpoint_written")))
+        states.append(st)
+        ys, uc = diag["u_centerline"]
+        assert len(ys) == 16 and ys[-1] == 15.0 and uc == st.fields._slab.u[:, 10].tolist()
+        assert diag["wall_time"] >= 0.0
+    assert [s[0] for s in seen] == [0, 1, 2, 3, 4] and all(s is states[0] for s in states)
+    assert drv.iteration == 5 and all(s[3] is None for s in seen)          # written AFTER the yield
+    slab = drv.state.fields._slab
+    # checkpoints at it = 0, 2, 4 read the fields through the read-only accessor: nothing is re-uploaded
+    assert slab.uploads == [("u", "v", "p")] and len(slab.downloads) == 9
+    st2, meta = load_checkpoint(ck)
+    assert meta["iteration"] == 4 and meta["structured_config_hash"] == cfg.config_hash
+    ost, odiags = orc.run(cfg, 5)
+    for f in ("u", "v", "p"):
+        assert np.array_equal(st2.fields[f], ost.fields[f])
+    assert [s[1] for s in seen] == [d["dt"] for d in odiags]
+    # restart: meta (dt_prev, history) is not checkpointed, exactly as in the reference, so the resumed
+    # run restarts the dt ramp; compare with the oracle doing the same
+    drv2 = SimulationDriver(cfg, st2)
+    out = list(drv2.run(max_steps=7, start_iteration=meta["iteration"] + 1))
+    assert [d["iteration"] for _s, _r, d in out] == [5, 6]
+    ost.meta.clear()
+    for it in (5, 6):
+        _, _, od = orc.step(cfg, ost, it)
+    assert out[-1][2]["dt"] == od["dt"] and np.array_equal(st2.fields["u"], ost.fields["u"])
+
+
+def test_nan_is_reported_and_logged_not_raised(slab_cls, tmp_path, monkeypatch):
+    from pyflow.core.ghost_fields import allocate_state, interior_view
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    monkeypatch.chdir(tmp_path)
+    buf = io.StringIO()
+    cfg = make_cfg(nx=10, ny=10, log_stream=buf, emergency_checkpoint_path=str(tmp_path / "em.npz"))
+    st = allocate_state(10, 10)
+    interior_view(st.fields["u"])[4, 4] = np.nan
+    _, res, diag = step(cfg, st, ResidualManager(), 0)
+    assert diag["nan_detected"] is True and diag["Rp_converged"] is False and diag["Rp_iterations"] == 300
+    assert np.isnan(res["Ru"]) or np.isnan(res["continuity"])
+    recs = [json.loads(line) for line in buf.getvalue().splitlines()]
+    assert [r["type"] for r in recs] == ["step", "error", "emergency_checkpoint"]
+    assert recs[1]["reason"] == "nan_detected" and recs[0]["nan"] is True
+    assert (tmp_path / "em_FAIL_NAN.npz").exists()
+
+
+# ------------------------------------------------------------------ CLI run loop, in process
+def test_cli_run_json_stream_checkpoint_restart(slab_cls, tmp_path, capsys):
+    from pyflow import cli
+    ck = str(tmp_path / "ck.npz")
+    rc = cli.main(["run", "--nx", "16", "--ny", "12", "--steps", "4", "--json-stream", "--checkpoint", ck,
+                   "--checkpoint-interval", "1", "--seed", "3"])
+    assert rc == 0
+    lines = [json.loads(line) for line in capsys.readouterr().out.splitlines() if line.startswith("{")]
+    assert [p["iteration"] for p in lines] == [0, 1, 2, 3] and all(p["type"] == "step" for p in lines)
+    first = lines[1]
+    assert set(first) == {"type", "iteration", "dt", "CFL", "continuity", "wall_time", "residuals", "diagnostics",
+                          "run_meta"}
+    assert set(first["residuals"]) == {"Ru", "Rv", "Rp", "continuity"} and first["run_meta"] == {"seed": 3}
+    assert {"Rp_iterations", "Rp_residual", "Rp_converged", "Rp_method", "divergence_norm", "nan_detected",
+            "u_centerline", "plateau_Ru", "max_residual", "residual_drop_Ru_orders", "nu",
+            "seed"} <= set(first["diagnostics"])
+    ocfg = make_cfg(nx=16, ny=12, Re=100.0)
+    _, odiags = orc.run(ocfg, 4)
+    assert [p["dt"] for p in lines] == [d["dt"] for d in odiags]
+    assert [p["continuity"] for p in lines] == [d["continuity"] for d in odiags]
+    # restart from the checkpoint of iteration 3 with the same configuration: continues at 4
+    same = ["--checkpoint", ck, "--checkpoint-interval", "1", "--seed", "3"]     # part of the hashed configuration
+    rc = cli.main(["run", "--nx", "16", "--ny", "12", "--steps", "6", "--json-stream", "--restart", ck, *same])
+    assert rc == 0
+    lines = [json.loads(line) for line in capsys.readouterr().out.splitlines() if line.startswith("{")]
+    assert [p["iteration"] for p in lines] == [4, 5]
+    # a different configuration is refused with exit code 3
+    rc = cli.main(["run", "--nx", "16", "--ny", "12", "--re", "55", "--steps", "6", "--restart", ck, *same])
+    assert rc == 3
+
+
+# ------------------------------------------------------------------ alternate dict-payload driver
+def test_alternate_driver_runs_on_the_device_statistics(slab_cls):
+    import pyflow.driver.simulation_driver as alt
+    cfg = alt.DriverConfig(nx=16, ny=16, max_steps=4, report_interval=1000)
+    drv = alt.SimulationDriver(cfg, alt.PhysicsConfig(lin_maxiter=200))
+    payloads = list(drv.run())
+    assert len(payloads) == 4 and all(p["state"] is drv.state for p in payloads)
+    slab = drv.state.fields._slab
+    m, n = slab.divergence_stats(drv.state.meta["dx"], drv.state.meta["dy"])
+    assert payloads[-1]["divergence_mean"] == m and payloads[-1]["divergence_mean_free_norm"] == n
+    assert slab.downloads == []                            # the statistics are device reductions, no field D2H
+
+
+# ------------------------------------------------------------------ array-level operator seams
+def test_operator_seams_signatures_and_shapes(slab_cls):
+    from pyflow.linear_solvers.interface import LinearSolveResult, NegLaplacianPinned, solve
+    from pyflow.linear_solvers.preconditioners import jacobi_preconditioner
+    from pyflow.numerics import fluid_ops
+    from pyflow.numerics.core_ops_coherent import divergence_coherent, gradient_coherent, laplacian_coherent
+    from pyflow.numerics.operators.advection import advect_quick, advect_upwind
+    rng = np.random.default_rng(5)
+    p, u, v = (rng.standard_normal((9, 13)) for _ in range(3))
+    dx, dy = 0.5, 0.25
+    gx, gy = gradient_coherent(p, dx, dy)
+    assert np.array_equal(laplacian_coherent(p, dx, dy), divergence_coherent(gx, gy, dx, dy))
+    assert np.array_equal(fluid_ops.divergence(u, v, dx, dy), orc.divergence_central(u, v, dx, dy))
+    cgx, cgy = fluid_ops.gradient(p, dx, dy)
+    ogx, ogy = orc.gradient_central(p, dx, dy)
+    assert np.array_equal(cgx, ogx) and np.array_equal(cgy, ogy)
+    assert np.array_equal(fluid_ops.laplacian(p, dx, dy), orc.laplacian_central(p, dx, dy))
+    assert np.array_equal(advect_quick(u, v, p, dx, dy), orc.advect_quick(u, v, p, dx, dy))
+    assert np.array_equal(advect_upwind(u, v, p, dx, dy), orc.advect_upwind(u, v, p, dx, dy))
+    from pyflow.core.ghost_fields import allocate_state, interior_view
+    st = allocate_state(13, 9)
+    interior_view(st.fields["u"])[:] = u
+    interior_view(st.fields["v"])[:] = v
+    fluid_ops.apply_pressure_correction(st, p, 0.01, dx, dy)
+    ou, ov = orc.pressure_correction_central(u, v, p, 0.01, dx, dy)
+    assert np.array_equal(interior_view(st.fields["u"]), ou) and np.array_equal(interior_view(st.fields["v"]), ov)
+    assert np.array_equal(interior_view(st.fields["p"]), p)
+    lg = fluid_ops.legacy_grad_p_state(st, dx, dy)
+    assert np.array_equal(lg[0], ogx) and np.array_equal(fluid_ops.legacy_divergence_state(st, dx, dy),
+                                                         orc.divergence_central(ou, ov, dx, dy))
+    with pytest.raises(ValueError):
+        fluid_ops.gradient(np.zeros((1, 5)), 1.0, 1.0)
+    # linear-solve seam: x0 = 0, scipy semantics of converged / iterations
+    A = NegLaplacianPinned(13, 9, dx, dy)
+    b = rng.standard_normal(13 * 9)
+    b -= b.mean()
+    b[0] = 0.0
+    r = solve(A, b, method="cg", tol=1e-10, maxiter=2000, M=jacobi_preconditioner(A))
+    assert isinstance(r, LinearSolveResult) and r.converged and r.iterations == 0 and r.method == "cg"
+    assert np.linalg.norm(A.matvec(r.x) - b) <= 1e-9 * np.linalg.norm(b) and r.x.shape == b.shape
+    r2 = solve(A, b, method="cg", tol=1e-10, maxiter=3)
+    assert (not r2.converged) and r2.iterations == 3
+    with pytest.raises(NotImplementedError):
+        solve(A, b, method="bicgstab")
+    with pytest.raises(NotImplementedError):
+        solve(np.eye(4), np.ones(4), method="cg")

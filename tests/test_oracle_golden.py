@@ -32,6 +32,21 @@ def test_central_divergence_right_column_quirk(golden):
     assert np.all(d[1:-1, -1] == 0.0) and np.any(d[1:-1, 0] != 0.0)
 
 
+LEGACY_TAGS = ["8x8", "16x12", "5x9", "2x2", "3x3", "2x7", "9x2", "33x17", "70x66"]
+
+
+@pytest.mark.parametrize("tag", LEGACY_TAGS)
+def test_legacy_central_operators_bit_exact(golden, tag):
+    """fluid_ops.gradient / laplacian / apply_pressure_correction (numerics/fluid_ops.py:43-125)."""
+    g = {k.split("/", 1)[1]: v for k, v in golden["legacy_ops"].items() if k.startswith(tag + "/")}
+    dx, dy, dt = (float(t) for t in g["dxdydt"])
+    gx, gy = orc.gradient_central(g["p"], dx, dy)
+    assert np.array_equal(gx, g["gx"]) and np.array_equal(gy, g["gy"])
+    assert np.array_equal(orc.laplacian_central(g["p"], dx, dy), g["lap"])
+    uc, vc = orc.pressure_correction_central(g["u"], g["v"], g["p"], dt, dx, dy)
+    assert np.array_equal(uc, g["ucorr"]) and np.array_equal(vc, g["vcorr"])
+
+
 def rel(a, b):
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) or 1.0))
 

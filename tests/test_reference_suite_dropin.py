@@ -1,0 +1,88 @@
+"""The reference's OWN test-suite, unmodified, run against the drop-in host package.
+
+Only where ``/root/reference`` exists (the build container; skipped on the GPU box, which
+never sees the reference).  The reference's test files are copied to a temporary directory
+at run time -- never into this repository -- next to a ``conftest.py`` / ``sitecustomize.py``
+that swap the GPU context for the oracle-backed stand-in (``tests/cpu_slab.py``), in the
+pytest process and in the ``python -m pyflow.cli`` subprocesses the CLI tests start.  What
+this proves is the HOST side of the drop-in: same import paths, signatures, dictionaries,
+State semantics, CLI flags / exit codes / JSON schema, checkpoint layout, as exercised by
+the reference's own assertions.  (The CUDA kernels are checked by the ``-m gpu`` suite.)
+
+Out of scope: the AI front-end, the benchmark harness and mf_ops
+test files.  Known reference test bugs: three tests call the CLI
+without its ``run`` sub-command or with a flag that does not exist and fail against the
+reference itself; they must fail here in the same way.
+"""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_TESTS = "/root/reference/tests"
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference is not present on this machine")
+
+OUT_OF_SCOPE = ("test_ai_control_layer.py", "test_benchmark_harness.py", "test_matrixfree_operator.py")
+REFERENCE_TEST_BUGS = {            # fail against the unmodified reference too (argparse: missing `run`)
+    "test_cli_json_stream.py::test_cli_json_stream_basic",
+    "test_cli_smoke.py::test_cli_json_smoke",
+}
+
+CONFTEST = '''
+import pytest
+
+@pytest.fixture(autouse=True)
+def _cpu_slab(monkeypatch):
+    import cpu_slab
+    cpu_slab.install(monkeypatch)
+    yield
+    from pyflow.logging.structured import close_all_jsonl_logs
+    close_all_jsonl_logs()
+'''
+
+SITECUSTOMIZE = '''
+import os
+if os.environ.get("PYFLOW_TEST_CPU_SLAB") == "1":
+    try:
+        import cpu_slab
+        cpu_slab.install(None)
+    except Exception as exc:            # pragma: no cover
+        print(f"[sitecustomize] cpu_slab not installed: {exc}")
+'''
+
+
+def test_reference_suite_passes_against_the_dropin_host_package(tmp_path):
+    # layout of the reference checkout: <root>/tests next to <root>/src (some CLI tests build
+    # PYTHONPATH=<root>/src themselves), with OUR package standing where the reference's is
+    work = tmp_path / "tests"
+    work.mkdir()
+    for src in glob.glob(os.path.join(REF_TESTS, "*.py")):
+        name = os.path.basename(src)
+        if name != "conftest.py" and name not in OUT_OF_SCOPE:
+            shutil.copy(src, work / name)
+    (work / "conftest.py").write_text(CONFTEST)
+    site = tmp_path / "src"
+    site.mkdir()
+    (site / "sitecustomize.py").write_text(SITECUSTOMIZE)
+    os.symlink(os.path.join(ROOT, "pyflow-solver_b200", "pyflow"), site / "pyflow")
+    os.symlink(os.path.join(ROOT, "oracle", "pyflow_oracle.py"), site / "pyflow_oracle.py")
+    os.symlink(os.path.join(ROOT, "tests", "cpu_slab.py"), site / "cpu_slab.py")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = str(site)
+    env["PYFLOW_TEST_CPU_SLAB"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-rf", str(work)],
+                       cwd=str(work), env=env, capture_output=True, text=True, timeout=900)
+    tail = r.stdout[-4000:] + r.stderr[-2000:]
+    failed = {line.split(" - ")[0].replace("FAILED ", "").strip() for line in r.stdout.splitlines()
+              if line.startswith("FAILED ")}
+    summary = [line for line in r.stdout.splitlines() if " passed" in line]
+    assert summary, tail
+    npassed = int(summary[-1].split(" passed")[0].split()[-1])
+    assert "error" not in summary[-1], tail                       # no collection / import errors
+    assert failed <= REFERENCE_TEST_BUGS, f"unexpected failures: {sorted(failed - REFERENCE_TEST_BUGS)}\n{tail}"
+    assert npassed >= 48, tail
