@@ -204,6 +204,17 @@ def workload_config(name, wl, n_gpus):
     }
 
 
+def cg_kernel_name(nx, ny_local, world, sm_count=148):
+    """Which CG kernel pf_step dispatches to for this slab (mirror of solve_on_device in csrc/pf_api.cu)."""
+    rows = -(-ny_local // sm_count)
+    if (world == 1 and nx % 2 == 0 and nx <= 2048 and rows * (nx // 2) <= 8 * 512
+            and 8 * nx * ((rows + 2) * 2 + rows) <= 200 * 1024):
+        return "k_cg_small<unit> (shared-memory-resident CG; L2/latency-bound workload, HBM roofline informational)"
+    if nx % 1024 == 0:
+        return "k_cg_tmad<unit> (TMA-fed persistent CG)"
+    return "k_cg_persistent<unit> (register-window persistent CG)"
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_gpu_arm(args, wl, rank, world):
     import numpy as np
@@ -317,7 +328,7 @@ def run_gpu_arm(args, wl, rank, world):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_cg_tmad<unit> (TMA-fed persistent CG)" if nx % 1024 == 0 else "k_cg_persistent<unit>",
+                "kernel": cg_kernel_name(nx, ny_global // world, world),
                 "algorithmic_bytes_per_launch": cg_bytes / max(1, len(cg_iters)),
                 "avg_launch_ms": statistics.mean(cg_ms) if cg_ms else None,
                 "frac_of_nominal_8TBs": achieved / 8000.0,

@@ -1,5 +1,5 @@
 import os, sys, ctypes as C
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, 'pyflow-solver_b200'))
 import numpy as np, torch, torch.distributed as dist
 from types import SimpleNamespace

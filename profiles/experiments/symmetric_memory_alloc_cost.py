@@ -1,5 +1,5 @@
 import os, sys, statistics
-sys.path.insert(0, '/root/repo/pyflow-solver_b200'); sys.path.insert(0,'/root/repo')
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(ROOT, 'pyflow-solver_b200')); sys.path.insert(0, ROOT)
 import torch, torch.distributed as dist
 from types import SimpleNamespace
 os.environ.setdefault("MASTER_ADDR","127.0.0.1"); os.environ.setdefault("MASTER_PORT","29811"); os.environ.setdefault("RANK","0"); os.environ.setdefault("WORLD_SIZE","1")
