@@ -9,7 +9,7 @@ Runs only where ``/root/reference`` exists (the build container).  It
      which travel to the GPU box where the reference itself cannot.
 
 Usage:  python oracle/make_golden.py [part ...]   (exit code != 0 on any mismatch; parts: operators,
-        legacy_ops, pressure, trajectories, config -- default all)
+        legacy_ops, pressure, trajectories, config, config2 -- default all)
 """
 from __future__ import annotations
 
@@ -302,6 +302,46 @@ def trajectory_vectors():
         json.dump(meta, fh, indent=1, sort_keys=True)
 
 
+def config2_vectors(steps=4):
+    """BASELINE config 2 (512x512, Re=1000, QUICK, lin_maxiter=300) stepped by the UNMODIFIED reference
+    (about 16 s per step: the lil_matrix assembly and the Python advection loops).  The fields are 2 MiB
+    each, so the fixture keeps per-step scalars, norms, the centre lines and an every-16th-cell sample."""
+    print(f"config 2 (512^2), {steps} reference steps")
+    kw = dict(nx=512, ny=512, Re=1000.0, advection_scheme="quick", lin_maxiter=300)
+    cfg = make_cfg(kw)
+    st = ref_allocate(cfg.nx, cfg.ny)
+    tr = ResidualManager()
+    _TRUE_ITERS.clear()
+    rows = []
+    for it in range(steps):
+        _, res, diag = quiet(ref_step, cfg, st, tr, it)
+        rows.append([diag["dt"], diag["CFL"], res["Ru"], res["Rv"], res["continuity"], diag["Rp_iterations"],
+                     diag["Rp_residual"], float(diag["Rp_converged"]), diag["divergence_norm"]])
+        print(f"    step {it}: dt={diag['dt']:.6g} continuity={res['continuity']:.6e}", flush=True)
+    ost, odiags = orc.run(make_cfg(kw), steps)
+    for f in ("u", "v", "p"):
+        check(f"config2 field {f}", ost.fields[f], st.fields[f])
+    check("config2 dt", [d["dt"] for d in odiags], [r[0] for r in rows])
+    check("config2 true iters", [d["true_iterations"] for d in odiags], list(_TRUE_ITERS))
+    nst, _ = orc.run(make_cfg(kw), steps, dot=orc.pairwise_dot)
+    noise = {f: float(np.linalg.norm(interior_view(st.fields[f]) - orc.interior(nst.fields[f]))
+                      / (np.linalg.norm(interior_view(st.fields[f])) or 1.0)) for f in ("u", "v", "p")}
+    print(f"    noise floor config2: {noise}")
+    out = {"scalars": np.array(rows), "true_iters": np.array(_TRUE_ITERS)}
+    for f in ("u", "v", "p"):
+        a = interior_view(st.fields[f])
+        out[f"{f}/norm"] = np.array([np.linalg.norm(a), np.abs(a).max(), a.sum()])
+        out[f"{f}/sample16"] = a[::16, ::16].copy()
+        out[f"{f}/center_col"] = a[:, cfg.nx // 2].copy()
+        out[f"{f}/center_row"] = a[cfg.ny // 2, :].copy()
+        out[f"{f}/top_rows"] = a[-3:, :].copy()
+    np.savez_compressed(os.path.join(GOLD, "config2_512.npz"), **out)
+    with open(os.path.join(GOLD, "config2_512.json"), "w") as fh:
+        json.dump({"cfg": kw, "steps": steps, "noise_floor": noise,
+                   "columns": ["dt", "CFL", "Ru", "Rv", "continuity", "Rp_iterations", "Rp_residual",
+                               "Rp_converged", "divergence_norm"]}, fh, indent=1, sort_keys=True)
+
+
 def config_vectors():
     print("config / checkpoint")
     from pyflow.config.model import SimulationConfig
@@ -325,7 +365,7 @@ def config_vectors():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     parts = {"operators": operator_vectors, "legacy_ops": legacy_ops_vectors, "pressure": pressure_vectors,
-             "trajectories": trajectory_vectors, "config": config_vectors}
+             "trajectories": trajectory_vectors, "config": config_vectors, "config2": config2_vectors}
     only = sys.argv[1:]                      # e.g. `make_golden.py legacy_ops` regenerates one fixture file
     for name, fn in parts.items():
         if not only or name in only:

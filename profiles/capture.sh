@@ -1,0 +1,41 @@
+#!/usr/bin/env bash
+# profiles/capture.sh -- the commands the files in profiles/ come from (run on a B200 box from the
+# repo root, e.g. `gpurun --timeout 900 -- 'bash profiles/capture.sh launches full4096'`).
+# Outputs go to gpurun_out/; copy the summaries you want kept into profiles/.
+# Numbers printed by a run under ncu / compute-sanitizer are never bench values.
+set -u
+mkdir -p gpurun_out
+for what in "$@"; do
+  case "$what" in
+    tests)        # parity suite
+      python -m pytest tests -m gpu -x -q 2>&1 | tee gpurun_out/gpu_tests.log | tail -5 ;;
+    bench)        # headline line + config 2 alone
+      python bench.py > gpurun_out/bench_cavity4096.json 2> gpurun_out/bench_cavity4096.err
+      python bench.py --workload cavity512 --steps 50 --no-cpu-baseline > gpurun_out/bench_cavity512.json ;;
+    launches)     # launch list of the bench command (kernel shares of a step)
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+          python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1 ;;
+    full4096)     # ncu --set full of the TMA-fed CG kernel (4096^2): DRAM bytes -> profiles/cg_traffic.json
+      ncu --set full --clock-control none --import-source on -k regex:k_cg_tmad -s 2 -c 1 \
+          -o gpurun_out/cg_tmad_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline \
+          > gpurun_out/cg_tmad_full.log 2>&1
+      ncu -i gpurun_out/cg_tmad_full.ncu-rep --page raw --csv | grep -E \
+          'dram__bytes_(read|write)\.sum|gpu__dram_throughput|gpu__time_duration|launch__registers_per_thread|smsp__issue_active|long_scoreboard' \
+          > gpurun_out/cg_tmad_full_summary.txt ;;
+    full512)      # the shared-memory-resident CG kernel (512^2): what bounds 5.6 us per iteration
+      ncu --set full --clock-control none --import-source on -k regex:k_cg_small -s 2 -c 1 \
+          -o gpurun_out/cg_small_full -f python bench.py --workload cavity512 --steps 1 --warmup 3 --no-cpu-baseline \
+          > gpurun_out/cg_small_full.log 2>&1
+      ncu -i gpurun_out/cg_small_full.ncu-rep --page raw --csv | grep -E \
+          'dram__bytes_(read|write)\.sum|lts__t_bytes|gpu__time_duration|launch__registers_per_thread|smsp__issue_active|smsp__average_warp.*stall|l1tex__data_bank_conflicts' \
+          > gpurun_out/cg_small_full_summary.txt ;;
+    sanitize)     # memcheck + racecheck + synccheck of every CG kernel variant on small grids
+      for tool in memcheck racecheck synccheck; do
+        timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 \
+          python -m pytest tests/test_gpu_parity.py -x -q -k "pcg_matches or forced_cg_kernel or strip_and_chunk" \
+          > gpurun_out/sanitizer_$tool.log 2>&1
+        echo "$tool rc=$?" | tee -a gpurun_out/sanitizer_summary.txt
+      done ;;
+    *) echo "unknown target $what (tests bench launches full4096 full512 sanitize)"; exit 2 ;;
+  esac
+done

@@ -9,6 +9,7 @@ Nothing here reads /root/reference (it does not exist on the GPU box).
 import os
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -63,11 +64,37 @@ def golden():
     import json
     import numpy as np
     out = {}
-    for name in ("operators", "legacy_ops", "pressure", "trajectories"):
+    for name in ("operators", "legacy_ops", "pressure", "trajectories", "config2_512"):
         with np.load(os.path.join(GOLDEN, f"{name}.npz")) as z:
             out[name] = {k: z[k] for k in z.files}
     with open(os.path.join(GOLDEN, "trajectories.json")) as fh:
         out["trajectories_meta"] = json.load(fh)
+    with open(os.path.join(GOLDEN, "config2_512.json")) as fh:
+        out["config2_512_meta"] = json.load(fh)
     with open(os.path.join(GOLDEN, "config_hashes.json")) as fh:
         out["config"] = json.load(fh)
     return out
+
+
+def check_config2_summary(golden, fields, rows, true_iters, tol_factor=100.0, scalar_rtol=1e-8, residual_rtol=1e-8):
+    """Compare a 512^2 run (BASELINE config 2, 4 steps from rest) with the summary fixture written from the
+    UNMODIFIED reference (oracle/make_golden.py config2): dt / CFL bit-identical, iteration counts equal, every
+    sampled field value within max(1e-9, tol_factor x the reference's own summation-order noise) relative L2."""
+    g, meta = golden["config2_512"], golden["config2_512_meta"]
+    ref = g["scalars"]
+    assert [r[0] for r in rows] == list(ref[:, 0]) and [r[1] for r in rows] == list(ref[:, 1])      # dt, CFL
+    assert list(true_iters) == list(g["true_iters"])
+    for k in range(2, 9):                                   # Ru, Rv, continuity, Rp_it, Rp_res, Rp_conv, div_norm
+        a, b = np.array([r[k] for r in rows], dtype=float), ref[:, k]
+        rtol = 0.0 if k in (5, 7) else residual_rtol if k in (6, 8) else scalar_rtol
+        assert np.allclose(a, b, rtol=rtol, atol=0.0), (meta["columns"][k], a, b)
+    for f in ("u", "v", "p"):
+        a = fields[f]
+        bar = max(1e-9, tol_factor * meta["noise_floor"][f])
+        for key, got in (("sample16", a[::16, ::16]), ("center_col", a[:, 256]), ("center_row", a[256, :]),
+                         ("top_rows", a[-3:, :])):
+            want = g[f"{f}/{key}"]
+            err = float(np.linalg.norm(got - want) / (np.linalg.norm(want) or 1.0))
+            assert err < bar, (f, key, err)
+        n = np.array([np.linalg.norm(a), np.abs(a).max(), a.sum()])
+        assert np.allclose(n[:2], g[f"{f}/norm"][:2], rtol=1e-9, atol=0.0), (f, n, g[f"{f}/norm"])

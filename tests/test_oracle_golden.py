@@ -155,3 +155,23 @@ def test_c_oracle_cg_matches_numpy_oracle():
                            orc.jacobi_inverse_diagonal(nx, ny, dx, dy))
     x1, info1, it1 = orc_c.pcg_pinned(b, nx, ny, dx, dy, 1e-10, 7)
     assert info0 == info1 == 7 and it1 == 7 and rel(x1, x0) < 1e-12
+
+
+# ---------------------------------------------------------------- BASELINE config 2 against the reference itself
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_config2_512_vs_reference_summary(golden, impl):
+    """512x512, Re=1000, QUICK, 300 CG iterations per step, 4 steps from rest: both oracles against the summary
+    fixture the unmodified reference wrote (tests/golden/config2_512.*)."""
+    from conftest import check_config2_summary
+    meta = golden["config2_512_meta"]
+    cfg = SimpleNamespace(lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10, disable_advection=False,
+                          diagnostics=False, **meta["cfg"])
+    st = orc.allocate_state(cfg.nx, cfg.ny)
+    ws = orc_c.Workspace(cfg.nx, cfg.ny) if impl == "c" else None
+    rows, iters = [], []
+    for it in range(meta["steps"]):
+        _, res, d = orc_c.step(cfg, st, it, ws) if impl == "c" else orc.step(cfg, st, it)
+        rows.append([d["dt"], d["CFL"], res["Ru"], res["Rv"], res["continuity"], d["Rp_iterations"], d["Rp_residual"],
+                     float(d["Rp_converged"]), d["divergence_norm"]])
+        iters.append(d["true_iterations"])
+    check_config2_summary(golden, {f: orc.interior(st.fields[f]) for f in ("u", "v", "p")}, rows, iters)
