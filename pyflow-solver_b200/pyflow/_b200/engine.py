@@ -6,8 +6,9 @@ Two kinds of state reach ``step`` / ``solve_pressure_poisson``:
   steps; only host-touched fields are uploaded, nothing is downloaded until
   somebody reads ``state.fields[...]``;
 * a foreign object with plain ``fields`` / ``meta`` dicts (e.g. the reference's
-  own dataclass): *eager* mode -- upload before, download after, every call,
-  into the caller's arrays in place (exact reference semantics, slower).
+  own dataclass), or our ``State`` with ``fields.eager`` set: *eager* mode --
+  upload before, download after, every call, into the caller's arrays in place
+  (exact reference semantics, slower).
 """
 from __future__ import annotations
 
@@ -47,23 +48,29 @@ class Binding:
             f.mark_device_updated()
             f._prestep = prestep_next
         else:
-            self.slab.download(u=f["u"], v=f["v"], p=f["p"])
+            if isinstance(f, SyncedFields):            # our State in eager mode: same arrays, nothing left stale
+                self.slab.download(u=f.peek("u"), v=f.peek("v"), p=f.peek("p"))
+                f._stale.clear()
+                f._prestep = None
+            else:
+                self.slab.download(u=f["u"], v=f["v"], p=f["p"])
 
 
 def attach(state) -> Binding:
     """Make the device copy of ``state`` current and return its binding."""
     f = state.fields
-    lazy = isinstance(f, SyncedFields)
-    u = f.peek("u") if lazy else f["u"]
+    ours = isinstance(f, SyncedFields)
+    lazy = ours and not f.eager
+    u = f.peek("u") if ours else f["u"]
     nx, ny = _dims(u)
-    slab = f._slab if lazy else getattr(state, "_pf_slab", None)
+    slab = f._slab if ours else getattr(state, "_pf_slab", None)
     if slab is None or (slab.nx, slab.ny_local) != (nx, ny):
         if getattr(state, "slab", None) is not None:      # row slab of a multi-GPU grid
             from .distributed import make_slab
             slab = make_slab(state)
         else:
             slab = DeviceSlab(nx, ny)
-        if lazy:
+        if ours:
             f._slab = slab
             f._touched.update(("u", "v", "p"))
             f._stale.clear()
@@ -80,5 +87,7 @@ def attach(state) -> Binding:
             f._touched.clear()
             f._prestep = None
     else:
+        # eager: the host arrays are authoritative before every call.  (For our own State, __getitem__ first pulls
+        # back anything a previous lazy call left stale.)
         slab.upload(u=_as_field(f["u"]), v=_as_field(f["v"]), p=_as_field(f["p"]))
     return Binding(state, slab, lazy)

@@ -14,7 +14,13 @@ step re-uploads it.  A consumer that only looks at the yielded scalars never
 pays a field transfer (at 4096^2 the three fields are 400 MB per step).
 Limitation, by design: an array obtained from ``state.fields`` reflects the
 device contents at the time of that access; re-read ``state.fields[name]`` after
-the next step (every reference call site does).
+the next step (every reference call site and every reference test does).  A
+caller that keeps array views across steps WITHOUT going back through
+``state.fields`` -- reading them after a step, or writing into them -- can ask
+for the reference's exact live-array semantics with ``state.fields.eager = True``
+(or ``PYFLOW_B200_EAGER=1`` in the environment): all three fields are then
+uploaded before and downloaded after every step, into the same arrays, at the
+cost of those transfers.
 """
 from __future__ import annotations
 
@@ -36,6 +42,8 @@ class SyncedFields(dict):
         self._stale: set[str] = set()  # host copy older than the device copy
         self._touched: set[str] = set(_SOLVER_FIELDS)  # host copy possibly newer than the device copy
         self._prestep = None           # cached (max|u|, max|v|, sum div_central^2) of the device fields
+        import os
+        self.eager = os.environ.get("PYFLOW_B200_EAGER", "0") == "1"   # live-array semantics, see module docstring
 
     # -- device binding (used by solvers.solver) -----------------------------
     def peek(self, name: str) -> np.ndarray:

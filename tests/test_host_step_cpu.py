@@ -112,6 +112,35 @@ def test_fields_stay_on_the_device_between_steps(slab_cls):
         assert np.array_equal(st.fields[f], ost.fields[f])
 
 
+def test_eager_mode_gives_live_array_semantics(slab_cls, monkeypatch):
+    """``state.fields.eager = True``: views taken ONCE stay live across steps, both ways, like the reference's
+    plain numpy State (upload before / download after every call)."""
+    from pyflow.core.ghost_fields import allocate_state, interior_view
+    from pyflow.drivers.simulation_driver import SimulationDriver
+    cfg = make_cfg(nx=16, ny=12)
+    st = allocate_state(16, 12)
+    st.fields.eager = True
+    ui = interior_view(st.fields["u"])                     # taken once, never re-fetched
+    ost = orc.allocate_state(16, 12)
+    for k, (s_, _r, d) in enumerate(SimulationDriver(cfg, st).run(max_steps=4)):
+        orc.step(cfg, ost, k)
+        assert np.array_equal(ui, orc.interior(ost.fields["u"]))               # reads see the new step
+        assert d["u_centerline"][1] == ui[:, 8].tolist()
+        if k == 1:                                                              # writes through the old view count
+            ui[5, 5] += 0.125
+            orc.interior(ost.fields["u"])[5, 5] += 0.125
+    slab = st.fields._slab
+    assert len(slab.uploads) == 4 and len(slab.downloads) == 4 and all(len(t) == 3 for t in slab.uploads)
+    # default (lazy) mode for contrast: the old view is stale until state.fields is consulted again
+    st2 = allocate_state(16, 12)
+    u2 = interior_view(st2.fields["u"])
+    list(SimulationDriver(cfg, st2).run(max_steps=2))
+    assert not u2.any() and st2.fields._slab.downloads == []
+    assert interior_view(st2.fields["u"]) is not None and u2.any()              # same array, refreshed in place
+    monkeypatch.setenv("PYFLOW_B200_EAGER", "1")
+    assert allocate_state(4, 4).fields.eager is True
+
+
 def test_foreign_state_objects_are_synchronised_eagerly(slab_cls):
     """A state that is not ours (plain dict fields, e.g. the reference's dataclass): upload before and
     download after every call, into the caller's own arrays."""
