@@ -10,15 +10,25 @@ added to the diagnostics (:89-99); checkpoints are written AFTER the yield when
 
 The centre-line column comes back with the step's scalar read-back (ny doubles)
 instead of slicing a host array, so a yield costs no field transfer.
+
+New, opt-in: ``driver.async_checkpoint = True``, a truthy
+``config.async_checkpoint`` or ``PYFLOW_B200_ASYNC_CHECKPOINT=1`` hands due
+checkpoints to ``io.checkpoint.BackgroundCheckpointWriter``: the fields are
+snapshotted from HBM at the reference's point in the loop (after the yield) and
+hashed / compressed / renamed on a worker thread while the next steps run.  Same
+bytes on disk; the file of checkpoint k is complete before checkpoint k+1 starts
+and before the generator finishes or is closed.  Default: synchronous, as in the
+reference.
 """
 from __future__ import annotations
 
+import os
 import time
 from collections.abc import Callable, Generator
 from typing import Any
 
 from ..core.ghost_fields import State, SyncedFields, allocate_state, interior_view
-from ..io.checkpoint import save_checkpoint
+from ..io.checkpoint import BackgroundCheckpointWriter, save_checkpoint
 from ..residuals.manager import ResidualManager
 from ..solvers.solver import step
 
@@ -32,6 +42,7 @@ class SimulationDriver:
         self.allocate_fn = allocate
         self._t0 = None
         self.iteration = 0
+        self.async_checkpoint = False
 
     def ensure_state(self, nx: int, ny: int) -> State:
         if self.state is None:
@@ -62,6 +73,17 @@ class SimulationDriver:
             ) -> Generator[tuple[State, dict[str, float], dict[str, Any]], None, None]:
         self.iteration = start_iteration
         self._t0 = time.time()
+        writer = None
+        if checkpoint_path and (self.async_checkpoint or getattr(self.config, "async_checkpoint", False)
+                                or os.environ.get("PYFLOW_B200_ASYNC_CHECKPOINT", "0") == "1"):
+            writer = BackgroundCheckpointWriter()
+        try:
+            yield from self._loop(max_steps, progress, checkpoint_path, checkpoint_interval, writer)
+        finally:
+            if writer is not None:
+                writer.wait()                  # the last checkpoint is on disk when the generator ends or is closed
+
+    def _loop(self, max_steps, progress, checkpoint_path, checkpoint_interval, writer):
         while True:
             if max_steps is not None and self.iteration >= max_steps:
                 return
@@ -84,8 +106,11 @@ class SimulationDriver:
             if checkpoint_path and checkpoint_interval and checkpoint_interval > 0:
                 if self.iteration % checkpoint_interval == 0:
                     try:
-                        save_checkpoint(checkpoint_path, state, self.iteration,
-                                        diagnostics.get("time", diagnostics.get("wall_time", 0.0)), self.config)
+                        sim_time = diagnostics.get("time", diagnostics.get("wall_time", 0.0))
+                        if writer is not None:
+                            writer.submit(checkpoint_path, state, self.iteration, sim_time, self.config)
+                        else:
+                            save_checkpoint(checkpoint_path, state, self.iteration, sim_time, self.config)
                         diagnostics["checkpoint_written"] = True
                     except Exception:  # pragma: no cover
                         diagnostics["checkpoint_written"] = False

@@ -13,6 +13,15 @@ restart resets dt -- kept for interchangeability).
 
 Device note: fields are pulled from HBM with the read-only accessor, so writing
 a checkpoint does not force a re-upload on the next step.
+
+``BackgroundCheckpointWriter`` (new) takes the expensive
+part off the time loop: at 4096^2 the sha1 hashes and the deflate of 400 MB
+cost seconds per checkpoint against a 53 ms step.  ``submit`` snapshots the three
+fields straight from HBM into its own page-locked buffers (the host copies of
+the State are not touched) and a worker thread hashes, compresses and renames
+while the GPU keeps stepping; the bytes on disk are the same as the synchronous
+writer's.  One write is in flight at most; ``wait`` joins it and re-raises its
+error.
 """
 from __future__ import annotations
 
@@ -21,6 +30,7 @@ import io
 import json
 import os
 import tempfile
+import threading
 from typing import Any
 
 import numpy as np
@@ -71,10 +81,14 @@ def _meta(state, fields, iteration, sim_time, cfg, structured: bool) -> dict[str
 
 
 def save_checkpoint(path: str, state, iteration: int, sim_time: float, cfg: Any) -> str:
-    folder = os.path.dirname(path) or "."
-    os.makedirs(folder, exist_ok=True)
     fields = _host_fields(state)
     meta = _meta(state, fields, iteration, sim_time, cfg, structured=True)
+    return _write_npz(path, meta, fields)
+
+
+def _write_npz(path: str, meta: dict[str, Any], fields: dict[str, np.ndarray]) -> str:
+    folder = os.path.dirname(path) or "."
+    os.makedirs(folder, exist_ok=True)
     fd, tmp = tempfile.mkstemp(suffix=".tmp", dir=folder)
     try:
         with os.fdopen(fd, "wb") as fh:
@@ -92,6 +106,67 @@ def save_checkpoint(path: str, state, iteration: int, sim_time: float, cfg: Any)
             except Exception:
                 pass
     return path
+
+
+class BackgroundCheckpointWriter:
+    """Snapshot now, hash / compress / rename on a worker thread (see the module docstring)."""
+
+    def __init__(self):
+        self._thread: threading.Thread | None = None
+        self._error: BaseException | None = None
+        self._buffers: dict[str, np.ndarray] = {}
+        self.written = 0
+
+    def _buffer(self, name: str, like: np.ndarray) -> np.ndarray:
+        buf = self._buffers.get(name)
+        if buf is None or buf.shape != like.shape:
+            from ..core.ghost_fields import _zeros
+            buf = self._buffers[name] = _zeros(like.shape)
+        return buf
+
+    def _snapshot(self, state) -> dict[str, np.ndarray]:
+        f = state.fields
+        lazy = isinstance(f, SyncedFields)
+        snap = {}
+        for k in list(f.keys()):
+            host = f.peek(k) if lazy else f[k]
+            buf = self._buffer(k, host)
+            if lazy and k in f._stale and f._slab is not None:
+                # newest copy is in HBM: D2H straight into the snapshot; the ghost ring comes from the host array
+                buf[0, :], buf[-1, :], buf[:, 0], buf[:, -1] = host[0, :], host[-1, :], host[:, 0], host[:, -1]
+                f._slab.download(**{k: buf})
+            else:
+                np.copyto(buf, host)
+            snap[k] = buf
+        return snap
+
+    def submit(self, path: str, state, iteration: int, sim_time: float, cfg: Any) -> None:
+        """Returns as soon as the fields are copied; the file appears when the worker is done."""
+        self.wait()                                    # one write in flight; its buffers are free again
+        fields = self._snapshot(state)
+        from types import SimpleNamespace
+        shape = SimpleNamespace(nx=state.nx, ny=state.ny)
+        head = _meta(shape, {}, iteration, sim_time, cfg, structured=True)     # config hashes taken now, not later
+
+        def work():
+            try:
+                meta = dict(head)
+                meta["field_hashes"] = {k: _hash_array(v) for k, v in fields.items()}
+                _write_npz(path, meta, fields)
+                self.written += 1
+            except BaseException as exc:           # surfaced by wait()
+                self._error = exc
+
+        self._thread = threading.Thread(target=work, name="pyflow-checkpoint", daemon=False)
+        self._thread.start()
+
+    def wait(self) -> None:
+        t, self._thread = self._thread, None
+        if t is not None:
+            t.join()
+        err, self._error = self._error, None
+        if err is not None:
+            raise err
 
 
 def _state_from_npz(data) -> tuple[State, dict[str, Any]]:
@@ -118,4 +193,5 @@ def load_checkpoint_bytes(buf: bytes) -> tuple[State, dict[str, Any]]:
         return _state_from_npz(data)
 
 
-__all__ = ["save_checkpoint", "load_checkpoint", "save_checkpoint_bytes", "load_checkpoint_bytes"]
+__all__ = ["save_checkpoint", "load_checkpoint", "save_checkpoint_bytes", "load_checkpoint_bytes",
+           "BackgroundCheckpointWriter"]

@@ -244,6 +244,74 @@ def test_driver_protocol_checkpoint_and_restart(slab_cls, tmp_path):
     assert out[-1][2]["dt"] == od["dt"] and np.array_equal(st2.fields["u"], ost.fields["u"])
 
 
+def test_background_checkpoint_writer(slab_cls, tmp_path, monkeypatch):
+    """Opt-in asynchronous checkpoints: snapshot at the reference's point in the loop, same bytes on disk as the
+    synchronous writer, written while later steps run, complete when the generator ends or is closed."""
+    import threading
+
+    import pyflow.io.checkpoint as ckpt
+    from pyflow.config.model import SimulationConfig
+    from pyflow.drivers.simulation_driver import SimulationDriver
+    cfg = SimulationConfig(nx=20, ny=16, Re=100.0, advection_scheme="quick", lin_maxiter=300, diagnostics=False)
+    sync_path, async_path = str(tmp_path / "sync.npz"), str(tmp_path / "async.npz")
+    for _ in SimulationDriver(cfg).run(max_steps=4, checkpoint_path=sync_path, checkpoint_interval=3):
+        pass
+    # slow the worker down: the write of checkpoint 0 is released only after two more steps have run
+    gate, started = threading.Event(), threading.Event()
+    real_write = ckpt._write_npz
+
+    def slow_write(path, meta, fields):
+        started.set()
+        assert gate.wait(timeout=60)
+        return real_write(path, meta, fields)
+
+    monkeypatch.setattr(ckpt, "_write_npz", slow_write)
+    drv = SimulationDriver(cfg)
+    drv.async_checkpoint = True
+    gen = drv.run(max_steps=4, checkpoint_path=async_path, checkpoint_interval=3)
+    seen = []
+    for st, _res, diag in gen:
+        seen.append(diag["iteration"])
+        if diag["iteration"] == 2:
+            assert started.wait(timeout=60)                     # checkpoint 0 was handed over after the first yield ...
+            assert not (tmp_path / "async.npz").exists()        # ... and is still being written two steps later
+            gate.set()
+    assert seen == [0, 1, 2, 3] and (tmp_path / "async.npz").exists()        # joined when the generator finished
+    slab = drv.state.fields._slab
+    assert slab.uploads == [("u", "v", "p")]                    # snapshots do not dirty the State's host copies
+    assert drv.state.fields._stale == {"u", "v", "p"}           # ... nor refresh them
+    a, ma = ckpt.load_checkpoint(async_path)
+    b, mb = ckpt.load_checkpoint(sync_path)
+    assert ma["iteration"] == mb["iteration"] == 3
+    assert {k: v for k, v in ma.items() if k != "time"} == {k: v for k, v in mb.items() if k != "time"}
+    assert list(ma) == list(mb)                                 # same key order in the meta JSON
+    for f in ("u", "v", "p"):
+        assert np.array_equal(a.fields[f], b.fields[f])
+    # the snapshot is isolated from later steps: checkpoint 0 (first pass, written late) held step-0 fields
+    monkeypatch.setattr(ckpt, "_write_npz", real_write)
+    w = ckpt.BackgroundCheckpointWriter()
+    drv2 = SimulationDriver(cfg)
+    g2 = drv2.run(max_steps=3)
+    st, _r, _d = next(g2)
+    w.submit(str(tmp_path / "c0.npz"), st, 0, 0.0, cfg)
+    for _ in g2:
+        pass
+    w.wait()
+    ost, _ = orc.run(cfg, 1)
+    c0, _m = ckpt.load_checkpoint(str(tmp_path / "c0.npz"))
+    assert np.array_equal(c0.fields["u"], ost.fields["u"]) and w.written == 1
+    # errors of the worker surface in wait(); closing the generator early still joins the writer
+    w.submit(str(tmp_path / "no" / "\0bad" / "x.npz"), st, 0, 0.0, cfg)
+    with pytest.raises(Exception):
+        w.wait()
+    drv3 = SimulationDriver(cfg)
+    drv3.async_checkpoint = True
+    g3 = drv3.run(max_steps=10, checkpoint_path=str(tmp_path / "early.npz"), checkpoint_interval=1)
+    next(g3); next(g3)
+    g3.close()
+    assert ckpt.load_checkpoint(str(tmp_path / "early.npz"))[1]["iteration"] == 0
+
+
 def test_nan_is_reported_and_logged_not_raised(slab_cls, tmp_path, monkeypatch):
     from pyflow.core.ghost_fields import allocate_state, interior_view
     from pyflow.residuals.manager import ResidualManager
