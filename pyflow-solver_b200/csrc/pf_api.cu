@@ -39,8 +39,8 @@ struct pf_ctx {
   int gen_grid = 0;                // co-resident CTAs of k_cg_generic
   int tma_grid = 0;                // co-resident CTAs of k_cg_tma (0: unavailable)
   bool small_ok = false;           // k_cg_small usable (dynamic shared memory attribute set)
-  double* small_halo = nullptr;    // [sm_count][2][pitch] boundary rows of r (k_cg_small)
-  double* small_part = nullptr;    // [2][sm_count][4]
+  double* small_halo = nullptr;    // [SM_MAX_GRID][2][packets per row][4] boundary rows of r as tagged packets (k_cg_small)
+  double* small_part = nullptr;    // [2][SM_MAX_GRID][4] reduction packets, double-buffered by epoch parity
   long long launches = 0;          // kernels of this library launched so far
   bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
   dim3 sgrid;                      // grid of the simple kernels
@@ -50,11 +50,12 @@ struct pf_ctx {
   size_t sync_off = 0;             // byte offset of the cross-GPU sync block inside the workspace
   char* peer_ws[pf::CG_MAX_RANKS] = {nullptr};   // the other ranks' workspaces mapped into this process
   bool peers = false;
-  int opt_multi_single = 0;
+  int opt_multi_single = 0;        // debug/tuning: run the multi-GPU persistent kernel with one rank
   int opt_sync = 0;
   int opt_rows_min = 4;            // minimum rows per warp tile of the register-window kernel
-  int opt_kernel = 3;              // 3: auto = TMA-fed dynamically scheduled kernel when eligible (nx % 1024 == 0, one GPU),
-                                   //    else the register-window kernels; 2: static TMA tiles; 1: register-window only        // debug/tuning: run the multi-GPU persistent kernel with one rank
+  int opt_kernel = 3;              // 3: auto = shared-memory-resident kernel for small grids, TMA-fed dynamically scheduled
+                                   //    kernel when nx % 1024 == 0, else the register-window kernels; 2: static TMA tiles;
+                                   //    1: register-window only
   char err[512] = {0};
 };
 
