@@ -9,7 +9,7 @@ Runs only where ``/root/reference`` exists (the build container).  It
      which travel to the GPU box where the reference itself cannot.
 
 Usage:  python oracle/make_golden.py [part ...]   (exit code != 0 on any mismatch; parts: operators,
-        legacy_ops, pressure, trajectories, config, config2 -- default all)
+        legacy_ops, pressure, trajectories, config, config2, tiny -- default all)
 """
 from __future__ import annotations
 
@@ -342,6 +342,39 @@ def config2_vectors(steps=4):
                                "Rp_converged", "divergence_norm"]}, fh, indent=1, sort_keys=True)
 
 
+TINY = [(3, 3, "quick"), (3, 3, "upwind"), (4, 3, "quick"), (3, 5, "upwind"), (5, 4, "quick"), (2, 2, "quick"),
+        (2, 5, "upwind"), (6, 2, "quick")]
+
+
+def tiny_vectors(steps=6):
+    """The smallest grids the reference steps (down to 2x2; SimulationConfig itself asks for >= 3): every cell is
+    a wall cell or next to one, QUICK's edge padding reaches across the whole grid, CG converges in a handful of
+    iterations."""
+    print("tiny grids")
+    out = {}
+    for nx, ny, scheme in TINY:
+        kw = dict(nx=nx, ny=ny, Re=100.0, advection_scheme=scheme, lin_maxiter=300)
+        cfg = make_cfg(kw)
+        st = ref_allocate(nx, ny)
+        tr = ResidualManager()
+        _TRUE_ITERS.clear()
+        rows = []
+        for it in range(steps):
+            _, res, diag = quiet(ref_step, cfg, st, tr, it)
+            rows.append([diag["dt"], diag["CFL"], res["Ru"], res["Rv"], res["continuity"], diag["Rp_iterations"],
+                         diag["Rp_residual"], float(diag["Rp_converged"]), diag["divergence_norm"]])
+        ost, odiags = orc.run(make_cfg(kw), steps)
+        tag = f"{nx}x{ny}_{scheme}"
+        for f in ("u", "v", "p"):
+            check(f"tiny {tag} field {f}", ost.fields[f], st.fields[f])
+            out[f"{tag}/{f}"] = st.fields[f].copy()
+        check(f"tiny {tag} dt", [d["dt"] for d in odiags], [r[0] for r in rows])
+        check(f"tiny {tag} true iters", [d["true_iterations"] for d in odiags], list(_TRUE_ITERS))
+        out[f"{tag}/scalars"] = np.array(rows)
+        out[f"{tag}/true_iters"] = np.array(_TRUE_ITERS)
+    np.savez_compressed(os.path.join(GOLD, "tiny.npz"), **out)
+
+
 def config_vectors():
     print("config / checkpoint")
     from pyflow.config.model import SimulationConfig
@@ -365,7 +398,7 @@ def config_vectors():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     parts = {"operators": operator_vectors, "legacy_ops": legacy_ops_vectors, "pressure": pressure_vectors,
-             "trajectories": trajectory_vectors, "config": config_vectors, "config2": config2_vectors}
+             "trajectories": trajectory_vectors, "config": config_vectors, "config2": config2_vectors, "tiny": tiny_vectors}
     only = sys.argv[1:]                      # e.g. `make_golden.py legacy_ops` regenerates one fixture file
     for name, fn in parts.items():
         if not only or name in only:

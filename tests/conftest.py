@@ -64,7 +64,7 @@ def golden():
     import json
     import numpy as np
     out = {}
-    for name in ("operators", "legacy_ops", "pressure", "trajectories", "config2_512"):
+    for name in ("operators", "legacy_ops", "pressure", "trajectories", "config2_512", "tiny"):
         with np.load(os.path.join(GOLDEN, f"{name}.npz")) as z:
             out[name] = {k: z[k] for k in z.files}
     with open(os.path.join(GOLDEN, "trajectories.json")) as fh:
@@ -98,3 +98,14 @@ def check_config2_summary(golden, fields, rows, true_iters, tol_factor=100.0, sc
             assert err < bar, (f, key, err)
         n = np.array([np.linalg.norm(a), np.abs(a).max(), a.sum()])
         assert np.allclose(n[:2], g[f"{f}/norm"][:2], rtol=1e-9, atol=0.0), (f, n, g[f"{f}/norm"])
+
+
+TINY_TAGS = ["3x3_quick", "3x3_upwind", "4x3_quick", "3x5_upwind", "5x4_quick", "2x2_quick", "2x5_upwind", "6x2_quick"]
+
+
+def tiny_cfg(tag):
+    from types import SimpleNamespace
+    shape, scheme = tag.split("_")
+    nx, ny = (int(t) for t in shape.split("x"))
+    return SimpleNamespace(nx=nx, ny=ny, Re=100.0, advection_scheme=scheme, lin_maxiter=300, lid_velocity=1.0,
+                           cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10, disable_advection=False, diagnostics=False)

@@ -175,3 +175,23 @@ def test_config2_512_vs_reference_summary(golden, impl):
                      float(d["Rp_converged"]), d["divergence_norm"]])
         iters.append(d["true_iterations"])
     check_config2_summary(golden, {f: orc.interior(st.fields[f]) for f in ("u", "v", "p")}, rows, iters)
+
+
+# ---------------------------------------------------------------- the smallest grids the reference steps
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_tiny_grids_vs_reference(golden, impl):
+    from conftest import TINY_TAGS, tiny_cfg
+    for tag in TINY_TAGS:
+        cfg = tiny_cfg(tag)
+        g = {k.split("/", 1)[1]: v for k, v in golden["tiny"].items() if k.startswith(tag + "/")}
+        st = orc.allocate_state(cfg.nx, cfg.ny)
+        ws = orc_c.Workspace(cfg.nx, cfg.ny) if impl == "c" else None
+        for it in range(len(g["true_iters"])):
+            _, res, d = orc_c.step(cfg, st, it, ws) if impl == "c" else orc.step(cfg, st, it)
+            assert d["dt"] == g["scalars"][it, 0] and d["CFL"] == g["scalars"][it, 1], (tag, it)
+            assert abs(d["true_iterations"] - g["true_iters"][it]) <= (0 if impl == "numpy" else 1), (tag, it)
+        for f in ("u", "v", "p"):
+            if impl == "numpy":
+                assert np.array_equal(st.fields[f], g[f]), (tag, f)
+            else:
+                assert rel(st.fields[f], g[f]) < 1e-9, (tag, f)

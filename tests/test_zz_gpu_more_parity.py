@@ -123,3 +123,26 @@ def test_background_checkpoint_writer_on_the_device_path(tmp_path):
     assert ma["iteration"] == mb["iteration"] == 4 and ma["field_hashes"] == mb["field_hashes"]
     for f in ("u", "v", "p"):
         assert bits_equal(a.fields[f], b.fields[f])
+
+
+def test_tiny_grids_vs_reference_golden(golden):
+    """The smallest grids the reference steps (2x2 ... 6x2, both schemes), 6 steps each, against golden
+    trajectories written by the unmodified reference: dt / CFL bit-identical, CG iterations within 1, fields to
+    1e-9 relative L2 (every solve converges in a handful of iterations)."""
+    from conftest import TINY_TAGS, tiny_cfg
+    from pyflow.core.ghost_fields import allocate_state
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    for tag in TINY_TAGS:
+        cfg = tiny_cfg(tag)
+        g = {k.split("/", 1)[1]: v for k, v in golden["tiny"].items() if k.startswith(tag + "/")}
+        st, tr = allocate_state(cfg.nx, cfg.ny), ResidualManager()
+        for it in range(len(g["true_iters"])):
+            _, _res, d = step(cfg, st, tr, it)
+            assert d["dt"] == g["scalars"][it, 0] and d["CFL"] == g["scalars"][it, 1], (tag, it)
+            assert abs(st.meta["cg_true_iterations"] - g["true_iters"][it]) <= 1, (tag, it)
+            assert d["Rp_iterations"] == g["scalars"][it, 5] and not d["nan_detected"], (tag, it)
+        for f in ("u", "v", "p"):
+            a, b = st.fields[f], g[f]
+            e = float(np.linalg.norm(a - b) / (np.linalg.norm(b) or 1.0))
+            assert e < 1e-9, (tag, f, e)
