@@ -28,7 +28,7 @@ sys.path.insert(0, HERE)
 
 CONFIGS = [
     # name, nx, ny, Re, timed steps (after step 0, which has b = 0 and no CG work)
-    ("config 1: 64x64 Re=100", 64, 64, 100.0, 20),
+    ("config 1: 64x64 Re=100 (all 50 steps of `pyflow run`; step 0 untimed)", 64, 64, 100.0, 49),
     ("config 2: 512x512 Re=1000", 512, 512, 1000.0, 3),
 ]
 
