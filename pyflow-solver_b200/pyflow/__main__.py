@@ -1,4 +1,6 @@
-from .cli import main
+"""``python -m pyflow ...`` is the ``pyflow`` console command (see ``pyflow/cli.py``)."""
+import sys
 
-if __name__ == "__main__":  # pragma: no cover
-    raise SystemExit(main())
+from pyflow.cli import main
+
+sys.exit(main(sys.argv[1:]))
