@@ -141,6 +141,59 @@ def test_eager_mode_gives_live_array_semantics(slab_cls, monkeypatch):
     assert allocate_state(4, 4).fields.eager is True
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_lazy_state_protocol_random_walk(slab_cls, seed, tmp_path):
+    """Random interleavings of steps, reads, in-place writes through freshly fetched arrays, whole-array
+    replacement, read-only checkpoint reads and projection-only calls: the device-resident State must stay
+    indistinguishable from plain numpy arrays stepped by the oracle, and must move only what was touched."""
+    from pyflow.core.ghost_fields import allocate_state, interior_view
+    from pyflow.io.checkpoint import load_checkpoint, save_checkpoint
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.pressure_solver import solve_pressure_poisson
+    from pyflow.solvers.solver import step
+    rng = np.random.default_rng(1000 + seed)
+    cfg = make_cfg(nx=10, ny=7, lin_maxiter=6, advection_scheme=("quick", "upwind")[seed % 2])
+    st, tr = allocate_state(10, 7), ResidualManager()
+    model = orc.allocate_state(10, 7)
+    it = 0
+    for _ in range(40):
+        op = rng.choice(["step", "step", "read", "write", "replace", "checkpoint", "project"])
+        name = str(rng.choice(["u", "v", "p"]))
+        if op == "step":
+            up0 = len(st.fields._slab.uploads) if st.fields._slab else 0
+            dirty = st.fields.host_touched()
+            step(cfg, st, tr, it)
+            orc.step(cfg, model, it)
+            it += 1
+            ups = st.fields._slab.uploads[up0:]
+            assert [set(t) for t in ups] == ([dirty] if dirty else [])          # only touched fields go up
+        elif op == "read":
+            assert np.array_equal(st.fields[name], model.fields[name]), (op, name)
+        elif op == "write":                                                    # fetch, then modify in place
+            j, i = int(rng.integers(0, 7)), int(rng.integers(0, 10))
+            delta = float(rng.standard_normal()) * 1e-3
+            interior_view(st.fields[name])[j, i] += delta
+            orc.interior(model.fields[name])[j, i] += delta
+        elif op == "replace":                                                  # state.fields[name] = new array
+            new = model.fields[name] * 0.5
+            st.fields[name] = new.copy()
+            model.fields[name] = new
+        elif op == "checkpoint":                                               # read-only: nothing becomes dirty
+            dirty = st.fields.host_touched()
+            path = str(tmp_path / "rw.npz")
+            save_checkpoint(path, st, it, 0.0, cfg)
+            assert st.fields.host_touched() == dirty
+            back, _meta = load_checkpoint(path)
+            for f in ("u", "v", "p"):
+                assert np.array_equal(back.fields[f], model.fields[f]), (op, f)
+        else:                                                                  # projection-only seam on the same state
+            p, _d = solve_pressure_poisson(st, 0.01, 1.0, 1.0, cfg)
+            op_, _od = orc.solve_pressure_poisson(model, 0.01, 1.0, 1.0, cfg)
+            assert np.array_equal(p, op_)
+    for f in ("u", "v", "p"):
+        assert np.array_equal(st.fields[f], model.fields[f]), f
+
+
 def test_foreign_state_objects_are_synchronised_eagerly(slab_cls):
     """A state that is not ours (plain dict fields, e.g. the reference's dataclass): upload before and
     download after every call, into the caller's own arrays."""
