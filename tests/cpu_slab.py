@@ -228,6 +228,57 @@ class CpuSlab:
         return (x.reshape(ny, nx).copy() if want_x else None), int(info), int(iters), rnorm, float(np.sqrt(_norm2(rhs)))
 
 
+class GatherSlab(CpuSlab):
+    """Stand-in for one rank's slab context of a multi-GPU run (host-logic tests under gloo).
+
+    Every call that the real library answers with halo exchanges and all-reduces is answered here by gathering
+    the whole grid on every rank (``torch.distributed.all_gather_object``), running the single-grid stand-in and
+    keeping this rank's rows -- so all ranks hold identical step scalars, exactly as with the real library."""
+
+    def __init__(self, nx, ny_local, ny_global, row_offset, rank, world):
+        CpuSlab.__init__(self, nx, ny_local)
+        self.ny_global, self.row_offset, self.rank, self.nranks = int(ny_global), int(row_offset), int(rank), int(world)
+
+    def _gathered(self):
+        import torch.distributed as dist
+        parts = [None] * self.nranks
+        dist.all_gather_object(parts, (self.u, self.v, self.p))
+        full = CpuSlab(self.nx, self.ny_global)
+        for k, name in enumerate(("u", "v", "p")):
+            getattr(full, name)[:] = np.concatenate([t[k] for t in parts], axis=0)
+        return full
+
+    def _keep_mine(self, full):
+        rows = slice(self.row_offset, self.row_offset + self.ny_local)
+        for name in ("u", "v", "p"):
+            getattr(self, name)[:] = getattr(full, name)[rows]
+
+    def prestep(self):
+        return self._gathered().prestep()
+
+    def step(self, params):
+        full = self._gathered()
+        out = full.step(params)
+        self._keep_mine(full)
+        self.steps += 1
+        return out
+
+    def divergence_stats(self, dx, dy):
+        return self._gathered().divergence_stats(dx, dy)
+
+
+def install_slabs(rank, world):
+    """Permanent swap (one process per rank under torchrun): slab states get a ``GatherSlab``."""
+    import pyflow._b200.distributed as distributed
+
+    def make_slab(state):
+        spec = state.slab
+        return GatherSlab(state.nx, state.ny, spec["ny_global"], spec["row_offset"], rank, world)
+
+    distributed.make_slab = make_slab
+    install(None)
+
+
 def install(monkeypatch=None):
     """Swap the GPU context for the stand-in in every module that binds it.  With a pytest
     ``monkeypatch`` the swap is undone at the end of the test; with ``None`` it is permanent
