@@ -137,7 +137,7 @@ class CpuSlab:
         out.vmax_raw = float(np.max(np.abs(self.v)))
         out.p00 = float(self.p[0, 0])
         out.nonfinite = int(not all(np.isfinite(a).all() for a in (self.u, self.v, self.p)))
-        out.cg_ms = out.step_ms = 0.0
+        out.cg_ms, out.step_ms = 1.0, 1.25                 # placeholders (nothing is timed here)
         self.steps += 1
         self._launches += 9
         return out
