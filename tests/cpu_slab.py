@@ -301,12 +301,15 @@ def install(monkeypatch=None):
         else:
             setattr(mod, name, value)
 
+    # import the modules that bind `slab_for_shape` by name BEFORE anything is swapped, so that what
+    # monkeypatch restores afterwards is the real function and not the stand-in
+    users = [importlib.import_module(name) for name in (
+        "pyflow.numerics.core_ops_coherent", "pyflow.numerics.fluid_ops", "pyflow.numerics.operators.advection",
+        "pyflow.linear_solvers.interface")]
     put(device, "DeviceSlab", CpuSlab)
     put(engine, "DeviceSlab", CpuSlab)
     put(device, "slab_for_shape", slab_for_shape)
-    for name in ("pyflow.numerics.core_ops_coherent", "pyflow.numerics.fluid_ops",
-                 "pyflow.numerics.operators.advection", "pyflow.linear_solvers.interface"):
-        mod = importlib.import_module(name)
+    for mod in users:
         if hasattr(mod, "slab_for_shape"):
             put(mod, "slab_for_shape", slab_for_shape)
     return CpuSlab
