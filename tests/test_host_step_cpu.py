@@ -473,3 +473,17 @@ def test_operator_seams_signatures_and_shapes(slab_cls):
         solve(A, b, method="bicgstab")
     with pytest.raises(NotImplementedError):
         solve(np.eye(4), np.ones(4), method="cg")
+
+
+# ------------------------------------------------------------------ benchmark sweep (reference-shaped harness)
+def test_benchmark_harness_records(slab_cls):
+    from pyflow.benchmark.harness import benchmark, make_config, run_case
+    res = benchmark([8, 12], steps=5)
+    assert res["benchmark"] == "lid_driven_cavity" and res["steps_requested"] == 5 and len(res["runs"]) == 2
+    for r in res["runs"]:
+        assert {"nx", "ny", "steps", "total_time_s", "avg_time_per_step_s", "avg_cg_iterations"} <= set(r)
+        assert r["steps"] == 5 and r["avg_time_per_step_s"] > 0.0
+        assert r["avg_true_cg_iterations"] > 0 and r["mlups"] > 0 and r["cg_iterations_per_s"] > 0   # a driven cavity
+    # the reference's own harness configuration is still reachable: nothing moves, no CG work
+    rest = run_case(8, 8, 3, make_config(8, 8, lid_velocity=0.0, disable_advection=True))
+    assert rest["avg_cg_iterations"] == 0 and rest["avg_true_cg_iterations"] == 0
