@@ -1,0 +1,161 @@
+"""Exhaustive model check of the fence-free exchange protocol of ``k_cg_small``
+(pyflow-solver_b200/csrc/pf_cg_small.cuh: ``small_allreduce``).
+
+The kernel synchronises its CTAs twice per CG iteration WITHOUT counters, fences or release
+flags: every CTA stores one self-validating 32-byte packet ``{epoch, partials}`` into its slot
+(slots double-buffered by epoch parity), warp 0 polls every slot until it carries the current
+epoch, and -- on the second exchange of an iteration -- the other warps publish the CTA's two
+boundary rows of ``r`` as packets tagged with the same epoch and fetch the neighbours' rows the
+same way.  A packet is written with ONE 256-bit store, so a reader sees it complete or not at
+all; what has to be proved is that nobody can ever miss an epoch:
+
+  SAFETY    whenever a CTA still waits for epoch ``e`` at some location, that location does
+            not already hold a LATER epoch (the wait could never end: epochs only grow);
+  LIVENESS  every reachable state can still reach completion (no deadlock).
+
+The model below is deliberately more permissive than the hardware: inside one exchange a CTA's
+stores and polls happen in any order (different lanes / warps), except that a CTA moves on to the
+next exchange only when all its polls of this one have been satisfied and all its stores issued
+(the trailing ``__syncthreads``); a store becomes VISIBLE to the other CTAs at an arbitrary later
+time (relaxed ``st.global``, no fence), stores of one thread to one address in issue order.  All
+interleavings of 3 CTAs over 4 exchanges (two CG iterations: every slot and every row packet is
+reused once; about two million states) are enumerated.  Two mutants show that the checker does find
+protocol bugs: single-buffered slots, and a CTA that posts its next packet before its row reads
+have finished.
+
+This is CPU-only evidence for the protocol's logic; racecheck / memcheck runs of the compiled
+kernel need a GPU (profiles/capture.sh sanitize).
+"""
+from collections import deque
+
+import pytest
+
+def _ops_of(cta, e, G, lazy_row_reads=False):
+    """Micro-operations of one CTA in exchange e: (kind, location, epoch tag).  Exchange 2k-1 is the p.Ap reduction,
+    exchange 2k the (r.r, r.z) reduction that also carries the boundary rows.  The poll of the CTA's own slot
+    is left out: it only waits for the CTA's own store and leaving it out makes the model MORE permissive.
+    ``lazy_row_reads`` is a MUTANT: the neighbours' rows of exchange e are fetched during exchange e+1, i.e. the
+    CTA posts its next reduction packet before its row reads have finished."""
+    ops = [("W", ("slot", e & 1, cta), e)]
+    ops += [("R", ("slot", e & 1, q), e) for q in range(G) if q != cta]
+    if e % 2 == 0:
+        ops += [("W", ("row", cta, side), e) for side in (0, 1)]
+    rows_of = e - 1 if lazy_row_reads else e
+    if rows_of >= 1 and rows_of % 2 == 0:
+        if cta > 0:
+            ops.append(("R", ("row", cta - 1, 1), rows_of))      # the lower neighbour's LAST row
+        if cta < G - 1:
+            ops.append(("R", ("row", cta + 1, 0), rows_of))      # the upper neighbour's FIRST row
+    return ops
+
+
+def explore(G=3, T=4, *, delayed_visibility=True, single_buffered=False, lazy_row_reads=False, max_states=4_000_000):
+    """Breadth-first over every interleaving of G CTAs over T exchanges.
+    Returns (number of states, violation or None, deadlocked state or None)."""
+    def loc_of(loc):
+        if single_buffered and loc[0] == "slot":
+            return ("slot", 0, loc[2])
+        return loc
+
+    plans = {(c, e): [(k, loc_of(loc), tag) for k, loc, tag in _ops_of(c, e, G, lazy_row_reads)]
+             for c in range(G) for e in range(1, T + 1)}
+    locations = sorted({loc for ops in plans.values() for _k, loc, _t in ops})
+    lidx = {loc: i for i, loc in enumerate(locations)}
+    nloc = len(locations)
+    full = {key: (1 << len(ops)) - 1 for key, ops in plans.items()}
+
+    # state: (exchange of each CTA, pending-op mask of each CTA, visible epoch per location,
+    #         per location the epochs stored but not yet visible, oldest first)
+    start = (tuple(1 for _ in range(G)), tuple(full[(c, 1)] for c in range(G)),
+             tuple(0 for _ in range(nloc)), tuple(() for _ in range(nloc)))
+    seen = {start}
+    todo = deque([start])
+    while todo:
+        st = todo.popleft()
+        epochs, masks, visible, inflight = st
+        succ = []
+        for c in range(G):
+            e = epochs[c]
+            if e > T:
+                continue
+            for k, (kind, loc, tag) in enumerate(plans[(c, e)]):
+                if not masks[c] >> k & 1:
+                    continue
+                i = lidx[loc]
+                nxt_vis, nxt_inf = visible, inflight
+                if kind == "R":
+                    if visible[i] > tag:                   # SAFETY: the awaited epoch has been overwritten
+                        return len(seen), (c, e, loc, tag, visible[i]), None
+                    if visible[i] != tag:
+                        continue                           # still polling
+                elif delayed_visibility:
+                    inf = list(inflight)
+                    inf[i] = inflight[i] + (tag,)
+                    nxt_inf = tuple(inf)
+                else:
+                    vis = list(visible)
+                    vis[i] = tag
+                    nxt_vis = tuple(vis)
+                ne, nms = list(epochs), list(masks)
+                nms[c] = masks[c] & ~(1 << k)
+                if nms[c] == 0:                            # trailing __syncthreads: on to the next exchange
+                    ne[c] = e + 1
+                    nms[c] = full[(c, e + 1)] if e + 1 <= T else 0
+                succ.append((tuple(ne), tuple(nms), nxt_vis, nxt_inf))
+        for i in range(nloc):                              # a store in flight becomes visible (oldest first)
+            if inflight[i]:
+                vis, inf = list(visible), list(inflight)
+                vis[i], inf[i] = inflight[i][0], inflight[i][1:]
+                succ.append((epochs, masks, tuple(vis), tuple(inf)))
+        if not succ and not all(ep > T for ep in epochs):
+            return len(seen), None, st                     # LIVENESS: nobody can move and not everybody is done
+        for s2 in succ:
+            if s2 not in seen:
+                seen.add(s2)
+                todo.append(s2)
+                if len(seen) > max_states:
+                    raise RuntimeError("state space larger than expected")
+    return len(seen), None, None
+
+
+@pytest.mark.parametrize("kw", [
+    dict(G=3, T=4),                                  # 3 CTAs, two CG iterations, stores visible arbitrarily late (2 M states)
+    dict(G=2, T=6),                                  # 2 CTAs, three CG iterations
+    dict(G=3, T=4, delayed_visibility=False),        # stores visible at once
+], ids=["3ctas-4exchanges-late-stores", "2ctas-6exchanges-late-stores", "3ctas-4exchanges"])
+def test_protocol_is_safe_and_live_over_all_interleavings(kw):
+    states, violation, deadlock = explore(**kw)
+    assert violation is None, f"a CTA can miss an epoch: {violation}"
+    assert deadlock is None, f"deadlock: {deadlock}"
+    assert states > 5_000                                   # the exploration was not trivially small
+
+
+@pytest.mark.parametrize("late", [False, True])
+def test_checker_finds_the_bug_in_single_buffered_slots(late):
+    """Without the parity double-buffering a fast CTA overwrites its packet of exchange e with e+1 while a slow
+    CTA still polls for e."""
+    _states, violation, _deadlock = explore(G=3 if not late else 2, single_buffered=True, delayed_visibility=late)
+    assert violation is not None and violation[2][0] == "slot"
+    _cta, _exchange, _loc, awaited, found = violation
+    assert found == awaited + 1
+
+
+@pytest.mark.parametrize("late", [False, True])
+def test_checker_finds_the_bug_when_the_next_packet_is_posted_before_the_row_reads_finish(late):
+    """The row packets are safe only because a CTA posts its next reduction packet AFTER its row reads: let the
+    reads trail into the next exchange and a neighbour runs ahead and overwrites a row that is still awaited."""
+    _states, violation, _deadlock = explore(G=3 if not late else 2, lazy_row_reads=True, delayed_visibility=late)
+    assert violation is not None and violation[2][0] == "row"
+    _cta, _exchange, _loc, awaited, found = violation
+    assert found == awaited + 2
+
+
+def test_model_mirrors_the_kernel_call_sequence():
+    """Exchange 2k-1 is small_allreduce<1,false> (p.Ap), exchange 2k is small_allreduce<2,true> (r.r, r.z + rows);
+    the middle CTA reads one row from each neighbour, the end CTAs from one."""
+    for e in range(1, 5):
+        kinds = {loc[0] for _k, loc, _t in _ops_of(1, e, 3)}
+        assert ("row" in kinds) == (e % 2 == 0)
+    assert sum(k == "R" and loc[0] == "row" for k, loc, _t in _ops_of(1, 2, 3)) == 2
+    assert sum(k == "R" and loc[0] == "row" for k, loc, _t in _ops_of(0, 2, 3)) == 1
+    assert ("R", ("row", 0, 1), 2) in _ops_of(1, 2, 3) and ("R", ("row", 2, 0), 2) in _ops_of(1, 2, 3)
