@@ -333,3 +333,35 @@ def test_alternate_driver_steady_detection_and_hooks(monkeypatch):
                             report_interval=1000)
     assert len(list(alt.SimulationDriver(cfg2).run())) == 12
     assert alt.create_default_driver().driver_cfg.nx == 65 and alt.PhysicsConfig().lin_maxiter == 800
+
+
+# ------------------------------------------------------------------ C-ABI conventions without a GPU
+def test_c_abi_argument_validation_and_clean_failure_without_a_gpu():
+    """0 / negative status codes, nothing throws or aborts across the ABI (include/pyflow_b200.h conventions):
+    argument errors are refused before any CUDA call; without a device pf_create reports PF_ERR_CUDA."""
+    import ctypes as C
+    from pyflow._b200 import lib
+    h = lib.load()
+    ctx = C.c_void_p()
+    fake = C.c_void_p(1 << 20)                                   # aligned, never dereferenced on these paths
+    big = h.pf_workspace_bytes(64, 64)
+    assert big > 9 * 68 * 64 * 8
+    assert h.pf_create(None, 64, 64, 64, 0, 0, fake, big) == -1                       # no out pointer
+    assert h.pf_create(C.byref(ctx), 1, 64, 64, 0, 0, fake, big) == -1                # nx < 2
+    assert h.pf_create(C.byref(ctx), 64, 64, 1, 0, 0, fake, big) == -1                # ny_global < 2
+    assert h.pf_create(C.byref(ctx), 64, 40, 64, 30, 0, fake, big) == -1              # slab sticks out of the grid
+    assert h.pf_create(C.byref(ctx), 64, 64, 64, 0, 0, None, big) == -1               # no workspace
+    assert h.pf_create(C.byref(ctx), 64, 64, 64, 0, 0, C.c_void_p((1 << 20) + 8), big) == -1      # misaligned
+    assert h.pf_create(C.byref(ctx), 64, 64, 64, 0, 0, fake, big - 1) == -1           # too small
+    assert ctx.value is None
+    if not _has_cuda():
+        assert h.pf_create(C.byref(ctx), 64, 64, 64, 0, 0, fake, big) == -2 and ctx.value is None
+    assert h.pf_destroy(None) == 0
+    for call in (lambda: h.pf_step(None, None, None, None), lambda: h.pf_upload(None, None, None, None, 66, None),
+                 lambda: h.pf_prestep_reduce(None, None, None), lambda: h.pf_centerline(None, None, None),
+                 lambda: h.pf_launch_count(None, None), lambda: h.pf_set_option(None, b"cg_kernel", 1),
+                 lambda: h.pf_comm_init(None, None, 0, 1), lambda: h.pf_comm_unique_id(None),
+                 lambda: h.pf_op_laplacian_central(None, None, None, 1.0, 1.0, None)):
+        assert call() == -1
+    names = {code: h.pf_strerror(code).decode() for code in (0, -1, -2, -3, -4, -5, -99)}
+    assert names[0] == "ok" and len(set(names.values())) == 7 and names[-99] == "unknown status"
