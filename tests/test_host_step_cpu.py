@@ -487,3 +487,32 @@ def test_benchmark_harness_records(slab_cls):
     # the reference's own harness configuration is still reachable: nothing moves, no CG work
     rest = run_case(8, 8, 3, make_config(8, 8, lid_velocity=0.0, disable_advection=True))
     assert rest["avg_cg_iterations"] == 0 and rest["avg_true_cg_iterations"] == 0
+
+
+def test_cli_keyboard_interrupt_writes_final_checkpoint_and_returns_130(slab_cls, tmp_path, monkeypatch, capsys):
+    """Reference cli.py:179-193: Ctrl-C during the run attempts a final checkpoint of the last yielded state."""
+    from pyflow import cli
+    from pyflow.drivers.simulation_driver import SimulationDriver
+    from pyflow.io.checkpoint import load_checkpoint
+    real_run = SimulationDriver.run
+
+    def interrupted_run(self, *a, **k):
+        for n, item in enumerate(real_run(self, *a, **k)):
+            yield item
+            if n == 2:
+                raise KeyboardInterrupt
+
+    monkeypatch.setattr(SimulationDriver, "run", interrupted_run)
+    ck = str(tmp_path / "final.npz")
+    rc = cli.main(["run", "--nx", "12", "--ny", "10", "--steps", "50", "--checkpoint", ck])
+    assert rc == 130
+    out = capsys.readouterr().out
+    assert "KeyboardInterrupt received" in out and "Final checkpoint written" in out
+    st, meta = load_checkpoint(ck)
+    assert meta["iteration"] == 2
+    ost, _ = orc.run(make_cfg(nx=12, ny=10, Re=100.0), 3)
+    assert np.array_equal(st.fields["u"], ost.fields["u"]) and np.array_equal(st.fields["p"], ost.fields["p"])
+    # --json-stream keeps stdout machine-readable even then
+    rc = cli.main(["run", "--nx", "12", "--ny", "10", "--steps", "50", "--checkpoint", ck, "--json-stream"])
+    lines = capsys.readouterr().out.splitlines()
+    assert rc == 130 and len(lines) == 3 and all(line.startswith("{") for line in lines)
