@@ -365,3 +365,31 @@ def test_c_abi_argument_validation_and_clean_failure_without_a_gpu():
         assert call() == -1
     names = {code: h.pf_strerror(code).decode() for code in (0, -1, -2, -3, -4, -5, -99)}
     assert names[0] == "ok" and len(set(names.values())) == 7 and names[-99] == "unknown status"
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/pyflow_b200.h against the argtypes declared in pyflow/_b200/lib.py: same number
+    of parameters, scalars of the same kind and width, pointers where the header has pointers."""
+    import ctypes as C
+    from pyflow._b200 import lib
+    h = lib.load()
+    hdr = open(os.path.join(ROOT, "include", "pyflow_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|const char\*)\s+(pf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) == len(lib.EXPORTS)
+    scalar = {"double": C.c_double, "int": C.c_int, "int64_t": C.c_int64, "size_t": C.c_size_t, "int32_t": C.c_int32}
+    pointer_like = (C.c_void_p, C.c_char_p)
+    for name, params in protos:
+        fn = getattr(h, name)
+        plist = [p.strip() for p in params.replace("\n", " ").split(",") if p.strip() and p.strip() != "void"]
+        if fn.argtypes is None:
+            assert not plist, f"{name}: header has parameters, binding declares none"
+            continue
+        assert len(fn.argtypes) == len(plist), (name, plist, fn.argtypes)
+        for decl, at in zip(plist, fn.argtypes):
+            is_ptr = "*" in decl or "[" in decl
+            if is_ptr:
+                assert at in pointer_like or hasattr(at, "contents") or issubclass(at, C._Pointer), (name, decl, at)
+            else:
+                ctype = decl.replace("const ", "").split()[0]
+                assert at is scalar[ctype], (name, decl, at)
