@@ -159,3 +159,110 @@ def test_model_mirrors_the_kernel_call_sequence():
     assert sum(k == "R" and loc[0] == "row" for k, loc, _t in _ops_of(1, 2, 3)) == 2
     assert sum(k == "R" and loc[0] == "row" for k, loc, _t in _ops_of(0, 2, 3)) == 1
     assert ("R", ("row", 0, 1), 2) in _ops_of(1, 2, 3) and ("R", ("row", 2, 0), 2) in _ops_of(1, 2, 3)
+
+
+# =====================================================================================================
+# The cross-GPU barrier of the persistent multi-GPU CG kernels (pf_cg.cuh: grid_exchange):
+#   every CTA arrives on its GPU's counter; the LAST CTA of a GPU folds the partials, stores one packet
+#   {epoch, sums} into the mailbox of EVERY rank (slot [epoch parity][source rank]), waits until its own
+#   mailbox holds the epoch from every rank, sums in rank order and publishes ONE release packet (single
+#   slot, not double-buffered) that all CTAs of the GPU poll.
+# Same two properties as above, over every interleaving of R ranks x G CTAs, stores visible arbitrarily late.
+# =====================================================================================================
+def explore_multi(R=2, G=2, T=3, *, single_buffered_mailbox=False, max_states=4_000_000):
+    def mbox(dest, e, src):
+        return ("mbox", dest, 0 if single_buffered_mailbox else e & 1, src)
+
+    locations = sorted({mbox(d, e, s) for d in range(R) for e in (0, 1) for s in range(R)} |
+                       {("gsum", r) for r in range(R)})
+    lidx = {loc: i for i, loc in enumerate(locations)}
+    nloc = len(locations)
+
+    def last_ops(r, e):
+        return [("W", mbox(q, e, r)) for q in range(R)] + [("R", mbox(r, e, q)) for q in range(R)]
+
+    # per CTA: (epoch, stage, pending mask); stage 0 arrive, 1 exchange (last CTA only), 2 release store, 3 wait release
+    start = (tuple((1, 0, 0) for _ in range(R * G)), tuple(0 for _ in range(R)),
+             tuple(0 for _ in range(nloc)), tuple(() for _ in range(nloc)))
+    seen = {start}
+    todo = deque([start])
+    while todo:
+        st = todo.popleft()
+        ctas, arrive, visible, inflight = st
+        succ = []
+
+        def with_cta(k, new, arr=arrive, vis=visible, inf=inflight):
+            lst = list(ctas)
+            lst[k] = new
+            succ.append((tuple(lst), arr, vis, inf))
+
+        for k, (e, stage, mask) in enumerate(ctas):
+            if e > T:
+                continue
+            r = k // G
+            if stage == 0:                                   # atomicAdd on the GPU's arrival counter
+                arr = list(arrive)
+                arr[r] += 1
+                is_last = arrive[r] == e * G - 1
+                ops = last_ops(r, e)
+                with_cta(k, (e, 1, (1 << len(ops)) - 1) if is_last else (e, 3, 0), arr=tuple(arr))
+            elif stage == 1:
+                ops = last_ops(r, e)
+                for j, (kind, loc) in enumerate(ops):
+                    if not mask >> j & 1:
+                        continue
+                    i = lidx[loc]
+                    if kind == "R":
+                        if visible[i] > e:
+                            return len(seen), (r, e, loc, visible[i]), None
+                        if visible[i] != e:
+                            continue
+                        nm = mask & ~(1 << j)
+                        with_cta(k, (e, 1, nm) if nm else (e, 2, 0))
+                    else:
+                        inf = list(inflight)
+                        inf[i] = inflight[i] + (e,)
+                        nm = mask & ~(1 << j)
+                        with_cta(k, (e, 1, nm) if nm else (e, 2, 0), inf=tuple(inf))
+            elif stage == 2:                                 # release packet for the CTAs of this GPU
+                i = lidx[("gsum", r)]
+                inf = list(inflight)
+                inf[i] = inflight[i] + (e,)
+                with_cta(k, (e, 3, 0), inf=tuple(inf))
+            else:                                            # every CTA polls the release packet
+                i = lidx[("gsum", r)]
+                if visible[i] > e:
+                    return len(seen), (r, e, ("gsum", r), visible[i]), None
+                if visible[i] == e:
+                    with_cta(k, (e + 1, 0, 0))
+        for i in range(nloc):
+            if inflight[i]:
+                vis, inf = list(visible), list(inflight)
+                vis[i], inf[i] = inflight[i][0], inflight[i][1:]
+                succ.append((ctas, arrive, tuple(vis), tuple(inf)))
+        if not succ and not all(c[0] > T for c in ctas):
+            return len(seen), None, st
+        for s2 in succ:
+            if s2 not in seen:
+                seen.add(s2)
+                todo.append(s2)
+                if len(seen) > max_states:
+                    raise RuntimeError("state space larger than expected")
+    return len(seen), None, None
+
+
+# (3 GPUs x 1 CTA over 4 barriers -- 2.8 M states, 95 s -- was run once when this was written: safe and live.)
+@pytest.mark.parametrize("kw", [dict(R=2, G=2, T=6), dict(R=2, G=4, T=3), dict(R=3, G=1, T=2)],
+                         ids=["2gpus-2ctas-6barriers", "2gpus-4ctas-3barriers", "3gpus-1cta-2barriers"])
+def test_cross_gpu_barrier_is_safe_and_live(kw):
+    states, violation, deadlock = explore_multi(**kw)
+    assert violation is None, f"a reader can miss an epoch: {violation}"
+    assert deadlock is None, f"deadlock: {deadlock}"
+    assert states > 1_000
+
+
+def test_checker_finds_the_bug_in_a_single_buffered_mailbox():
+    """Without the parity double-buffering of the mailbox a fast GPU stores its packet of barrier e+1 over the
+    one of barrier e that a slow GPU's last CTA has not read yet."""
+    _states, violation, _deadlock = explore_multi(R=2, G=1, T=3, single_buffered_mailbox=True)
+    assert violation is not None and violation[2][0] == "mbox"
