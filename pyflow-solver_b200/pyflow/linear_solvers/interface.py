@@ -18,7 +18,7 @@ from typing import Literal
 import numpy as np
 
 from .._b200.device import slab_for_shape
-from .preconditioners import RingJacobi
+from .preconditioners import resolve
 
 
 @dataclass(slots=True)
@@ -62,8 +62,8 @@ def solve(A, b, method: Literal["cg", "bicgstab"] = "bicgstab", tol: float = 1e-
     M = kwargs.pop("M", None)
     if kwargs:
         raise TypeError(f"unsupported solver arguments: {sorted(kwargs)}")
-    if M is not None and not isinstance(M, RingJacobi):
-        raise NotImplementedError("only the ring-identity Jacobi preconditioner (or None) runs on the device")
+    if M is not None:
+        M = resolve(M, A.nx, A.ny)          # RingJacobi, or the diagonal of assemble_negative_laplacian; else raises
     b = np.asarray(b, dtype=np.float64)
     slab = slab_for_shape(A.ny, A.nx)
     x, info, _iters, rnorm = slab.pcg(b.reshape(A.ny, A.nx), A.dx, A.dy, tol, maxiter, jacobi=M is not None,

@@ -1,14 +1,28 @@
 """Jacobi preconditioner (drop-in for the reference's
 ``src/pyflow/linear_solvers/preconditioners.py:jacobi_preconditioner`` :8-25).
 
-On the device the only preconditioner is the one the reference actually uses
-on the hot path: the inverse diagonal of ``assemble_negative_laplacian`` --
-1.0 on the boundary ring, ``1/(2/dx^2 + 2/dy^2)`` inside -- applied inside the
-CG kernels.  ``RingJacobi`` is its descriptor.
+The reference builds ``M`` from the diagonal of an ASSEMBLED matrix,
+``invD = where(D != 0, 1/D, 0)``, and on the hot path that matrix is always
+``assemble_negative_laplacian(nx, ny, dx, dy)`` (pressure_solver.py:139-143):
+identity rows on the boundary ring, ``2/dx^2 + 2/dy^2`` inside.  The device
+applies exactly that diagonal analytically inside the CG kernels, so here a
+preconditioner is a DESCRIPTOR, not an operator:
+
+* ``jacobi_preconditioner(NegLaplacianPinned(...))`` -> ``RingJacobi`` (the
+  matrix-free route: nothing is assembled);
+* ``jacobi_preconditioner(<scipy sparse matrix or 2-D array>)`` -- the
+  reference's own recipe -- reads the diagonal and returns a
+  ``DiagonalJacobi``; at solve time it is accepted if it IS the ring-identity
+  diagonal of the grid being solved (checked value by value), i.e. for the
+  matrix ``assemble_negative_laplacian`` returns;
+* any other diagonal, and arbitrary ``LinearOperator`` objects, raise
+  ``NotImplementedError``: there is no host path to fall back to.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
+
+import numpy as np
 
 
 @dataclass(frozen=True)
@@ -28,11 +42,71 @@ class RingJacobi:
         return (n, n)
 
 
-def jacobi_preconditioner(A) -> RingJacobi:
-    """``A`` is the device operator descriptor (``NegLaplacianPinned``)."""
+@dataclass(frozen=True, eq=False)
+class DiagonalJacobi:
+    """Inverse diagonal read off an assembled matrix (reference preconditioners.py:17-19)."""
+    inv_diag: np.ndarray = field(repr=False)
+
+    @property
+    def shape(self):
+        n = int(self.inv_diag.shape[0])
+        return (n, n)
+
+    def as_ring(self, nx: int, ny: int) -> RingJacobi | None:
+        """The equivalent ``RingJacobi`` if this is the ring-identity diagonal of an ``ny x nx`` grid:
+        1.0 on the whole boundary ring and one common value inside.  ``None`` otherwise."""
+        if self.inv_diag.shape != (nx * ny,):
+            return None
+        d = self.inv_diag.reshape(ny, nx)
+        ring = np.ones((ny, nx), dtype=bool)
+        ring[1:-1, 1:-1] = False
+        if not np.all(d[ring] == 1.0):
+            return None
+        inner = d[~ring]
+        if inner.size == 0:
+            return RingJacobi(nx, ny, 1.0, 1.0)
+        if not np.all(inner == inner[0]) or not inner[0] > 0.0:
+            return None
+        return _RingWithValue(nx, ny, 1.0, 1.0, float(inner[0]))
+
+
+@dataclass(frozen=True)
+class _RingWithValue(RingJacobi):
+    """Ring-identity diagonal whose interior value was read from a matrix rather than derived from dx, dy."""
+    value: float = 0.25
+
+    @property
+    def inv_diag_interior(self) -> float:
+        return self.value
+
+
+def jacobi_preconditioner(A):
+    """Descriptor of the Jacobi preconditioner of ``A`` (see the module docstring)."""
     from .interface import NegLaplacianPinned
     if isinstance(A, NegLaplacianPinned):
         return RingJacobi(A.nx, A.ny, A.dx, A.dy)
+    diagonal = getattr(A, "diagonal", None)
+    if callable(diagonal) and len(getattr(A, "shape", ())) == 2 and A.shape[0] == A.shape[1]:
+        D = np.asarray(diagonal(), dtype=np.float64).reshape(-1)
+        with np.errstate(divide="ignore"):
+            return DiagonalJacobi(np.where(D != 0, 1.0 / D, 0.0))
     raise NotImplementedError(
-        "jacobi_preconditioner on the device needs the matrix-free NegLaplacianPinned operator; assembled sparse "
-        "matrices are not part of the B200 hot path (no CPU fallback)")
+        "jacobi_preconditioner needs the matrix-free NegLaplacianPinned operator or an assembled (sparse) matrix; "
+        "general LinearOperators have no diagonal to read and there is no CPU fallback")
+
+
+def resolve(preconditioner, nx: int, ny: int) -> RingJacobi:
+    """What the device can apply for ``preconditioner`` on an ``ny x nx`` grid, or NotImplementedError."""
+    if isinstance(preconditioner, RingJacobi):
+        return preconditioner
+    if isinstance(preconditioner, DiagonalJacobi):
+        ring = preconditioner.as_ring(nx, ny)
+        if ring is not None:
+            return ring
+        raise NotImplementedError(
+            "this diagonal preconditioner is not the ring-identity Jacobi diagonal of the grid being solved "
+            "(1 on the boundary ring, one value inside); only that one is applied on the device")
+    raise NotImplementedError(
+        "only the ring-identity Jacobi preconditioner (jacobi_preconditioner of the pinned operator or of "
+        "assemble_negative_laplacian) or None runs on the device; arbitrary LinearOperator preconditioners are "
+        "not supported (SURVEY.md 8f item 2)")

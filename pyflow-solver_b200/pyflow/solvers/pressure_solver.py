@@ -41,14 +41,12 @@ def assemble_negative_laplacian(nx: int, ny: int, dx: float, dy: float):
     return A.tocsr()
 
 
-def _projection_params(cfg, dt, dx, dy, preconditioner=None, default_maxiter=400) -> _lib.StepParams:
+def _projection_params(cfg, dt, dx, dy, preconditioner=None, default_maxiter=400, grid=None) -> _lib.StepParams:
+    inv_diag_interior = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)      # reference :35 and preconditioners.py:19
     if preconditioner is not None:
-        from ..linear_solvers.preconditioners import RingJacobi
-        if not isinstance(preconditioner, RingJacobi):
-            raise NotImplementedError(
-                "only the ring-identity Jacobi preconditioner (jacobi_preconditioner of the pinned operator) or "
-                "None runs on the device; arbitrary LinearOperator preconditioners are not supported "
-                "(SURVEY.md 8f item 2)")
+        from ..linear_solvers.preconditioners import resolve
+        nx, ny = grid if grid is not None else (getattr(preconditioner, "nx", 0), getattr(preconditioner, "ny", 0))
+        inv_diag_interior = resolve(preconditioner, nx, ny).inv_diag_interior
         jacobi = 1
     else:
         jacobi = 1 if getattr(cfg, "enable_jacobi_pc", True) else 0
@@ -57,8 +55,7 @@ def _projection_params(cfg, dt, dx, dy, preconditioner=None, default_maxiter=400
     p.lin_tol = float(getattr(cfg, "lin_tol", 1e-10))
     p.lin_maxiter = int(getattr(cfg, "lin_maxiter", default_maxiter))
     p.jacobi = jacobi
-    # reference :35 (diagonal) and preconditioners.py:19 (1.0 / D), same float expression
-    p.inv_diag_interior = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)
+    p.inv_diag_interior = inv_diag_interior
     p.scheme = _lib.PF_ADV_NONE
     p.projection_only = 1
     return p
@@ -122,7 +119,7 @@ def solve_pressure_poisson(state, dt: float, dx: float, dy: float, cfg, precondi
         return _solve_manufactured(state, dx, dy, cfg, preconditioner, rhs_override)
     verbose = getattr(cfg, "diagnostics", True) and not getattr(cfg, "force_quiet", False)
     bind = attach(state)
-    params = _projection_params(cfg, dt, dx, dy, preconditioner)
+    params = _projection_params(cfg, dt, dx, dy, preconditioner, grid=(bind.slab.nx, bind.slab.ny_global))
     out = bind.slab.step(params)
     bind.finish(prestep_next=None)
     diag = _rp_diagnostics(cfg, out)

@@ -516,3 +516,47 @@ def test_cli_keyboard_interrupt_writes_final_checkpoint_and_returns_130(slab_cls
     rc = cli.main(["run", "--nx", "12", "--ny", "10", "--steps", "50", "--checkpoint", ck, "--json-stream"])
     lines = capsys.readouterr().out.splitlines()
     assert rc == 130 and len(lines) == 3 and all(line.startswith("{") for line in lines)
+
+
+def test_reference_recipe_for_the_jacobi_preconditioner_is_recognised(slab_cls):
+    """pressure_solver.py:139-143 builds M as jacobi_preconditioner(csr(assemble_negative_laplacian(...))): that
+    object (a diagonal read off the assembled matrix) is accepted when it IS the ring-identity diagonal of the grid
+    being solved; other diagonals and generic operators are refused -- there is no host path."""
+    import scipy.sparse as sp
+    from pyflow.core.ghost_fields import allocate_state, interior_view
+    from pyflow.linear_solvers.interface import NegLaplacianPinned, solve
+    from pyflow.linear_solvers.preconditioners import DiagonalJacobi, RingJacobi, jacobi_preconditioner
+    from pyflow.solvers.pressure_solver import assemble_negative_laplacian, solve_pressure_poisson
+    nx, ny, dx, dy = 18, 14, 0.5, 0.25
+    A = assemble_negative_laplacian(nx, ny, dx, dy)
+    M = jacobi_preconditioner(sp.csr_matrix(A))
+    assert isinstance(M, DiagonalJacobi) and M.shape == (nx * ny, nx * ny)
+    ring = M.as_ring(nx, ny)
+    assert isinstance(ring, RingJacobi) and ring.inv_diag_interior == RingJacobi(nx, ny, dx, dy).inv_diag_interior
+    assert M.as_ring(ny, nx) is None and M.as_ring(nx, ny + 1) is None
+    assert np.array_equal(M.inv_diag, orc.jacobi_inverse_diagonal(nx, ny, dx, dy))
+    cfg = SimpleNamespace(lin_tol=1e-10, lin_maxiter=300, diagnostics=False, enable_jacobi_pc=False)
+    results = []
+    for pre in (M, None):
+        st = allocate_state(nx, ny)
+        interior_view(st.fields["u"])[ny // 3, nx // 3] = 1.0
+        c = cfg if pre is not None else SimpleNamespace(**{**vars(cfg), "enable_jacobi_pc": True})
+        results.append(solve_pressure_poisson(st, 0.01, dx, dy, c, preconditioner=pre)[0])
+    assert np.array_equal(results[0], results[1])
+    # the linear-solve seam takes it too
+    op = NegLaplacianPinned(nx, ny, dx, dy)
+    b = np.random.default_rng(2).standard_normal(nx * ny)
+    b -= b.mean()
+    b[0] = 0.0
+    r1 = solve(op, b, method="cg", tol=1e-10, maxiter=3000, M=M)
+    r2 = solve(op, b, method="cg", tol=1e-10, maxiter=3000, M=jacobi_preconditioner(op))
+    assert r1.converged and np.array_equal(r1.x, r2.x)
+    # anything else is refused
+    other = DiagonalJacobi(np.linspace(0.1, 1.0, nx * ny))
+    with pytest.raises(NotImplementedError):
+        solve_pressure_poisson(allocate_state(nx, ny), 0.01, dx, dy, cfg, preconditioner=other)
+    with pytest.raises(NotImplementedError):
+        solve(op, b, method="cg", M=jacobi_preconditioner(sp.identity(nx * ny, format="csr") * 2.0))
+    with pytest.raises(NotImplementedError):
+        jacobi_preconditioner(lambda x: x)
+    assert jacobi_preconditioner(sp.identity(4, format="csr")).as_ring(2, 2).inv_diag_interior == 0.25
