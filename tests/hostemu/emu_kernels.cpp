@@ -1,0 +1,156 @@
+// Host execution of the ELEMENT-WISE CUDA kernels of libpyflow_b200 (tests only).
+//
+// The .cuh sources are compiled by g++ against a minimal stand-in for <cuda_runtime.h> (this directory) and each
+// kernel body is run once per emulated thread, block after block, on buffers in the device field layout
+// ((ny + 2*HALO) rows x pitch doubles).  That is a faithful execution for kernels whose threads do not communicate
+// (no __syncthreads, no shuffles, no atomics): the operator-level kernels, the predictor, the correction, the lid row,
+// the centre line.  Compiled with -ffp-contract=off it evaluates the very expressions nvcc compiles with -fmad=false,
+// so the results must equal the golden vectors of the reference bit for bit -- on a machine without a GPU.
+// Kernels with grid reductions and the cooperative CG kernels are NOT emulated here; their parity is a GPU matter.
+#include "cuda_runtime.h"
+
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+
+#include "pf_kernels.cuh"
+
+using namespace pf;
+
+namespace {
+
+Slab slab_of(int nx, int ny) {
+  Slab s;
+  s.nx = nx; s.nyl = ny; s.nyg = ny; s.row0 = 0;
+  s.pitch = (nx + PITCH_ALIGN - 1) / PITCH_ALIGN * PITCH_ALIGN;
+  return s;
+}
+
+// same launch geometry as simple_grid() in pf_api.cu
+template <class Body>
+void launch(const Slab& s, Body body) {
+  const unsigned gx = (unsigned)((s.nx + KT - 1) / KT);
+  unsigned gy = 2368u / gx;
+  if (gy < 1u) gy = 1u;
+  if (gy > (unsigned)s.nyl) gy = (unsigned)s.nyl;
+  gridDim = dim3(gx, gy, 1);
+  blockDim = dim3(KT, 1, 1);
+  for (unsigned by = 0; by < gy; ++by)
+    for (unsigned bx = 0; bx < gx; ++bx)
+      for (unsigned tx = 0; tx < (unsigned)KT; ++tx) {
+        blockIdx = {bx, by, 0};
+        threadIdx = {tx, 0, 0};
+        body();
+      }
+}
+
+template <class Body>
+void launch_1d(int n, Body body) {
+  const unsigned gx = (unsigned)((n + KT - 1) / KT);
+  gridDim = dim3(gx, 1, 1);
+  blockDim = dim3(KT, 1, 1);
+  for (unsigned bx = 0; bx < gx; ++bx)
+    for (unsigned tx = 0; tx < (unsigned)KT; ++tx) {
+      blockIdx = {bx, 0, 0};
+      threadIdx = {tx, 0, 0};
+      body();
+    }
+}
+
+bool unit(double dx, double dy) { return dx == 1.0 && dy == 1.0; }
+
+}  // namespace
+
+extern "C" {
+
+int emu_pitch(int nx) { return slab_of(nx, 1).pitch; }
+int emu_halo(void) { return HALO; }
+
+void emu_op_grad(int nx, int ny, const double* p, double* gx, double* gy, double dx, double dy) {
+  const Slab s = slab_of(nx, ny);
+  if (unit(dx, dy)) launch(s, [&] { k_op_grad<true>(s, p, gx, gy, dx, dy); });
+  else launch(s, [&] { k_op_grad<false>(s, p, gx, gy, dx, dy); });
+}
+
+void emu_op_div(int nx, int ny, const double* u, const double* v, double* out, double dx, double dy, int central) {
+  const Slab s = slab_of(nx, ny);
+  if (unit(dx, dy)) launch(s, [&] { k_op_div<true>(s, u, v, out, dx, dy, central); });
+  else launch(s, [&] { k_op_div<false>(s, u, v, out, dx, dy, central); });
+}
+
+void emu_op_lap(int nx, int ny, const double* p, double* out, double dx, double dy) {
+  const Slab s = slab_of(nx, ny);
+  if (unit(dx, dy)) launch(s, [&] { k_op_lap<true>(s, p, out, dx, dy); });
+  else launch(s, [&] { k_op_lap<false>(s, p, out, dx, dy); });
+}
+
+void emu_op_advect(int scheme, int nx, int ny, const double* u, const double* v, const double* f, double* out,
+                   double dx, double dy) {
+  const Slab s = slab_of(nx, ny);
+  const bool un = unit(dx, dy);
+  if (scheme == PF_ADV_UPWIND) {
+    if (un) launch(s, [&] { k_op_advect<true, PF_ADV_UPWIND>(s, u, v, f, out, dx, dy); });
+    else launch(s, [&] { k_op_advect<false, PF_ADV_UPWIND>(s, u, v, f, out, dx, dy); });
+  } else {
+    if (un) launch(s, [&] { k_op_advect<true, PF_ADV_QUICK>(s, u, v, f, out, dx, dy); });
+    else launch(s, [&] { k_op_advect<false, PF_ADV_QUICK>(s, u, v, f, out, dx, dy); });
+  }
+}
+
+void emu_op_grad_central(int nx, int ny, const double* p, double* gx, double* gy, double dx, double dy) {
+  const Slab s = slab_of(nx, ny);
+  if (unit(dx, dy)) launch(s, [&] { k_op_grad_central<true>(s, p, gx, gy, dx, dy); });
+  else launch(s, [&] { k_op_grad_central<false>(s, p, gx, gy, dx, dy); });
+}
+
+void emu_op_lap_central(int nx, int ny, const double* p, double* out, double dx, double dy) {
+  const Slab s = slab_of(nx, ny);
+  if (unit(dx, dy)) launch(s, [&] { k_op_lap_central<true>(s, p, out, dx, dy); });
+  else launch(s, [&] { k_op_lap_central<false>(s, p, out, dx, dy); });
+}
+
+void emu_op_correct_central(int dir, int nx, int ny, const double* p, const double* f, double* out, double dt,
+                            double dx, double dy) {
+  const Slab s = slab_of(nx, ny);
+  const bool un = unit(dx, dy);
+  const double h = dir == 0 ? dx : dy;
+  if (dir == 0) {
+    if (un) launch(s, [&] { k_op_correct_central<true, 0>(s, p, f, out, dt, h); });
+    else launch(s, [&] { k_op_correct_central<false, 0>(s, p, f, out, dt, h); });
+  } else {
+    if (un) launch(s, [&] { k_op_correct_central<true, 1>(s, p, f, out, dt, h); });
+    else launch(s, [&] { k_op_correct_central<false, 1>(s, p, f, out, dt, h); });
+  }
+}
+
+// solver.py:71-95 -- (uo, vo) -> (un, vn)
+void emu_predict(int scheme, int nx, int ny, const double* uo, const double* vo, double* un, double* vn, double dt,
+                 double dx, double dy) {
+  const Slab s = slab_of(nx, ny);
+  const bool unt = unit(dx, dy);
+#define PF_EMU_PREDICT(U, S) launch(s, [&] { k_predict<U, S>(s, uo, vo, un, vn, dt, dx, dy); })
+  if (scheme == PF_ADV_UPWIND) { if (unt) PF_EMU_PREDICT(true, PF_ADV_UPWIND); else PF_EMU_PREDICT(false, PF_ADV_UPWIND); }
+  else if (scheme == PF_ADV_QUICK) { if (unt) PF_EMU_PREDICT(true, PF_ADV_QUICK); else PF_EMU_PREDICT(false, PF_ADV_QUICK); }
+  else { if (unt) PF_EMU_PREDICT(true, PF_ADV_NONE); else PF_EMU_PREDICT(false, PF_ADV_NONE); }
+#undef PF_EMU_PREDICT
+}
+
+// pressure_solver.py:147-157 -- p = x - x[0]; u -= dt dp/dx; v -= dt dp/dy  (x0 passed through the scalar block)
+void emu_correct(int nx, int ny, double* x, double* u, double* v, double dt, double dx, double dy, double x0) {
+  const Slab s = slab_of(nx, ny);
+  double scal[S_COUNT] = {0.0};
+  scal[S_X0] = x0;
+  if (unit(dx, dy)) launch(s, [&] { k_correct<true>(s, x, x, u, v, dt, dx, dy, scal); });
+  else launch(s, [&] { k_correct<false>(s, x, x, u, v, dt, dx, dy, scal); });
+}
+
+void emu_lid(int nx, int ny, double* u, double lid) {
+  const Slab s = slab_of(nx, ny);
+  launch_1d(nx, [&] { k_lid(s, u, lid); });
+}
+
+void emu_centerline(int nx, int ny, const double* u, double* center) {
+  const Slab s = slab_of(nx, ny);
+  launch_1d(ny, [&] { k_centerline(s, u, center); });
+}
+
+}  // extern "C"
