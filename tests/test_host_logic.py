@@ -84,6 +84,8 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "pyflow_oracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f
+                # ... nor the test doubles (oracle-backed stand-in slab, host emulation of the kernels)
+                assert "cpu_slab" not in src and "hostemu" not in src and "PF_HOST_EMULATION" not in src, f
 
 
 # ------------------------------------------------------------------ config
