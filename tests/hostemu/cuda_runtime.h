@@ -1,27 +1,86 @@
-// Minimal stand-in for <cuda_runtime.h>: lets g++ parse the .cuh sources of libpyflow_b200 so that the bodies of
-// the element-wise kernels can be executed on the host, one emulated thread at a time (tests only).
+// Minimal stand-in for <cuda_runtime.h> (tests only): lets g++ compile the .cuh sources of libpyflow_b200 so that
+// kernel bodies can be executed on the host.
+//
+// Two execution styles (emu_kernels.cpp):
+//  * kernels whose threads do not communicate run one emulated thread after the other on the calling thread;
+//  * kernels with block reductions (and the cooperative plain CG kernel, on a grid of ONE block) run one OS thread per
+//    CUDA thread of a block: __syncthreads is a barrier over the block, warp shuffles exchange through a per-warp
+//    buffer between two warp barriers, the atomics are real atomics.  Blocks of a grid run one after the other, which
+//    is a legal CUDA schedule for every non-cooperative kernel here ("the last block folds the partials").
 #pragma once
 #include <math.h>
+#include <pthread.h>
 #include <stddef.h>
 #include <stdint.h>
+
 #define __device__
 #define __host__
 #define __global__ static inline
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
+
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct double2 { double x, y; };
 static inline double2 make_double2(double a, double b) { double2 v; v.x = a; v.y = b; return v; }
 typedef void* cudaStream_t;
+
 extern thread_local uint3 threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
-static inline void __syncthreads() {}
-static inline void __threadfence() {}
-static inline void __threadfence_system() {}
-static inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
-static inline double __shfl_up_sync(unsigned, double v, int) { return v; }
-static inline double __shfl_down_sync(unsigned, double v, int) { return v; }
-static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+
+namespace emu {
+constexpr int MAX_THREADS = 512;
+struct Team {                       // the block currently executing with one OS thread per CUDA thread
+  bool threaded = false;
+  pthread_barrier_t block;
+  pthread_barrier_t warp[MAX_THREADS / 32];
+  double xchg[MAX_THREADS];
+};
+extern Team team;
+inline void block_sync() { if (team.threaded) pthread_barrier_wait(&team.block); }
+inline void grid_sync() { block_sync(); }          // cooperative kernels are emulated on a grid of one block
+inline double shuffle(double v, int src_lane) {
+  if (!team.threaded) return v;
+  const int t = (int)threadIdx.x, w = t >> 5;
+  team.xchg[t] = v;
+  pthread_barrier_wait(&team.warp[w]);
+  const double r = team.xchg[(w << 5) | (src_lane & 31)];
+  pthread_barrier_wait(&team.warp[w]);
+  return r;
+}
+}  // namespace emu
+
+static inline void __syncthreads() { emu::block_sync(); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline double __shfl_xor_sync(unsigned, double v, int o) { return emu::shuffle(v, ((int)threadIdx.x & 31) ^ o); }
+static inline double __shfl_up_sync(unsigned, double v, int d) {
+  const int lane = (int)threadIdx.x & 31;
+  const double r = emu::shuffle(v, lane - d < 0 ? lane : lane - d);
+  return r;
+}
+static inline double __shfl_down_sync(unsigned, double v, int d) {
+  const int lane = (int)threadIdx.x & 31;
+  return emu::shuffle(v, lane + d > 31 ? lane : lane + d);
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
+}
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+  unsigned long long o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return o;
+}
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+  unsigned long long o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return o;
+}
+static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) {
+  return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST);
+}
+static inline long long clock64() { return 0; }
+static inline double __longlong_as_double(long long v) { double d; __builtin_memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; __builtin_memcpy(&v, &d, 8); return v; }

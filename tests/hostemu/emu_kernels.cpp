@@ -9,10 +9,17 @@
 // Kernels with grid reductions and the cooperative CG kernels are NOT emulated here; their parity is a GPU matter.
 #include "cuda_runtime.h"
 
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
+emu::Team emu::team;
 
 #include "pf_kernels.cuh"
+#include "pf_cg_generic.cuh"
 
 using namespace pf;
 
@@ -57,6 +64,40 @@ void launch_1d(int n, Body body) {
 }
 
 bool unit(double dx, double dy) { return dx == 1.0 && dy == 1.0; }
+
+// One OS thread per CUDA thread of a block; the blocks of the grid one after the other.
+template <class Body>
+void launch_threaded(dim3 grid, int nthreads, Body body) {
+  emu::Team& t = emu::team;
+  pthread_barrier_init(&t.block, nullptr, (unsigned)nthreads);
+  for (int w = 0; w < nthreads / 32; ++w) pthread_barrier_init(&t.warp[w], nullptr, 32u);
+  t.threaded = true;
+  std::vector<std::thread> pool;
+  for (int tx = 0; tx < nthreads; ++tx)
+    pool.emplace_back([=] {
+      threadIdx = {(unsigned)tx, 0, 0};
+      gridDim = grid;
+      blockDim = dim3((unsigned)nthreads, 1, 1);
+      for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+          blockIdx = {bx, by, 0};
+          body();
+          pthread_barrier_wait(&emu::team.block);      // the next block reuses the (static) shared memory
+        }
+    });
+  for (auto& th : pool) th.join();
+  t.threaded = false;
+  pthread_barrier_destroy(&t.block);
+  for (int w = 0; w < nthreads / 32; ++w) pthread_barrier_destroy(&t.warp[w]);
+}
+
+dim3 simple_grid(const Slab& s) {
+  const unsigned gx = (unsigned)((s.nx + KT - 1) / KT);
+  unsigned gy = 2368u / gx;
+  if (gy < 1u) gy = 1u;
+  if (gy > (unsigned)s.nyl) gy = (unsigned)s.nyl;
+  return dim3(gx, gy, 1);
+}
 
 }  // namespace
 
@@ -152,5 +193,91 @@ void emu_centerline(int nx, int ny, const double* u, double* center) {
   const Slab s = slab_of(nx, ny);
   launch_1d(ny, [&] { k_centerline(s, u, center); });
 }
+
+// ---- kernels with grid reductions: one OS thread per CUDA thread -----------------------------------------------
+// `scratch` holds the reduction workspace: MAX_RED_VALS*MAX_RED_BLOCKS partials, then 4 counters (as doubles' bytes),
+// `scal` the S_COUNT-slot device scalar block.
+static Red red_of(double* scratch, double* scal) {
+  Red r;
+  r.part = scratch;
+  r.counter = (unsigned*)(scratch + (size_t)MAX_RED_VALS * MAX_RED_BLOCKS);
+  r.scal = scal;
+  return r;
+}
+int emu_scratch_doubles(void) { return MAX_RED_VALS * MAX_RED_BLOCKS + 8; }
+int emu_scal_count(void) { return S_COUNT; }
+int emu_slot(const char* name) {
+#define PF_EMU_SLOT(n) if (!strcmp(name, #n)) return n
+  PF_EMU_SLOT(S_UMAX); PF_EMU_SLOT(S_VMAX); PF_EMU_SLOT(S_DIVC_SUMSQ); PF_EMU_SLOT(S_DIVA_SUMSQ);
+  PF_EMU_SLOT(S_RU_SUMSQ); PF_EMU_SLOT(S_RV_SUMSQ); PF_EMU_SLOT(S_NONFINITE); PF_EMU_SLOT(S_UNAN); PF_EMU_SLOT(S_VNAN);
+  PF_EMU_SLOT(S_DIVB_SUMSQ); PF_EMU_SLOT(S_RHS_SUM); PF_EMU_SLOT(S_BB); PF_EMU_SLOT(S_BZ); PF_EMU_SLOT(S_RES_SUMSQ);
+  PF_EMU_SLOT(S_X0); PF_EMU_SLOT(S_RR); PF_EMU_SLOT(S_INFO); PF_EMU_SLOT(S_ITERS); PF_EMU_SLOT(S_TMP0); PF_EMU_SLOT(S_TMP1);
+#undef PF_EMU_SLOT
+  return -1;
+}
+
+void emu_prestep(int nx, int ny, const double* u, const double* v, double* scratch, double* scal) {
+  const Slab s = slab_of(nx, ny);
+  const Red red = red_of(scratch, scal);
+  launch_threaded(simple_grid(s), KT, [&] { k_prestep(s, u, v, red); });
+}
+
+void emu_rhs1(int nx, int ny, const double* u, const double* v, double* b, double dt_safe, double dx, double dy,
+              double* scratch, double* scal) {
+  const Slab s = slab_of(nx, ny);
+  const Red red = red_of(scratch, scal);
+  if (unit(dx, dy)) launch_threaded(simple_grid(s), KT, [&] { k_rhs1<true>(s, u, v, b, dt_safe, dx, dy, red); });
+  else launch_threaded(simple_grid(s), KT, [&] { k_rhs1<false>(s, u, v, b, dt_safe, dx, dy, red); });
+}
+
+void emu_rhs2(int nx, int ny, double* b, double* x, double* r, int subtract_mean, int pin, double invd,
+              double* scratch, double* scal) {
+  const Slab s = slab_of(nx, ny);
+  const Red red = red_of(scratch, scal);
+  const double ncells = (double)nx * (double)ny;
+  launch_threaded(simple_grid(s), KT, [&] { k_rhs2(s, b, x, r, ncells, subtract_mean, pin, invd, red); });
+}
+
+void emu_resid(int nx, int ny, const double* b, const double* x, double dx, double dy, double* scratch, double* scal) {
+  const Slab s = slab_of(nx, ny);
+  const Red red = red_of(scratch, scal);
+  if (unit(dx, dy)) launch_threaded(simple_grid(s), KT, [&] { k_resid<true>(s, b, x, dx, dy, red); });
+  else launch_threaded(simple_grid(s), KT, [&] { k_resid<false>(s, b, x, dx, dy, red); });
+}
+
+void emu_divnorm(int nx, int ny, const double* u, const double* v, double dx, double dy, double* scratch, double* scal) {
+  const Slab s = slab_of(nx, ny);
+  const Red red = red_of(scratch, scal);
+  if (unit(dx, dy)) launch_threaded(simple_grid(s), KT, [&] { k_divnorm<true>(s, u, v, dx, dy, red, S_DIVA_SUMSQ); });
+  else launch_threaded(simple_grid(s), KT, [&] { k_divnorm<false>(s, u, v, dx, dy, red, S_DIVA_SUMSQ); });
+}
+
+void emu_post(int nx, int ny, const double* u, const double* v, const double* uo, const double* vo, const double* p,
+              double* center, double* scratch, double* scal) {
+  const Slab s = slab_of(nx, ny);
+  const Red red = red_of(scratch, scal);
+  launch_threaded(simple_grid(s), KT, [&] { k_post(s, u, v, uo, vo, p, center, red); });
+}
+
+void emu_divc_stats(int nx, int ny, const double* u, const double* v, double dx, double dy, int pass, double* scratch,
+                    double* scal) {
+  const Slab s = slab_of(nx, ny);
+  const Red red = red_of(scratch, scal);
+  const double ncells = (double)nx * (double)ny;
+  if (unit(dx, dy)) launch_threaded(simple_grid(s), KT, [&] { k_divc_stats<true>(s, u, v, dx, dy, pass, ncells, red); });
+  else launch_threaded(simple_grid(s), KT, [&] { k_divc_stats<false>(s, u, v, dx, dy, pass, ncells, red); });
+}
+
+// The plain device CG (q stored, one thread per cell) on a cooperative grid of ONE block.
+void emu_cg_generic(int mode, int nx, int ny, const double* b, double* x, double* r, double* p, double* q, double dx,
+                    double dy, double invd, double tol, int maxiter, double* part, double* scal) {
+  GenArgs a;
+  a.s = slab_of(nx, ny);
+  a.b = b; a.x = x; a.r = r; a.p = p; a.q = q; a.part = part; a.scal = scal;
+  a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter; a.mode = mode;
+  if (unit(dx, dy)) launch_threaded(dim3(1, 1, 1), CG_THREADS, [&] { k_cg_generic<true>(a); });
+  else launch_threaded(dim3(1, 1, 1), CG_THREADS, [&] { k_cg_generic<false>(a); });
+}
+int emu_cg_part_doubles(void) { return 3 * CG_MAX_GRID; }
 
 }  // extern "C"

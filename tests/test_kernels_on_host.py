@@ -1,4 +1,5 @@
-"""The element-wise CUDA kernels EXECUTED ON THE HOST, bit for bit against the reference's golden vectors.
+"""The CUDA kernel sources EXECUTED ON THE HOST: element-wise kernels bit for bit against the reference's golden
+vectors, reduction kernels and the plain CG kernel against numpy / the oracle, whole projection steps chained from them.
 
 ``tests/hostemu/emu_kernels.cpp`` includes the real kernel sources (``pyflow-solver_b200/csrc/pf_kernels.cuh``)
 under a minimal stand-in for ``<cuda_runtime.h>`` and runs each kernel body once per emulated thread, in the
@@ -8,8 +9,14 @@ written by the unmodified reference -- which lets the arithmetic of these kernel
 machine without a GPU.  Halo rows and padding columns are filled with NaN: a kernel that read outside the domain
 would poison its output.
 
-Scope: kernels whose threads do not communicate (operators, legacy central operators, predictor, correction, lid
-row, centre line).  Kernels with grid reductions and the cooperative CG kernels are covered by ``-m gpu`` only.
+Two execution styles: kernels whose threads do not communicate (operators, legacy central operators, predictor,
+correction, lid row, centre line) run one emulated thread after the other; kernels with grid reductions (pre-step,
+rhs, residual, divergence norms, post-step pass) and the plain cooperative CG kernel (``k_cg_generic``, on a grid of
+one block) run with ONE OS THREAD PER CUDA THREAD -- ``__syncthreads`` is a barrier, warp shuffles go through a
+per-warp exchange buffer, atomics are atomics -- so the "last block folds the partials" machinery and the whole CG
+recurrence execute as written.  Chained in the order of ``pf_step`` they make a complete projection step from the
+CUDA sources on the host, compared with the oracle.  The tuned CG kernels (TMA / register-window / shared-memory,
+PTX inside) are NOT emulated; their parity is the ``-m gpu`` suite's business.
 """
 import ctypes as C
 import os
@@ -29,7 +36,7 @@ UPWIND, QUICK, NONE = 0, 1, 2
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("hostemu") / "emu_kernels.so")
-    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-pthread", "-fPIC", "-shared",
            "-I", os.path.join(ROOT, "tests", "hostemu"), "-I", os.path.join(ROOT, "pyflow-solver_b200", "csrc"),
            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "hostemu", "emu_kernels.cpp"), "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -47,6 +54,15 @@ def emu(tmp_path_factory):
     lib.emu_correct.argtypes = [i, i, dp, dp, dp, d, d, d, d]
     lib.emu_lid.argtypes = [i, i, dp, d]
     lib.emu_centerline.argtypes = [i, i, dp, dp]
+    lib.emu_slot.argtypes = [C.c_char_p]
+    lib.emu_prestep.argtypes = [i, i, dp, dp, dp, dp]
+    lib.emu_rhs1.argtypes = [i, i, dp, dp, dp, d, d, d, dp, dp]
+    lib.emu_rhs2.argtypes = [i, i, dp, dp, dp, i, i, d, dp, dp]
+    lib.emu_resid.argtypes = [i, i, dp, dp, d, d, dp, dp]
+    lib.emu_divnorm.argtypes = [i, i, dp, dp, d, d, dp, dp]
+    lib.emu_post.argtypes = [i, i, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.emu_divc_stats.argtypes = [i, i, dp, dp, d, d, i, dp, dp]
+    lib.emu_cg_generic.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     return lib
 
 
@@ -164,3 +180,169 @@ def test_nan_and_inf_propagate_like_numpy(emu):
         assert same(dev.get(out), orc.laplacian_coherent(p, 1.0, 1.0))
         emu.emu_op_lap_central(20, 12, ptr(dev.put(p)), ptr(out), 0.5, 0.25)
         assert same(dev.get(out), orc.laplacian_central(p, 0.5, 0.25))
+
+
+# ===================================================================================================================
+# kernels with grid reductions and the plain CG kernel: one OS thread per CUDA thread
+# ===================================================================================================================
+class Scalars:
+    def __init__(self, lib):
+        self.lib = lib
+        self.scal = np.zeros(lib.emu_scal_count())
+        self.scratch = np.zeros(lib.emu_scratch_doubles())
+
+    def __getitem__(self, name):
+        k = self.lib.emu_slot(name.encode())
+        assert k >= 0, name
+        return float(self.scal[k])
+
+
+def close(a, b, rtol=1e-13):
+    return abs(a - b) <= rtol * max(abs(a), abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("shape,unit", [((20, 24), True), ((9, 300), False), ((2, 2), True), ((33, 17), False)])
+def test_reduction_kernels_vs_numpy(emu, shape, unit):
+    ny, nx = shape
+    rng = np.random.default_rng(ny * 31 + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.37, 1.9)
+    dt = 0.0123
+    u, v, uo, vo, p = (rng.standard_normal(shape) for _ in range(5))
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    du, dv_ = dev.put(u), dev.put(v)
+    # k_prestep: solver.py:25-26,45
+    emu.emu_prestep(nx, ny, ptr(du), ptr(dv_), ptr(S.scratch), ptr(S.scal))
+    assert S["S_UMAX"] == np.abs(u).max() and S["S_VMAX"] == np.abs(v).max() and S["S_UNAN"] == 0.0
+    dc = orc.divergence_central(u, v, 1.0, 1.0)
+    assert close(S["S_DIVC_SUMSQ"], float(np.sum(dc * dc)))
+    # k_rhs1: pressure_solver.py:116-123 -- b bit-exact, sums in another order
+    b = dev.put()
+    emu.emu_rhs1(nx, ny, ptr(du), ptr(dv_), ptr(b), dt, dx, dy, ptr(S.scratch), ptr(S.scal))
+    div = orc.divergence_coherent(u, v, dx, dy)
+    rhs = -div / dt
+    assert same(dev.get(b), rhs)
+    assert close(S["S_DIVB_SUMSQ"], float(np.sum(div * div))) and close(S["S_RHS_SUM"], float(rhs.sum()), 1e-11)
+    # k_rhs2: mean shift with the DEVICE's sum, pin, r = b, x = 0, b.b, b.Mb
+    x, r = dev.put(np.ones(shape)), dev.put()
+    invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)
+    emu.emu_rhs2(nx, ny, ptr(b), ptr(x), ptr(r), 1, 1, invd, ptr(S.scratch), ptr(S.scal))
+    want = rhs - S["S_RHS_SUM"] / (nx * ny)
+    want[0, 0] = 0.0
+    assert same(dev.get(b), want) and same(dev.get(r), want) and not dev.get(x).any()
+    M = orc.jacobi_inverse_diagonal(nx, ny, dx, dy).reshape(shape)
+    assert close(S["S_BB"], float(np.sum(want * want))) and close(S["S_BZ"], float(np.sum(want * (M * want))))
+    # k_resid: ||b - A x||^2 with the pinned operator, x[0] recorded
+    xr = rng.standard_normal(shape)
+    emu.emu_resid(nx, ny, ptr(b), ptr(dev.put(xr)), dx, dy, ptr(S.scratch), ptr(S.scal))
+    res = want.ravel() - orc.neg_laplacian_pinned(xr.ravel(), nx, ny, dx, dy)
+    assert close(S["S_RES_SUMSQ"], float(res @ res)) and S["S_X0"] == xr[0, 0]
+    # k_divnorm
+    emu.emu_divnorm(nx, ny, ptr(du), ptr(dv_), dx, dy, ptr(S.scratch), ptr(S.scal))
+    assert close(S["S_DIVA_SUMSQ"], float(np.sum(div * div)))
+    # k_post: solver.py:108-121, next step's maxima, the driver's centre line
+    center = np.full(ny, np.nan)
+    emu.emu_post(nx, ny, ptr(du), ptr(dv_), ptr(dev.put(uo)), ptr(dev.put(vo)), ptr(dev.put(p)), ptr(center),
+                 ptr(S.scratch), ptr(S.scal))
+    assert close(S["S_RU_SUMSQ"], float(np.sum((u - uo) ** 2))) and close(S["S_RV_SUMSQ"], float(np.sum((v - vo) ** 2)))
+    assert close(S["S_DIVC_SUMSQ"], float(np.sum(dc * dc))) and S["S_NONFINITE"] == 0.0
+    assert S["S_UMAX"] == np.abs(u).max() and same(center, u[:, nx // 2])
+    # ... and a NaN is counted, not lost
+    un = u.copy()
+    un[ny // 2, nx // 2] = np.nan
+    emu.emu_post(nx, ny, ptr(dev.put(un)), ptr(dv_), ptr(dev.put(uo)), ptr(dev.put(vo)), ptr(dev.put(p)), ptr(center),
+                 ptr(S.scratch), ptr(S.scal))
+    assert S["S_NONFINITE"] > 0.0 and S["S_UNAN"] == 1.0
+    # k_divc_stats (alternate driver): mean, then mean-free norm
+    emu.emu_divc_stats(nx, ny, ptr(du), ptr(dv_), dx, dy, 0, ptr(S.scratch), ptr(S.scal))
+    emu.emu_divc_stats(nx, ny, ptr(du), ptr(dv_), dx, dy, 1, ptr(S.scratch), ptr(S.scal))
+    dcs = orc.divergence_central(u, v, dx, dy)
+    assert close(S["S_TMP0"] / (nx * ny), float(dcs.mean()), 1e-10)
+    assert close(S["S_TMP1"], float(np.sum((dcs - S["S_TMP0"] / (nx * ny)) ** 2)), 1e-12)
+
+
+def _cg_generic(emu, mode, b, dx, dy, invd, tol, maxiter):
+    ny, nx = b.shape
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    x, r, p, q = dev.put(), dev.put(), dev.put(), dev.put()
+    part = np.zeros(emu.emu_cg_part_doubles())
+    emu.emu_cg_generic(mode, nx, ny, ptr(dev.put(b)), ptr(x), ptr(r), ptr(p), ptr(q), dx, dy, invd, tol, maxiter,
+                       ptr(part), ptr(S.scal))
+    return dev.get(x), int(S["S_INFO"]), int(S["S_ITERS"]), S["S_RES_SUMSQ"] ** 0.5
+
+
+@pytest.mark.parametrize("shape,unit,jacobi,maxiter", [((12, 16), True, True, 2000), ((9, 7), False, True, 2000),
+                                                       ((10, 10), True, False, 2000), ((12, 16), True, True, 7)])
+def test_plain_cg_kernel_follows_scipys_recurrence(emu, shape, unit, jacobi, maxiter):
+    """k_cg_generic, pinned operator: x0 = 0, strict test at the top of the loop, info = maxiter when exhausted."""
+    ny, nx = shape
+    rng = np.random.default_rng(5 * ny + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.5, 0.25)
+    b = rng.standard_normal(shape)
+    b -= b.mean()
+    b[0, 0] = 0.0
+    invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2) if jacobi else 1.0
+    x, info, iters, rnorm = _cg_generic(emu, 0, b, dx, dy, invd, 1e-10, maxiter)
+    inv = orc.jacobi_inverse_diagonal(nx, ny, dx, dy) if jacobi else None
+    A = lambda z: orc.neg_laplacian_pinned(z, nx, ny, dx, dy)        # noqa: E731
+    xo, io, to = orc.pcg(A, b.ravel().copy(), 1e-10, maxiter, inv)
+    assert info == io and abs(iters - to) <= 1
+    assert np.linalg.norm(x.ravel() - xo) <= 1e-9 * np.linalg.norm(xo)
+    assert close(rnorm, float(np.linalg.norm(b.ravel() - A(x.ravel()))), 1e-6)
+    zero = _cg_generic(emu, 0, np.zeros(shape), dx, dy, invd, 1e-10, 50)
+    assert zero[1] == 0 and zero[2] == 0 and not zero[0].any()       # b = 0  =>  x = 0, no iterations
+
+
+def test_plain_cg_kernel_dirichlet_mode_vs_oracle(emu):
+    """Manufactured / Dirichlet mode (pressure_solver.py:61-93): +laplacian with identity rows on the ring."""
+    nx, ny = 14, 11
+    dx, dy = 1.0 / (nx - 1), 1.0 / (ny - 1)
+    X, Y = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 1, ny))
+    rhs = np.zeros((ny, nx))
+    rhs[1:-1, 1:-1] = (-2.0 * np.pi ** 2 * np.sin(np.pi * X) * np.sin(np.pi * Y))[1:-1, 1:-1]
+    x, info, iters, _rn = _cg_generic(emu, 1, rhs, dx, dy, 1.0, 1e-10, 500)
+    from types import SimpleNamespace
+    po, od = orc.solve_manufactured(orc.allocate_state(nx, ny), dx, dy,
+                                    SimpleNamespace(lin_tol=1e-10, lin_maxiter=500), rhs.reshape(-1))
+    assert info == od["info"] and abs(iters - od["true_iterations"]) <= 1
+    assert np.linalg.norm(x - po) <= 1e-9 * np.linalg.norm(po)
+
+
+@pytest.mark.parametrize("scheme_name,nx,ny,spacing", [("quick", 12, 10, None), ("upwind", 9, 7, (2.0, 1.0))])
+def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_name, nx, ny, spacing):
+    """The kernels chained in the order of pf_step (pf_api.cu), plain CG kernel for the solve, host dt logic from
+    the oracle: three steps of a driven cavity against the oracle."""
+    from types import SimpleNamespace
+    cfg = SimpleNamespace(nx=nx, ny=ny, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
+                          lin_maxiter=3000, advection_scheme=scheme_name, disable_advection=False, diagnostics=False)
+    if spacing:
+        cfg.lx, cfg.ly = spacing
+    scheme = QUICK if scheme_name == "quick" else UPWIND
+    ost = orc.allocate_state(nx, ny)
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    u, v, uo, vo = dev.put(), dev.put(), dev.put(), dev.put()
+    b, x, r, p, q = dev.put(), dev.put(), dev.put(), dev.put(), dev.put()
+    part = np.zeros(emu.emu_cg_part_doubles())
+    center = np.zeros(ny)
+    for it in range(3):
+        _, ores, od = orc.step(cfg, ost, it)
+        dt, dx, dy = od["dt"], ost.meta["dx"], ost.meta["dy"]
+        invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)
+        emu.emu_predict(scheme, nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), dt, dx, dy)
+        u, uo, v, vo = uo, u, vo, v                                   # u, v hold u*, v*; uo, vo the previous step
+        emu.emu_rhs1(nx, ny, ptr(u), ptr(v), ptr(b), max(dt, 1e-14), dx, dy, ptr(S.scratch), ptr(S.scal))
+        emu.emu_rhs2(nx, ny, ptr(b), ptr(x), ptr(r), 1, 1, invd, ptr(S.scratch), ptr(S.scal))
+        emu.emu_cg_generic(0, nx, ny, ptr(b), ptr(x), ptr(r), ptr(p), ptr(q), dx, dy, invd, 1e-10, 3000, ptr(part),
+                           ptr(S.scal))
+        assert abs(int(S["S_ITERS"]) - od["true_iterations"]) <= 1
+        emu.emu_resid(nx, ny, ptr(b), ptr(x), dx, dy, ptr(S.scratch), ptr(S.scal))
+        emu.emu_correct(nx, ny, ptr(x), ptr(u), ptr(v), dt, dx, dy, S["S_X0"])
+        emu.emu_divnorm(nx, ny, ptr(u), ptr(v), dx, dy, ptr(S.scratch), ptr(S.scal))
+        assert close(S["S_DIVA_SUMSQ"] ** 0.5, od["divergence_norm"], 1e-6)
+        emu.emu_lid(nx, ny, ptr(u), 1.0)
+        emu.emu_post(nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), ptr(x), ptr(center), ptr(S.scratch), ptr(S.scal))
+        assert close(S["S_RU_SUMSQ"] ** 0.5 / (nx * ny), ores["Ru"], 1e-8) and S["S_NONFINITE"] == 0.0
+        assert close(S["S_DIVC_SUMSQ"] ** 0.5 / (nx * ny), ores["continuity"], 1e-8)
+    for name, buf in (("u", u), ("v", v), ("p", x)):
+        a, want = dev.get(buf), orc.interior(ost.fields[name])
+        assert np.linalg.norm(a - want) <= 1e-9 * (np.linalg.norm(want) or 1.0), name
+    assert same(center, dev.get(u)[:, nx // 2])
