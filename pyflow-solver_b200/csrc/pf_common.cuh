@@ -78,6 +78,21 @@ __device__ __forceinline__ double neg_lap(double c, double w, double e, double s
 
 // ---- raw global memory access (never the non-coherent path: buffers are
 // rewritten between phases of the persistent kernel) -------------------------
+#ifdef PF_HOST_EMULATION
+// tests/hostemu compiles these sources with g++ and executes kernel bodies on the host (one OS thread per CUDA
+// thread): the PTX accessors below become plain loads and stores there.  Never defined in the product build.
+__device__ __forceinline__ double2 ld2(const double* p) { return make_double2(p[0], p[1]); }
+__device__ __forceinline__ double ld1(const double* p) { return *(const volatile double*)p; }
+__device__ __forceinline__ uint64_t policy_evict_first() { return 0; }
+__device__ __forceinline__ uint64_t policy_evict_last() { return 0; }
+__device__ __forceinline__ uint64_t policy_evict_normal() { return 0; }
+__device__ __forceinline__ double2 ld2_hint(const double* p, uint64_t) { return make_double2(p[0], p[1]); }
+__device__ __forceinline__ double2 ld2_hint_nol1(const double* p, uint64_t) { return make_double2(p[0], p[1]); }
+__device__ __forceinline__ void st2_hint(double* p, double a, double b, uint64_t) { p[0] = a; p[1] = b; }
+__device__ __forceinline__ void st2(double* p, double a, double b) { p[0] = a; p[1] = b; }
+__device__ __forceinline__ void st1(double* p, double a) { p[0] = a; }
+__device__ __forceinline__ double ld_cg(const double* p) { return *(const volatile double*)p; }
+#else
 __device__ __forceinline__ double2 ld2(const double* p) {
   double2 v;
   asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
@@ -128,14 +143,11 @@ __device__ __forceinline__ void st1(double* p, double a) {
   asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
 }
 __device__ __forceinline__ double ld_cg(const double* p) {  // L2-only (partials, scalars)
-#ifdef PF_HOST_EMULATION      // tests/hostemu executes the kernel sources on the host: a plain load there
-  return *(const volatile double*)p;
-#else
   double v;
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
-#endif
 }
+#endif  // PF_HOST_EMULATION
 
 // ---- deterministic reductions ----------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -278,6 +278,32 @@ void emu_cg_generic(int mode, int nx, int ny, const double* b, double* x, double
   if (unit(dx, dy)) launch_threaded(dim3(1, 1, 1), CG_THREADS, [&] { k_cg_generic<true>(a); });
   else launch_threaded(dim3(1, 1, 1), CG_THREADS, [&] { k_cg_generic<false>(a); });
 }
-int emu_cg_part_doubles(void) { return 3 * CG_MAX_GRID; }
+int emu_cg_part_doubles(void) { return PF_PART_DOUBLES; }
+
+// The register-window persistent CG kernel (k_cg_persistent, the production kernel for widths that are not a multiple
+// of 1024) on a cooperative grid of ONE block, with the tile geometry cg_geometry() of pf_api.cu computes for it.
+// r = b, x = 0, S_BB and S_BZ must have been prepared (k_rhs2), as solve_on_device does.
+void emu_cg_persistent(int nx, int ny, const double* b, double* x, double* r, double* p0, double* p1, double dx,
+                       double dy, double invd, double tol, int maxiter, int rows_min_per_warp, double* part,
+                       double* scal) {
+  CgArgs a{};
+  a.s = slab_of(nx, ny);
+  a.b = b; a.x = x; a.r = r; a.p0 = p0; a.p1 = p1; a.part = part; a.scal = scal;
+  a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
+  const int G = 1;
+  const int nstrips = (nx + STRIP - 1) / STRIP;
+  int wx = 1;
+  while (wx * 2 <= CG_WARPS && wx * 2 <= nstrips) wx *= 2;
+  a.wx = wx;
+  a.wy = CG_WARPS / wx;
+  a.nchunks = (nstrips + wx - 1) / wx;
+  const int rows_min = rows_min_per_warp * a.wy;
+  const int max_bands = ny / rows_min > 1 ? ny / rows_min : 1;
+  const int want = G / a.nchunks > 1 ? G / a.nchunks : 1;
+  a.nbands = want < max_bands ? want : max_bands;
+  a.ntiles = a.nchunks * a.nbands;
+  if (unit(dx, dy)) launch_threaded(dim3(G, 1, 1), CG_THREADS, [&] { k_cg_persistent<true>(a); });
+  else launch_threaded(dim3(G, 1, 1), CG_THREADS, [&] { k_cg_persistent<false>(a); });
+}
 
 }  // extern "C"

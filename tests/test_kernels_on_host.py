@@ -15,8 +15,9 @@ rhs, residual, divergence norms, post-step pass) and the plain cooperative CG ke
 one block) run with ONE OS THREAD PER CUDA THREAD -- ``__syncthreads`` is a barrier, warp shuffles go through a
 per-warp exchange buffer, atomics are atomics -- so the "last block folds the partials" machinery and the whole CG
 recurrence execute as written.  Chained in the order of ``pf_step`` they make a complete projection step from the
-CUDA sources on the host, compared with the oracle.  The tuned CG kernels (TMA / register-window / shared-memory,
-PTX inside) are NOT emulated; their parity is the ``-m gpu`` suite's business.
+CUDA sources on the host, compared with the oracle.  The register-window production CG kernel (``k_cg_persistent``)
+runs the same way on one CTA.  The TMA-fed and shared-memory-resident CG kernels and the multi-GPU variants (mbarrier /
+bulk-copy / packet PTX, several co-resident CTAs) are NOT emulated; their parity is the ``-m gpu`` suite's business.
 """
 import ctypes as C
 import os
@@ -36,7 +37,7 @@ UPWIND, QUICK, NONE = 0, 1, 2
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("hostemu") / "emu_kernels.so")
-    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-pthread", "-fPIC", "-shared",
+    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-pthread", "-fPIC", "-shared",
            "-I", os.path.join(ROOT, "tests", "hostemu"), "-I", os.path.join(ROOT, "pyflow-solver_b200", "csrc"),
            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "hostemu", "emu_kernels.cpp"), "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -63,6 +64,7 @@ def emu(tmp_path_factory):
     lib.emu_post.argtypes = [i, i, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.emu_divc_stats.argtypes = [i, i, dp, dp, d, d, i, dp, dp]
     lib.emu_cg_generic.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
+    lib.emu_cg_persistent.argtypes = [i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp]
     return lib
 
 
@@ -270,8 +272,8 @@ def _cg_generic(emu, mode, b, dx, dy, invd, tol, maxiter):
     return dev.get(x), int(S["S_INFO"]), int(S["S_ITERS"]), S["S_RES_SUMSQ"] ** 0.5
 
 
-@pytest.mark.parametrize("shape,unit,jacobi,maxiter", [((12, 16), True, True, 2000), ((9, 7), False, True, 2000),
-                                                       ((10, 10), True, False, 2000), ((12, 16), True, True, 7)])
+@pytest.mark.parametrize("shape,unit,jacobi,maxiter", [((8, 10), True, True, 2000), ((7, 5), False, True, 2000),
+                                                       ((6, 6), True, False, 2000), ((8, 10), True, True, 7)])
 def test_plain_cg_kernel_follows_scipys_recurrence(emu, shape, unit, jacobi, maxiter):
     """k_cg_generic, pinned operator: x0 = 0, strict test at the top of the loop, info = maxiter when exhausted."""
     ny, nx = shape
@@ -307,10 +309,12 @@ def test_plain_cg_kernel_dirichlet_mode_vs_oracle(emu):
     assert np.linalg.norm(x - po) <= 1e-9 * np.linalg.norm(po)
 
 
-@pytest.mark.parametrize("scheme_name,nx,ny,spacing", [("quick", 12, 10, None), ("upwind", 9, 7, (2.0, 1.0))])
-def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_name, nx, ny, spacing):
-    """The kernels chained in the order of pf_step (pf_api.cu), plain CG kernel for the solve, host dt logic from
-    the oracle: three steps of a driven cavity against the oracle."""
+@pytest.mark.parametrize("scheme_name,nx,ny,spacing,solver", [("quick", 8, 6, None, "generic"),
+                                                              ("upwind", 7, 5, (2.0, 1.0), "register-window")])
+def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_name, nx, ny, spacing, solver):
+    """The kernels chained in the order of pf_step (pf_api.cu) -- the solve by the plain CG kernel or by the
+    register-window kernel the library itself picks for an odd width --, host dt logic from the oracle: three steps
+    of a driven cavity against the oracle."""
     from types import SimpleNamespace
     cfg = SimpleNamespace(nx=nx, ny=ny, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
                           lin_maxiter=3000, advection_scheme=scheme_name, disable_advection=False, diagnostics=False)
@@ -331,8 +335,12 @@ def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_na
         u, uo, v, vo = uo, u, vo, v                                   # u, v hold u*, v*; uo, vo the previous step
         emu.emu_rhs1(nx, ny, ptr(u), ptr(v), ptr(b), max(dt, 1e-14), dx, dy, ptr(S.scratch), ptr(S.scal))
         emu.emu_rhs2(nx, ny, ptr(b), ptr(x), ptr(r), 1, 1, invd, ptr(S.scratch), ptr(S.scal))
-        emu.emu_cg_generic(0, nx, ny, ptr(b), ptr(x), ptr(r), ptr(p), ptr(q), dx, dy, invd, 1e-10, 3000, ptr(part),
-                           ptr(S.scal))
+        if solver == "generic":
+            emu.emu_cg_generic(0, nx, ny, ptr(b), ptr(x), ptr(r), ptr(p), ptr(q), dx, dy, invd, 1e-10, 3000, ptr(part),
+                               ptr(S.scal))
+        else:
+            emu.emu_cg_persistent(nx, ny, ptr(b), ptr(x), ptr(r), ptr(p), ptr(q), dx, dy, invd, 1e-10, 3000, 4,
+                                  ptr(part), ptr(S.scal))
         assert abs(int(S["S_ITERS"]) - od["true_iterations"]) <= 1
         emu.emu_resid(nx, ny, ptr(b), ptr(x), dx, dy, ptr(S.scratch), ptr(S.scal))
         emu.emu_correct(nx, ny, ptr(x), ptr(u), ptr(v), dt, dx, dy, S["S_X0"])
@@ -346,3 +354,44 @@ def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_na
         a, want = dev.get(buf), orc.interior(ost.fields[name])
         assert np.linalg.norm(a - want) <= 1e-9 * (np.linalg.norm(want) or 1.0), name
     assert same(center, dev.get(u)[:, nx // 2])
+
+
+# ===================================================================================================================
+# the register-window persistent CG kernel (production kernel for widths that are not a multiple of 1024)
+# ===================================================================================================================
+def _cg_persistent(emu, b, dx, dy, jacobi, tol, maxiter):
+    ny, nx = b.shape
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2) if jacobi else 1.0
+    bb, x, r, p0, p1 = dev.put(b), dev.put(), dev.put(), dev.put(), dev.put()
+    emu.emu_rhs2(nx, ny, ptr(bb), ptr(x), ptr(r), 0, 0, invd, ptr(S.scratch), ptr(S.scal))     # r = b, x = 0, b.b, b.Mb
+    part = np.zeros(emu.emu_cg_part_doubles())
+    emu.emu_cg_persistent(nx, ny, ptr(bb), ptr(x), ptr(r), ptr(p0), ptr(p1), dx, dy, invd, tol, maxiter, 4, ptr(part),
+                          ptr(S.scal))
+    return dev.get(x), dev.get(r), int(S["S_INFO"]), int(S["S_ITERS"])
+
+
+@pytest.mark.parametrize("ny,nx,unit,jacobi,maxiter", [
+    (3, 3, True, True, 300), (5, 3, True, True, 300), (4, 5, False, True, 300),       # the smallest odd-width grids
+    (33, 17, False, True, 10), (12, 65, True, True, 12), (9, 129, True, False, 10),    # one partial strip; nx % 64 == 1
+    (10, 200, False, True, 8), (40, 70, True, True, 10),                               # wall + partial strips, 5 rows per warp
+    (7, 577, True, True, 8),                                                           # two chunks of eight strips
+])
+def test_register_window_cg_kernel_vs_oracle(emu, ny, nx, unit, jacobi, maxiter):
+    """k_cg_persistent on one CTA against scipy's recurrence (oracle.pcg): same stopping decisions, x and the
+    recursive residual to 1e-10, on the column layouts that select its strip kinds (inside / wall / partial)."""
+    rng = np.random.default_rng(ny * 1009 + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.5, 0.25)
+    b = rng.standard_normal((ny, nx))
+    b -= b.mean()
+    b[0, 0] = 0.0
+    x, r, info, iters = _cg_persistent(emu, b, dx, dy, jacobi, 1e-10, maxiter)
+    inv = orc.jacobi_inverse_diagonal(nx, ny, dx, dy) if jacobi else None
+    A = lambda z: orc.neg_laplacian_pinned(z, nx, ny, dx, dy)        # noqa: E731
+    xo, io, to = orc.pcg(A, b.ravel().copy(), 1e-10, maxiter, inv)
+    assert info == io and abs(iters - to) <= 1, (info, io, iters, to)
+    assert np.isfinite(x).all() and np.isfinite(r).all()
+    if iters == to:
+        assert np.linalg.norm(x.ravel() - xo) <= 1e-10 * np.linalg.norm(xo)
+    else:
+        assert np.linalg.norm(x.ravel() - xo) <= 1e-8 * np.linalg.norm(xo)
