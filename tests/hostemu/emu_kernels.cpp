@@ -306,4 +306,49 @@ void emu_cg_persistent(int nx, int ny, const double* b, double* x, double* r, do
   else launch_threaded(dim3(G, 1, 1), CG_THREADS, [&] { k_cg_persistent<false>(a); });
 }
 
+// The split-phase CG kernels (k_cg_begin / k_cg_phaseA / k_cg_phaseB / k_cg_update / k_cg_finish): the sequence the
+// library launches between NCCL calls on multi-GPU slabs without peer memory, here for ONE rank (no exchange needed)
+// on a grid of G CTAs, so that several bands per chunk and several tiles per CTA are exercised.
+void emu_cg_split(int nx, int ny, int G, const double* b, double* x, double* r, double* p0, double* p1, double dx,
+                  double dy, double invd, double tol, int maxiter, int rows_min_per_warp, double* part, double* scal,
+                  double* scratch) {
+  CgArgs a{};
+  a.s = slab_of(nx, ny);
+  a.b = b; a.x = x; a.r = r; a.p0 = p0; a.p1 = p1; a.part = part; a.scal = scal;
+  a.dx = dx; a.dy = dy; a.invd = invd; a.tol = tol; a.maxiter = maxiter;
+  const int nstrips = (nx + STRIP - 1) / STRIP;
+  int wx = 1;
+  while (wx * 2 <= CG_WARPS && wx * 2 <= nstrips) wx *= 2;
+  a.wx = wx;
+  a.wy = CG_WARPS / wx;
+  a.nchunks = (nstrips + wx - 1) / wx;
+  const int rows_min = rows_min_per_warp * a.wy;
+  const int max_bands = ny / rows_min > 1 ? ny / rows_min : 1;
+  const int want = G / a.nchunks > 1 ? G / a.nchunks : 1;
+  a.nbands = want < max_bands ? want : max_bands;
+  a.ntiles = a.nchunks * a.nbands;
+  unsigned* counter = (unsigned*)(scratch + (size_t)MAX_RED_VALS * MAX_RED_BLOCKS) + 1;
+  const bool un = unit(dx, dy);
+  launch_threaded(dim3(1, 1, 1), 32, [&] { k_cg_begin(scal, tol); });
+  for (int it = 0; it < maxiter; ++it) {
+    if (un) launch_threaded(dim3(G, 1, 1), CG_THREADS, [&] { k_cg_phaseA<true>(a, it, counter); });
+    else launch_threaded(dim3(G, 1, 1), CG_THREADS, [&] { k_cg_phaseA<false>(a, it, counter); });
+    if (un) launch_threaded(dim3(G, 1, 1), CG_THREADS, [&] { k_cg_phaseB<true>(a, it, counter); });
+    else launch_threaded(dim3(G, 1, 1), CG_THREADS, [&] { k_cg_phaseB<false>(a, it, counter); });
+    launch_threaded(dim3(1, 1, 1), 32, [&] { k_cg_update(scal, it, maxiter); });
+    if (scal[S_DONE] != 0.0) break;
+  }
+  launch_threaded(dim3(1, 1, 1), 32, [&] { k_cg_finish(scal, maxiter); });
+}
+int emu_cg_ntiles(int nx, int ny, int G, int rows_min_per_warp) {
+  const int nstrips = (nx + STRIP - 1) / STRIP;
+  int wx = 1;
+  while (wx * 2 <= CG_WARPS && wx * 2 <= nstrips) wx *= 2;
+  const int wy = CG_WARPS / wx, nchunks = (nstrips + wx - 1) / wx;
+  const int rows_min = rows_min_per_warp * wy;
+  const int max_bands = ny / rows_min > 1 ? ny / rows_min : 1;
+  const int want = G / nchunks > 1 ? G / nchunks : 1;
+  return nchunks * (want < max_bands ? want : max_bands);
+}
+
 }  // extern "C"

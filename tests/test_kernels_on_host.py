@@ -65,6 +65,7 @@ def emu(tmp_path_factory):
     lib.emu_divc_stats.argtypes = [i, i, dp, dp, d, d, i, dp, dp]
     lib.emu_cg_generic.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     lib.emu_cg_persistent.argtypes = [i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp]
+    lib.emu_cg_split.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp, dp]
     return lib
 
 
@@ -395,3 +396,35 @@ def test_register_window_cg_kernel_vs_oracle(emu, ny, nx, unit, jacobi, maxiter)
         assert np.linalg.norm(x.ravel() - xo) <= 1e-10 * np.linalg.norm(xo)
     else:
         assert np.linalg.norm(x.ravel() - xo) <= 1e-8 * np.linalg.norm(xo)
+
+
+@pytest.mark.parametrize("ny,nx,G,unit,maxiter,tiles", [
+    (70, 17, 2, True, 6, 2),          # one partial strip, two bands of 35 rows
+    (40, 200, 3, False, 6, 3),        # wall + partial strips, three bands
+    (16, 577, 4, True, 5, 4),         # two column chunks x two bands, four CTAs
+    (34, 66, 2, True, 200, 2),        # runs to convergence: the device-side done flag stops the sequence
+    (12, 20, 3, True, 4, 1),          # more CTAs than tiles: idle CTAs take part in the folds
+])
+def test_split_phase_cg_kernels_vs_oracle(emu, ny, nx, G, unit, maxiter, tiles):
+    """k_cg_begin / phaseA / phaseB / update / finish -- the sequence used between NCCL calls on multi-GPU slabs
+    without peer memory -- for one rank on several CTAs (several row bands per chunk) against scipy's recurrence."""
+    assert emu.emu_cg_ntiles(nx, ny, G, 4) == tiles
+    rng = np.random.default_rng(ny * 1013 + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.5, 0.25)
+    b = rng.standard_normal((ny, nx))
+    b -= b.mean()
+    b[0, 0] = 0.0
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)
+    bb, x, r, p0, p1 = dev.put(b), dev.put(), dev.put(), dev.put(), dev.put()
+    emu.emu_rhs2(nx, ny, ptr(bb), ptr(x), ptr(r), 0, 0, invd, ptr(S.scratch), ptr(S.scal))
+    part = np.zeros(emu.emu_cg_part_doubles())
+    tol = 1e-10 if maxiter < 100 else 0.3
+    emu.emu_cg_split(nx, ny, G, ptr(bb), ptr(x), ptr(r), ptr(p0), ptr(p1), dx, dy, invd, tol, maxiter, 4, ptr(part),
+                     ptr(S.scal), ptr(S.scratch))
+    A = lambda z: orc.neg_laplacian_pinned(z, nx, ny, dx, dy)        # noqa: E731
+    xo, io, to = orc.pcg(A, b.ravel().copy(), tol, maxiter, orc.jacobi_inverse_diagonal(nx, ny, dx, dy))
+    assert int(S["S_INFO"]) == io and abs(int(S["S_ITERS"]) - to) <= 1
+    got = dev.get(x).ravel()
+    assert np.isfinite(got).all()
+    assert np.linalg.norm(got - xo) <= (1e-10 if int(S["S_ITERS"]) == to else 1e-6) * np.linalg.norm(xo)
