@@ -103,6 +103,19 @@ dim3 simple_grid(const Slab& s) {
 
 extern "C" {
 
+// Can this machine run `n` OS threads at once?  (The threaded emulation needs one per CUDA thread of a block.)
+int emu_thread_probe(int n) {
+  std::vector<std::thread> pool;
+  bool ok = true;
+  try {
+    for (int k = 0; k < n; ++k) pool.emplace_back([] {});
+  } catch (...) {
+    ok = false;
+  }
+  for (auto& th : pool) th.join();
+  return ok ? 1 : 0;
+}
+
 int emu_pitch(int nx) { return slab_of(nx, 1).pitch; }
 int emu_halo(void) { return HALO; }
 
