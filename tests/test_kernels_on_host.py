@@ -430,3 +430,36 @@ def test_split_phase_cg_kernels_vs_oracle(emu, ny, nx, G, unit, maxiter, tiles):
     got = dev.get(x).ravel()
     assert np.isfinite(got).all()
     assert np.linalg.norm(got - xo) <= (1e-10 if int(S["S_ITERS"]) == to else 1e-6) * np.linalg.norm(xo)
+
+
+@pytest.mark.parametrize("tag", ["3x3_quick", "3x3_upwind", "3x5_upwind", "5x4_quick"])
+def test_smallest_odd_width_cavities_from_the_cuda_sources_vs_reference_golden(emu, golden, tag):
+    """The odd-width cases of tests/golden/tiny.npz (trajectories written by the unmodified reference), stepped by
+    the kernels in the order of pf_step with the register-window CG kernel -- the one the library picks for them."""
+    from conftest import tiny_cfg
+    cfg = tiny_cfg(tag)
+    nx, ny = cfg.nx, cfg.ny
+    g = {k.split("/", 1)[1]: v for k, v in golden["tiny"].items() if k.startswith(tag + "/")}
+    scheme = QUICK if cfg.advection_scheme == "quick" else UPWIND
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    u, v, uo, vo = dev.put(), dev.put(), dev.put(), dev.put()
+    b, x, r, p, q = dev.put(), dev.put(), dev.put(), dev.put(), dev.put()
+    part = np.zeros(emu.emu_cg_part_doubles())
+    center = np.zeros(ny)
+    for it in range(len(g["true_iters"])):
+        dt = float(g["scalars"][it, 0])                     # the reference's own dt sequence (host logic, not kernels)
+        emu.emu_predict(scheme, nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), dt, 1.0, 1.0)
+        u, uo, v, vo = uo, u, vo, v
+        emu.emu_rhs1(nx, ny, ptr(u), ptr(v), ptr(b), max(dt, 1e-14), 1.0, 1.0, ptr(S.scratch), ptr(S.scal))
+        emu.emu_rhs2(nx, ny, ptr(b), ptr(x), ptr(r), 1, 1, 0.25, ptr(S.scratch), ptr(S.scal))
+        emu.emu_cg_persistent(nx, ny, ptr(b), ptr(x), ptr(r), ptr(p), ptr(q), 1.0, 1.0, 0.25, 1e-10, 300, 4, ptr(part),
+                              ptr(S.scal))
+        assert abs(int(S["S_ITERS"]) - int(g["true_iters"][it])) <= 1 and int(S["S_INFO"]) == 0, (tag, it)
+        emu.emu_resid(nx, ny, ptr(b), ptr(x), 1.0, 1.0, ptr(S.scratch), ptr(S.scal))
+        emu.emu_correct(nx, ny, ptr(x), ptr(u), ptr(v), dt, 1.0, 1.0, S["S_X0"])
+        emu.emu_lid(nx, ny, ptr(u), 1.0)
+        emu.emu_post(nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), ptr(x), ptr(center), ptr(S.scratch), ptr(S.scal))
+        assert close(S["S_DIVC_SUMSQ"] ** 0.5 / (nx * ny), float(g["scalars"][it, 4]), 1e-7), (tag, it)      # continuity
+    for name, buf in (("u", u), ("v", v), ("p", x)):
+        a, want = dev.get(buf), g[name][1:-1, 1:-1]
+        assert np.linalg.norm(a - want) <= 1e-9 * (np.linalg.norm(want) or 1.0), (tag, name)
