@@ -29,26 +29,34 @@ typedef void* cudaStream_t;
 extern thread_local uint3 threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
 
+#define __align__(n)
+
 namespace emu {
 constexpr int MAX_THREADS = 512;
-struct Team {                       // the block currently executing with one OS thread per CUDA thread
+struct Team {                       // one block executing with one OS thread per CUDA thread
   bool threaded = false;
   pthread_barrier_t block;
   pthread_barrier_t warp[MAX_THREADS / 32];
   double xchg[MAX_THREADS];
+  double* dyn = nullptr;            // dynamic shared memory of the block (kernels launched with several blocks at once)
+  double small[4][128];             // its small __shared__ arrays
 };
-extern Team team;
-inline void block_sync() { if (team.threaded) pthread_barrier_wait(&team.block); }
-inline void grid_sync() { block_sync(); }          // cooperative kernels are emulated on a grid of one block
+extern Team team;                   // the block of a one-block-at-a-time launch
+extern thread_local Team* mine;     // the block this OS thread belongs to
+inline void block_sync() { if (mine->threaded) pthread_barrier_wait(&mine->block); }
+inline void grid_sync() { block_sync(); }          // cg::grid_group: only used on grids of one block here
 inline double shuffle(double v, int src_lane) {
-  if (!team.threaded) return v;
+  Team& t_ = *mine;
+  if (!t_.threaded) return v;
   const int t = (int)threadIdx.x, w = t >> 5;
-  team.xchg[t] = v;
-  pthread_barrier_wait(&team.warp[w]);
-  const double r = team.xchg[(w << 5) | (src_lane & 31)];
-  pthread_barrier_wait(&team.warp[w]);
+  t_.xchg[t] = v;
+  pthread_barrier_wait(&t_.warp[w]);
+  const double r = t_.xchg[(w << 5) | (src_lane & 31)];
+  pthread_barrier_wait(&t_.warp[w]);
   return r;
 }
+inline double* dyn_shared() { return mine->dyn; }
+inline double* blk_shared(int k) { return mine->small[k]; }
 }  // namespace emu
 
 static inline void __syncthreads() { emu::block_sync(); }
@@ -81,6 +89,6 @@ static inline unsigned long long atomicMax(unsigned long long* p, unsigned long 
 static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) {
   return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST);
 }
-static inline long long clock64() { return 0; }
+long long clock64();                                 // SM clock stand-in: nanoseconds x 2 (emu_kernels.cpp)
 static inline double __longlong_as_double(long long v) { double d; __builtin_memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; __builtin_memcpy(&v, &d, 8); return v; }

@@ -16,8 +16,10 @@ one block) run with ONE OS THREAD PER CUDA THREAD -- ``__syncthreads`` is a barr
 per-warp exchange buffer, atomics are atomics -- so the "last block folds the partials" machinery and the whole CG
 recurrence execute as written.  Chained in the order of ``pf_step`` they make a complete projection step from the
 CUDA sources on the host, compared with the oracle.  The register-window production CG kernel (``k_cg_persistent``)
-runs the same way on one CTA.  The TMA-fed and shared-memory-resident CG kernels and the multi-GPU variants (mbarrier /
-bulk-copy / packet PTX, several co-resident CTAs) are NOT emulated; their parity is the ``-m gpu`` suite's business.
+runs the same way on one CTA, the split-phase chain of the NCCL fallback on several CTAs one after the other, and the
+shared-memory-resident kernel (``k_cg_small``) with ALL its CTAs at once, exchanging their tagged packets for real.
+The TMA-fed kernels and the multi-GPU peer-memory variants (mbarrier / bulk-copy PTX, NVLink stores) are NOT
+emulated; their parity is the ``-m gpu`` suite's business.
 """
 import ctypes as C
 import os
@@ -34,10 +36,58 @@ LEGACY_TAGS = ["8x8", "16x12", "5x9", "2x2", "3x3", "2x7", "9x2", "33x17", "70x6
 UPWIND, QUICK, NONE = 0, 1, 2
 
 
+# Host stand-ins for the three PTX helpers k_cg_small uses beyond pf_common.cuh (32-byte packets, relaxed u64 load):
+# spliced into a GENERATED copy of pf_cg_small.cuh, together with per-block storage for its shared memory, so that
+# several of its CTAs can run at once in one process.  The product source is not touched; if one of the patterns
+# below no longer occurs exactly once the generation fails loudly.
+SMALL_HOST_PACKETS = '''
+#include <sched.h>
+#include <string.h>
+namespace pf {
+static pthread_mutex_t emu_packet_mutex = PTHREAD_MUTEX_INITIALIZER;     // a packet is complete or absent
+inline Packet emu_ld_packet(const void* p) {
+  sched_yield();                                   // pollers give way to the CTAs they wait for
+  Packet k;
+  pthread_mutex_lock(&emu_packet_mutex);
+  memcpy(&k, p, sizeof(k));
+  pthread_mutex_unlock(&emu_packet_mutex);
+  return k;
+}
+inline void emu_st_packet(void* p, unsigned long long e, double v0, double v1, double v2) {
+  Packet k;
+  k.epoch = e; k.v[0] = v0; k.v[1] = v1; k.v[2] = v2;
+  pthread_mutex_lock(&emu_packet_mutex);
+  memcpy(p, &k, sizeof(k));
+  pthread_mutex_unlock(&emu_packet_mutex);
+}
+inline unsigned long long emu_ld_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+}  // namespace pf
+#define ld_packet_gpu emu_ld_packet
+#define st_packet_gpu emu_st_packet
+#define ld_relaxed_u64 emu_ld_u64
+'''
+
+
+def generate_small_kernel_copy(dest_dir):
+    src = open(os.path.join(ROOT, "pyflow-solver_b200", "csrc", "pf_cg_small.cuh")).read()
+    for old, new in (
+            ('#include "pf_cg.cuh"', '#include "pf_cg.cuh"\n' + SMALL_HOST_PACKETS),
+            ("extern __shared__ __align__(16) double smem_d[];", "double* smem_d = emu::dyn_shared();"),
+            ("__shared__ double sm[3 * 32];", "double* sm = emu::blk_shared(0);"),
+            ("__shared__ double s_res[8];", "double* s_res = emu::blk_shared(1);")):
+        assert src.count(old) == 1, f"pf_cg_small.cuh changed: {old!r} occurs {src.count(old)} times"
+        src = src.replace(old, new)
+    with open(os.path.join(dest_dir, "pf_cg_small_emu.cuh"), "w") as fh:
+        fh.write(src)
+
+
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("hostemu") / "emu_kernels.so")
-    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-pthread", "-fPIC", "-shared",
+    build = str(tmp_path_factory.mktemp("hostemu"))
+    out = os.path.join(build, "emu_kernels.so")
+    generate_small_kernel_copy(build)
+    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-DPF_EMU_WITH_SMALL", "-pthread",
+           "-fPIC", "-shared", "-I", build,
            "-I", os.path.join(ROOT, "tests", "hostemu"), "-I", os.path.join(ROOT, "pyflow-solver_b200", "csrc"),
            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "hostemu", "emu_kernels.cpp"), "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -66,6 +116,7 @@ def emu(tmp_path_factory):
     lib.emu_cg_generic.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     lib.emu_cg_persistent.argtypes = [i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp]
     lib.emu_cg_split.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp, dp]
+    lib.emu_cg_small.argtypes = [i, i, i, dp, dp, dp, dp, dp, C.POINTER(C.c_ulonglong), d, d, d, d, i]
     return lib
 
 
@@ -460,6 +511,89 @@ def test_smallest_odd_width_cavities_from_the_cuda_sources_vs_reference_golden(e
         emu.emu_lid(nx, ny, ptr(u), 1.0)
         emu.emu_post(nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), ptr(x), ptr(center), ptr(S.scratch), ptr(S.scal))
         assert close(S["S_DIVC_SUMSQ"] ** 0.5 / (nx * ny), float(g["scalars"][it, 4]), 1e-7), (tag, it)      # continuity
+    for name, buf in (("u", u), ("v", v), ("p", x)):
+        a, want = dev.get(buf), g[name][1:-1, 1:-1]
+        assert np.linalg.norm(a - want) <= 1e-9 * (np.linalg.norm(want) or 1.0), (tag, name)
+
+
+# ===================================================================================================================
+# the shared-memory-resident CG kernel (k_cg_small): ALL its CTAs at once, talking through tagged packets
+# ===================================================================================================================
+class SmallSolver:
+    """Persistent state of k_cg_small between solves on one grid: packet slots and the barrier epoch."""
+
+    def __init__(self, emu, ny, nx, rows):
+        if not emu.emu_thread_probe(512 * ((ny + rows - 1) // rows)):
+            pytest.skip("this machine cannot run one OS thread per CUDA thread of every CTA at once")
+        self.emu, self.ny, self.nx, self.rows = emu, ny, nx, rows
+        G = (ny + rows - 1) // rows
+        self.rhalo = np.zeros(G * 2 * emu.emu_small_row_packets(nx) * 4)
+        self.part = np.zeros(2 * G * 4)
+        self.sync = np.zeros(2, dtype=np.uint64)             # epoch (persisted), error flag
+
+    def solve(self, b_dev, x_dev, scal, dx, dy, invd, tol, maxiter):
+        self.sync[1] = 0
+        self.emu.emu_cg_small(self.nx, self.ny, self.rows, ptr(b_dev), ptr(x_dev), ptr(self.rhalo), ptr(self.part),
+                              ptr(scal), self.sync.ctypes.data_as(C.POINTER(C.c_ulonglong)), dx, dy, invd, tol, maxiter)
+        assert self.sync[1] == 0, "a bounded wait inside k_cg_small timed out"
+
+
+@pytest.mark.parametrize("ny,nx,rows,unit,jacobi,maxiter", [
+    (2, 2, 1, True, True, 50), (3, 4, 1, True, True, 50), (5, 2, 1, True, True, 50), (2, 6, 1, True, True, 50),
+    (4, 6, 1, False, True, 300),          # four CTAs of one row, non-unit spacing, runs to convergence
+    (7, 10, 3, True, False, 12),          # bands of 3, 3 and 1 rows, no preconditioner, truncated early
+])
+def test_shared_memory_cg_kernel_with_concurrent_ctas_vs_oracle(emu, ny, nx, rows, unit, jacobi, maxiter):
+    """The real k_cg_small source, one OS thread per CUDA thread of EVERY CTA at once, in the configuration the
+    library uses for small grids (bands of ceil(ny / #SMs) rows): halo rows of p recomputed from exchanged rows of r,
+    both reductions and the rows travelling as tagged packets, two solves in a row on the same packet slots."""
+    rng = np.random.default_rng(ny * 1019 + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.5, 0.25)
+    invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2) if jacobi else 1.0
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    solver = SmallSolver(emu, ny, nx, rows)
+    A = lambda z: orc.neg_laplacian_pinned(z, nx, ny, dx, dy)        # noqa: E731
+    inv = orc.jacobi_inverse_diagonal(nx, ny, dx, dy) if jacobi else None
+    for _repeat in range(2):                                          # the epoch carries over to the second solve
+        b = rng.standard_normal((ny, nx))
+        b -= b.mean()
+        b[0, 0] = 0.0
+        bb, x, r = dev.put(b), dev.put(), dev.put()
+        emu.emu_rhs2(nx, ny, ptr(bb), ptr(x), ptr(r), 0, 0, invd, ptr(S.scratch), ptr(S.scal))
+        solver.solve(bb, x, S.scal, dx, dy, invd, 1e-10, maxiter)
+        xo, io, to = orc.pcg(A, b.ravel().copy(), 1e-10, maxiter, inv)
+        assert int(S["S_INFO"]) == io and abs(int(S["S_ITERS"]) - to) <= 1
+        got = dev.get(x).ravel()
+        assert np.linalg.norm(got - xo) <= 1e-9 * np.linalg.norm(xo)      # the parity bar of the project
+    assert int(solver.sync[0]) > 0
+
+
+@pytest.mark.parametrize("tag", ["2x2_quick", "4x3_quick", "2x5_upwind", "6x2_quick"])
+def test_smallest_even_width_cavities_from_the_cuda_sources_vs_reference_golden(emu, golden, tag):
+    """The even-width cases of tests/golden/tiny.npz, stepped by the kernels in the order of pf_step with k_cg_small
+    on one-row bands (one CTA per grid row, as on the GPU)."""
+    from conftest import tiny_cfg
+    cfg = tiny_cfg(tag)
+    nx, ny = cfg.nx, cfg.ny
+    g = {k.split("/", 1)[1]: v for k, v in golden["tiny"].items() if k.startswith(tag + "/")}
+    scheme = QUICK if cfg.advection_scheme == "quick" else UPWIND
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    solver = SmallSolver(emu, ny, nx, 1)
+    u, v, uo, vo = dev.put(), dev.put(), dev.put(), dev.put()
+    b, x, r = dev.put(), dev.put(), dev.put()
+    center = np.zeros(ny)
+    for it in range(len(g["true_iters"])):
+        dt = float(g["scalars"][it, 0])
+        emu.emu_predict(scheme, nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), dt, 1.0, 1.0)
+        u, uo, v, vo = uo, u, vo, v
+        emu.emu_rhs1(nx, ny, ptr(u), ptr(v), ptr(b), max(dt, 1e-14), 1.0, 1.0, ptr(S.scratch), ptr(S.scal))
+        emu.emu_rhs2(nx, ny, ptr(b), ptr(x), ptr(r), 1, 1, 0.25, ptr(S.scratch), ptr(S.scal))
+        solver.solve(b, x, S.scal, 1.0, 1.0, 0.25, 1e-10, 300)
+        assert abs(int(S["S_ITERS"]) - int(g["true_iters"][it])) <= 1 and int(S["S_INFO"]) == 0, (tag, it)
+        emu.emu_resid(nx, ny, ptr(b), ptr(x), 1.0, 1.0, ptr(S.scratch), ptr(S.scal))
+        emu.emu_correct(nx, ny, ptr(x), ptr(u), ptr(v), dt, 1.0, 1.0, S["S_X0"])
+        emu.emu_lid(nx, ny, ptr(u), 1.0)
+        emu.emu_post(nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), ptr(x), ptr(center), ptr(S.scratch), ptr(S.scal))
     for name, buf in (("u", u), ("v", v), ("p", x)):
         a, want = dev.get(buf), g[name][1:-1, 1:-1]
         assert np.linalg.norm(a - want) <= 1e-9 * (np.linalg.norm(want) or 1.0), (tag, name)
