@@ -32,7 +32,7 @@ extern thread_local dim3 blockDim, gridDim;
 #define __align__(n)
 
 namespace emu {
-constexpr int MAX_THREADS = 512;
+constexpr int MAX_THREADS = 1024;
 struct Team {                       // one block executing with one OS thread per CUDA thread
   bool threaded = false;
   pthread_barrier_t block;
@@ -72,6 +72,21 @@ static inline double __shfl_down_sync(unsigned, double v, int d) {
   const int lane = (int)threadIdx.x & 31;
   return emu::shuffle(v, lane + d > 31 ? lane : lane + d);
 }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+  if (emu::mine->threaded) pthread_barrier_wait(&emu::mine->warp[(int)threadIdx.x >> 5]);
+}
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src_lane) {      // 4- and 8-byte integer types
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  double carrier = 0.0;
+  __builtin_memcpy(&carrier, &v, sizeof(T));
+  carrier = emu::shuffle(carrier, src_lane);
+  T out;
+  __builtin_memcpy(&out, &carrier, sizeof(T));
+  return out;
+}
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
   return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);

@@ -18,8 +18,9 @@ recurrence execute as written.  Chained in the order of ``pf_step`` they make a 
 CUDA sources on the host, compared with the oracle.  The register-window production CG kernel (``k_cg_persistent``)
 runs the same way on one CTA, the split-phase chain of the NCCL fallback on several CTAs one after the other, and the
 shared-memory-resident kernel (``k_cg_small``) with ALL its CTAs at once, exchanging their tagged packets for real.
-The TMA-fed kernels and the multi-GPU peer-memory variants (mbarrier / bulk-copy PTX, NVLink stores) are NOT
-emulated; their parity is the ``-m gpu`` suite's business.
+The TMA-fed production kernel (``k_cg_tmad``, single-GPU instantiation) runs on one CTA of 16 compute warps + the
+producer warp, its mbarriers and bulk copies replaced by host stand-ins in a generated copy.  NOT emulated: the
+multi-GPU peer-memory instantiations (NVLink stores into other processes' memory) and anything about timing.
 """
 import ctypes as C
 import os
@@ -81,12 +82,120 @@ def generate_small_kernel_copy(dest_dir):
         fh.write(src)
 
 
+# The TMA-fed kernels: the block of mbarrier / bulk-copy PTX helpers at the top of pf_cg_tma.cuh is replaced, in a
+# GENERATED copy, by host stand-ins -- an mbarrier is its 64-bit word of "shared memory" holding {phase, pending
+# arrivals, expected count, outstanding bytes}; arrive / expect_tx / complete_tx update it under a mutex and flip the
+# phase when arrivals and bytes are both down to zero; try_wait(parity) is true once the phase of that parity has
+# completed; a bulk copy is a memcpy followed by complete_tx.  Everything else (ring, tickets, tile partials) is the
+# product source, untouched.
+TMA_HOST_MBAR = '''// ---- mbarrier / bulk-copy PTX: HOST STAND-INS (generated copy, tests only) --------
+struct EmuMbar { uint32_t phase : 1, pending : 15, count : 15; int32_t tx; };
+static_assert(sizeof(EmuMbar) == 8, "an mbarrier is one 64-bit word of shared memory");
+static pthread_mutex_t emu_mbar_mutex = PTHREAD_MUTEX_INITIALIZER;
+inline void emu_mbar_update(uint64_t* bar, int arrive, int tx_delta) {
+  pthread_mutex_lock(&emu_mbar_mutex);
+  EmuMbar s;
+  memcpy(&s, bar, 8);
+  s.tx += tx_delta;
+  s.pending -= (uint32_t)arrive;
+  if (s.pending == 0 && s.tx == 0) { s.phase ^= 1u; s.pending = s.count; }      // the phase completes
+  memcpy(bar, &s, 8);
+  pthread_mutex_unlock(&emu_mbar_mutex);
+}
+inline uint32_t smem_u32(const void* p) { return (uint32_t)(size_t)p; }
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+  EmuMbar s;
+  s.phase = 0; s.pending = count; s.count = count; s.tx = 0;
+  memcpy(bar, &s, 8);
+}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { emu_mbar_update(bar, 1, (int)bytes); }
+inline void mbar_arrive(uint64_t* bar) { emu_mbar_update(bar, 1, 0); }
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  pthread_mutex_lock(&emu_mbar_mutex);
+  EmuMbar s;
+  memcpy(&s, bar, 8);
+  pthread_mutex_unlock(&emu_mbar_mutex);
+  const bool done = s.phase != parity;              // the phase with this parity has completed
+  if (!done) sched_yield();
+  return done;
+}
+inline bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 40000000000LL) return false;
+  }
+  return true;
+}
+inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  memcpy(dst_smem, src_gmem, bytes);                // the copy engine: data lands, then complete_tx
+  emu_mbar_update(bar, 0, -(int)bytes);
+}
+inline void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t) {
+  bulk_g2s(dst_smem, src_gmem, bytes, bar);
+}
+
+'''
+
+TMA_HOST_PACKETS = '''
+#include <sched.h>
+#include <string.h>
+// ---- host stand-ins for the packet / acquire / timer PTX of pf_cg.cuh (generated copy, tests only) ----
+namespace pf {
+static pthread_mutex_t emu_tma_packet_mutex = PTHREAD_MUTEX_INITIALIZER;
+inline Packet emu_tma_ld_packet(const void* p) {
+  sched_yield();
+  Packet k;
+  pthread_mutex_lock(&emu_tma_packet_mutex);
+  memcpy(&k, p, sizeof(k));
+  pthread_mutex_unlock(&emu_tma_packet_mutex);
+  return k;
+}
+inline void emu_tma_st_packet(void* p, unsigned long long e, double v0, double v1, double v2) {
+  Packet k;
+  k.epoch = e; k.v[0] = v0; k.v[1] = v1; k.v[2] = v2;
+  pthread_mutex_lock(&emu_tma_packet_mutex);
+  memcpy(p, &k, sizeof(k));
+  pthread_mutex_unlock(&emu_tma_packet_mutex);
+}
+inline unsigned long long emu_tma_ld_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+inline unsigned long long emu_tma_gtime() { return (unsigned long long)clock64(); }
+}  // namespace pf
+#define ld_packet_sys emu_tma_ld_packet
+#define st_packet_sys emu_tma_st_packet
+#define ld_acquire_sys emu_tma_ld_u64
+#define gtime emu_tma_gtime
+#ifndef ld_relaxed_u64
+#define ld_relaxed_u64 emu_tma_ld_u64
+#endif
+'''
+
+
+def generate_tma_kernel_copy(dest_dir):
+    src = open(os.path.join(ROOT, "pyflow-solver_b200", "csrc", "pf_cg_tma.cuh")).read()
+    begin, end = "// ---- mbarrier / bulk-copy PTX", "struct TmaTile {"
+    assert src.count(begin) == 1 and src.count(end) == 1, "pf_cg_tma.cuh changed: PTX helper block not found"
+    src = src[:src.index(begin)] + TMA_HOST_MBAR + src[src.index(end):]
+    for old, new, times in (
+            ('asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");', "__threadfence();", 2),
+            ("extern __shared__ __align__(128) unsigned char smem_raw[];",
+             "unsigned char* smem_raw = (unsigned char*)emu::dyn_shared();", 2),
+            ('asm volatile("mov.u32 %0, %smid;" : "=r"(smid));', "smid = 0;", 2),
+            ('#include "pf_cg.cuh"', '#include "pf_cg.cuh"\n' + TMA_HOST_PACKETS, 1)):
+        assert src.count(old) == times, f"pf_cg_tma.cuh changed: {old!r} occurs {src.count(old)} times"
+        src = src.replace(old, new)
+    with open(os.path.join(dest_dir, "pf_cg_tma_emu.cuh"), "w") as fh:
+        fh.write(src)
+
+
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     build = str(tmp_path_factory.mktemp("hostemu"))
     out = os.path.join(build, "emu_kernels.so")
     generate_small_kernel_copy(build)
-    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-DPF_EMU_WITH_SMALL", "-pthread",
+    generate_tma_kernel_copy(build)
+    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-DPF_EMU_WITH_SMALL",
+           "-DPF_EMU_WITH_TMA", "-pthread",
            "-fPIC", "-shared", "-I", build,
            "-I", os.path.join(ROOT, "tests", "hostemu"), "-I", os.path.join(ROOT, "pyflow-solver_b200", "csrc"),
            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "hostemu", "emu_kernels.cpp"), "-o", out]
@@ -117,6 +226,7 @@ def emu(tmp_path_factory):
     lib.emu_cg_persistent.argtypes = [i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp]
     lib.emu_cg_split.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp, dp]
     lib.emu_cg_small.argtypes = [i, i, i, dp, dp, dp, dp, dp, C.POINTER(C.c_ulonglong), d, d, d, d, i]
+    lib.emu_cg_tmad.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp, C.POINTER(C.c_ulonglong)]
     return lib
 
 
@@ -597,3 +707,86 @@ def test_smallest_even_width_cavities_from_the_cuda_sources_vs_reference_golden(
     for name, buf in (("u", u), ("v", v), ("p", x)):
         a, want = dev.get(buf), g[name][1:-1, 1:-1]
         assert np.linalg.norm(a - want) <= 1e-9 * (np.linalg.norm(want) or 1.0), (tag, name)
+
+
+# ===================================================================================================================
+# the TMA-fed, dynamically scheduled CG kernel (k_cg_tmad): the production kernel of the 4096^2 ... 16384^2 configs
+# ===================================================================================================================
+def _tmad_solve(emu, dev, S, sync, b, dx, dy, invd, tol, maxiter, tile_rows):
+    ny, nx = b.shape
+    bb, x, r, p0, p1 = dev.put(b), dev.put(), dev.put(), dev.put(), dev.put()
+    emu.emu_rhs2(nx, ny, ptr(bb), ptr(x), ptr(r), 0, 0, invd, ptr(S.scratch), ptr(S.scal))
+    part = np.zeros(emu.emu_cg_part_doubles())
+    emu.emu_cg_tmad(nx, ny, tile_rows, ptr(bb), ptr(x), ptr(r), ptr(p0), ptr(p1), dx, dy, invd, tol, maxiter, ptr(part),
+                    ptr(S.scal), sync.ctypes.data_as(C.POINTER(C.c_ulonglong)))
+    assert sync[3] == 0, "a bounded wait inside k_cg_tmad timed out"
+    return dev.get(x)
+
+
+@pytest.mark.parametrize("ny,nx,tile_rows,unit,jacobi,maxiter", [
+    (6, 1024, 4, True, True, 5),           # two tiles of 4 and 2 rows, one column chunk
+    (9, 1024, 4, False, True, 5),          # three tiles, non-unit spacing
+    (5, 2048, 4, True, False, 4),          # two column chunks x two bands = four tiles, no preconditioner
+    (33, 1024, 16, True, True, 4),         # the library's default 16-row tiles: 16 + 16 + 1 rows
+    (3, 1024, 4, True, True, 300),         # runs to convergence at a loose tolerance
+])
+def test_tma_fed_cg_kernel_vs_oracle(emu, ny, nx, tile_rows, unit, jacobi, maxiter):
+    """k_cg_tmad<unit, single GPU> on one CTA: producer thread, 8-stage ring, ticket-drawn tiles (ascending in phase
+    A, descending in phase B), per-tile partials -- against scipy's recurrence; two solves in a row, so the ticket
+    base persisted by the first launch is used by the second."""
+    if not emu.emu_thread_probe(544):
+        pytest.skip("this machine cannot run 544 OS threads at once")
+    rng = np.random.default_rng(ny * 1021 + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.5, 0.25)
+    invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2) if jacobi else 1.0
+    tol = 1e-10 if maxiter < 100 else 0.3
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    sync = np.zeros(16, dtype=np.uint64)
+    A = lambda z: orc.neg_laplacian_pinned(z, nx, ny, dx, dy)        # noqa: E731
+    inv = orc.jacobi_inverse_diagonal(nx, ny, dx, dy) if jacobi else None
+    for _repeat in range(2):
+        b = rng.standard_normal((ny, nx))
+        b -= b.mean()
+        b[0, 0] = 0.0
+        x = _tmad_solve(emu, dev, S, sync, b, dx, dy, invd, tol, maxiter, tile_rows)
+        xo, io, to = orc.pcg(A, b.ravel().copy(), tol, maxiter, inv)
+        assert int(S["S_INFO"]) == io and abs(int(S["S_ITERS"]) - to) <= 1
+        assert np.linalg.norm(x.ravel() - xo) <= (1e-10 if int(S["S_ITERS"]) == to else 1e-6) * np.linalg.norm(xo)
+    assert int(sync[5]) == int(sync[4]) > 0                          # every ticket drawn was accounted for
+    zero = _tmad_solve(emu, dev, S, sync, np.zeros((ny, nx)), dx, dy, invd, tol, 10, tile_rows)
+    assert int(S["S_INFO"]) == 0 and int(S["S_ITERS"]) == 0 and not zero.any()
+
+
+def test_whole_projection_steps_with_the_tma_fed_kernel_vs_oracle(emu):
+    """A 1024 x 6 driven cavity, three steps in the order of pf_step with k_cg_tmad for the pressure solve."""
+    if not emu.emu_thread_probe(544):
+        pytest.skip("this machine cannot run 544 OS threads at once")
+    from types import SimpleNamespace
+    nx, ny = 1024, 6
+    cfg = SimpleNamespace(nx=nx, ny=ny, Re=1000.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
+                          lin_maxiter=12, advection_scheme="quick", disable_advection=False, diagnostics=False)
+    ost = orc.allocate_state(nx, ny)
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    sync = np.zeros(16, dtype=np.uint64)
+    u, v, uo, vo = dev.put(), dev.put(), dev.put(), dev.put()
+    b, x, r, p0, p1 = dev.put(), dev.put(), dev.put(), dev.put(), dev.put()
+    part = np.zeros(emu.emu_cg_part_doubles())
+    center = np.zeros(ny)
+    for it in range(3):
+        _, ores, od = orc.step(cfg, ost, it)
+        dt = od["dt"]
+        emu.emu_predict(QUICK, nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), dt, 1.0, 1.0)
+        u, uo, v, vo = uo, u, vo, v
+        emu.emu_rhs1(nx, ny, ptr(u), ptr(v), ptr(b), max(dt, 1e-14), 1.0, 1.0, ptr(S.scratch), ptr(S.scal))
+        emu.emu_rhs2(nx, ny, ptr(b), ptr(x), ptr(r), 1, 1, 0.25, ptr(S.scratch), ptr(S.scal))
+        emu.emu_cg_tmad(nx, ny, 4, ptr(b), ptr(x), ptr(r), ptr(p0), ptr(p1), 1.0, 1.0, 0.25, 1e-10, 12, ptr(part),
+                        ptr(S.scal), sync.ctypes.data_as(C.POINTER(C.c_ulonglong)))
+        assert int(S["S_ITERS"]) == od["true_iterations"] and sync[3] == 0
+        emu.emu_resid(nx, ny, ptr(b), ptr(x), 1.0, 1.0, ptr(S.scratch), ptr(S.scal))
+        emu.emu_correct(nx, ny, ptr(x), ptr(u), ptr(v), dt, 1.0, 1.0, S["S_X0"])
+        emu.emu_lid(nx, ny, ptr(u), 1.0)
+        emu.emu_post(nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), ptr(x), ptr(center), ptr(S.scratch), ptr(S.scal))
+        assert close(S["S_DIVC_SUMSQ"] ** 0.5 / (nx * ny), ores["continuity"], 1e-8)
+    for name, buf in (("u", u), ("v", v), ("p", x)):
+        a, want = dev.get(buf), orc.interior(ost.fields[name])
+        assert np.linalg.norm(a - want) <= 1e-9 * (np.linalg.norm(want) or 1.0), name
