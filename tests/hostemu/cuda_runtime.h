@@ -12,6 +12,7 @@
 #include <pthread.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define __device__
 #define __host__
@@ -40,6 +41,8 @@ struct Team {                       // one block executing with one OS thread pe
   double xchg[MAX_THREADS];
   double* dyn = nullptr;            // dynamic shared memory of the block (kernels launched with several blocks at once)
   double small[4][128];             // its small __shared__ arrays
+  void* slots[48] = {nullptr};      // per-block storage of rewritten `__shared__` declarations (see shared_slot)
+  pthread_mutex_t slot_mutex = PTHREAD_MUTEX_INITIALIZER;
 };
 extern Team team;                   // the block of a one-block-at-a-time launch
 extern thread_local Team* mine;     // the block this OS thread belongs to
@@ -54,6 +57,16 @@ inline double shuffle(double v, int src_lane) {
   const double r = t_.xchg[(w << 5) | (src_lane & 31)];
   pthread_barrier_wait(&t_.warp[w]);
   return r;
+}
+// `__shared__ T name[...]` of a generated kernel copy becomes a reference to the block's own zero-initialised storage,
+// so that several blocks (or several ranks' grids) can run at once in one process.
+inline void* shared_slot(int id, size_t bytes) {
+  Team& t = *mine;
+  pthread_mutex_lock(&t.slot_mutex);
+  if (!t.slots[id]) t.slots[id] = calloc(1, bytes < 8 ? 8 : bytes);
+  void* p = t.slots[id];
+  pthread_mutex_unlock(&t.slot_mutex);
+  return p;
 }
 inline double* dyn_shared() { return mine->dyn; }
 inline double* blk_shared(int k) { return mine->small[k]; }
