@@ -203,14 +203,102 @@ def generate_tma_kernel_copy(dest_dir):
         fh.write(src)
 
 
+# The multi-GPU register-window kernel lives in pf_cg.cuh, which every other source includes: its section (from the
+# "multi-GPU persistent variant" banner to the "split-phase variant" banner) is copied into namespace pf::emu_multi,
+# where the PTX helper functions are dropped in favour of host stand-ins of the same names (they shadow the originals),
+# `__shared__` declarations get per-block storage, and the two templates that argument-dependent lookup would otherwise
+# find twice are renamed.
+MULTI_PTX_HELPERS = ["ld_acquire_sys", "st_release_sys", "ld_acquire_gpu", "st_release_gpu", "st_sys_f64", "ld_sys_f64",
+                     "ld_relaxed_u64", "ld_relaxed_sys_u64", "gtime", "ld_packet_gpu", "ld_packet_sys", "st_packet_gpu",
+                     "st_packet_sys"]
+MULTI_HEAD = '''// GENERATED (tests only) from the multi-GPU section of pf_cg.cuh.
+#pragma once
+#include "pf_cg.cuh"
+#include <sched.h>
+#include <string.h>
+namespace pf {
+namespace emu_multi {
+inline unsigned long long ld_acquire_sys(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+inline void st_release_sys(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long ld_acquire_gpu(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+inline void st_release_gpu(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+inline void st_sys_f64(double* p, double v) { *(volatile double*)p = v; }
+inline double ld_sys_f64(const double* p) { return *(const volatile double*)p; }
+inline unsigned long long ld_relaxed_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+inline unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+inline unsigned long long gtime() { return (unsigned long long)clock64(); }
+'''
+MULTI_PACKETS = '''
+static pthread_mutex_t emu_packet_mutex = PTHREAD_MUTEX_INITIALIZER;     // a packet is complete or absent
+inline Packet ld_packet_sys(const void* p) {
+  sched_yield();
+  Packet k;
+  pthread_mutex_lock(&emu_packet_mutex);
+  memcpy(&k, p, sizeof(k));
+  pthread_mutex_unlock(&emu_packet_mutex);
+  return k;
+}
+inline Packet ld_packet_gpu(const void* p) { return ld_packet_sys(p); }
+inline void st_packet_sys(void* p, unsigned long long e, double v0, double v1, double v2) {
+  Packet k;
+  k.epoch = e; k.v[0] = v0; k.v[1] = v1; k.v[2] = v2;
+  pthread_mutex_lock(&emu_packet_mutex);
+  memcpy(p, &k, sizeof(k));
+  pthread_mutex_unlock(&emu_packet_mutex);
+}
+inline void st_packet_gpu(void* p, unsigned long long e, double v0, double v1, double v2) { st_packet_sys(p, e, v0, v1, v2); }
+'''
+
+
+def generate_multi_kernel_copy(dest_dir):
+    import re
+    src = open(os.path.join(ROOT, "pyflow-solver_b200", "csrc", "pf_cg.cuh")).read()
+    begin, end = "// ---- multi-GPU persistent variant", "// ---- split-phase variant"
+    assert src.count(begin) == 1 and src.count(end) == 1, "pf_cg.cuh changed: section banners not found"
+    sec = src[src.index(begin):src.index(end)]
+    for name in MULTI_PTX_HELPERS:                       # drop each PTX helper (brace-matched), keep everything else
+        m = re.search(r"__device__ __forceinline__ [^\n(]*\b%s\(" % name, sec)
+        assert m, f"pf_cg.cuh changed: helper {name} not found"
+        j, depth = sec.index("{", m.end()), 0
+        while True:
+            depth += {"{": 1, "}": -1}.get(sec[j], 0)
+            if depth == 0:
+                break
+            j += 1
+        assert "asm volatile" in sec[m.start():j + 1], name
+        sec = sec[:m.start()] + sec[j + 1:]
+    smid = 'asm volatile("mov.u32 %0, %smid;" : "=r"(smid));'
+    assert sec.count(smid) == 1
+    sec = sec.replace(smid, "smid = 0;")
+    assert "asm volatile" not in sec, "pf_cg.cuh changed: PTX left in the multi-GPU section"
+    m = re.search(r"struct Packet \{.*?\};\n", sec, flags=re.S)
+    assert m
+    sec = sec[:m.end()] + MULTI_PACKETS + sec[m.end():]
+    counter = [19]                                       # ids 1.. are taken by the TMA copy
+
+    def per_block(mm):
+        counter[0] += 1
+        indent, ctype, name, dims, rest = mm.groups()
+        return (f"{indent}auto& {name} = *reinterpret_cast<{ctype}(*){dims}>"
+                f"(emu::shared_slot({counter[0]}, sizeof({ctype}{dims})));{rest}")
+
+    sec = re.sub(r"^(\s*)__shared__\s+([A-Za-z_][\w ]*?)\s+(\w+)((?:\[[^\]]+\])*);(.*)$", per_block, sec, flags=re.M)
+    assert "__shared__" not in sec and counter[0] < 48
+    sec = (sec.replace("trace_slot(", "trace_slot_emu(").replace("grid_exchange<", "grid_exchange_emu<")
+           .replace("bool grid_exchange(", "bool grid_exchange_emu("))
+    with open(os.path.join(dest_dir, "pf_cg_multi_emu.cuh"), "w") as fh:
+        fh.write(MULTI_HEAD + sec + "\n}  // namespace emu_multi\n}  // namespace pf\n")
+
+
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     build = str(tmp_path_factory.mktemp("hostemu"))
     out = os.path.join(build, "emu_kernels.so")
     generate_small_kernel_copy(build)
     generate_tma_kernel_copy(build)
+    generate_multi_kernel_copy(build)
     cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-DPF_EMU_WITH_SMALL",
-           "-DPF_EMU_WITH_TMA", "-pthread",
+           "-DPF_EMU_WITH_TMA", "-DPF_EMU_WITH_MULTI", "-pthread",
            "-fPIC", "-shared", "-I", build,
            "-I", os.path.join(ROOT, "tests", "hostemu"), "-I", os.path.join(ROOT, "pyflow-solver_b200", "csrc"),
            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "hostemu", "emu_kernels.cpp"), "-o", out]
@@ -245,6 +333,7 @@ def emu(tmp_path_factory):
     ppd = C.POINTER(dp)
     lib.emu_cg_tmad_multi.argtypes = [i, i, i, i, ppd, ppd, ppd, ppd, ppd, d, d, d, d, i, ppd, ppd,
                                       C.POINTER(C.POINTER(C.c_ubyte))]
+    lib.emu_cg_persistent_multi.argtypes = lib.emu_cg_tmad_multi.argtypes
     return lib
 
 
@@ -846,7 +935,7 @@ class Ranks:
     def arr(self, bufs):
         return (C.POINTER(C.c_double) * self.R)(*[ptr(a) for a in bufs])
 
-    def solve(self, b, dx, dy, jacobi, tol, maxiter, tile_rows):
+    def solve(self, b, dx, dy, jacobi, tol, maxiter, tile_rows, kernel="tmad"):
         emu, R = self.emu, self.R
         invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2) if jacobi else 1.0
         M = orc.jacobi_inverse_diagonal(self.nx, self.ny, dx, dy).reshape(b.shape) if jacobi else np.ones_like(b)
@@ -857,8 +946,9 @@ class Ranks:
         zeros = np.zeros_like(b)
         p0, p1 = self.slabs(zeros, halo=zeros), self.slabs(zeros, halo=zeros)
         sy = (C.POINTER(C.c_ubyte) * R)(*[s_.ctypes.data_as(C.POINTER(C.c_ubyte)) for s_ in self.syncs])
-        emu.emu_cg_tmad_multi(R, self.nx, self.ny, tile_rows, self.arr(bs), self.arr(xs), self.arr(rs), self.arr(p0),
-                              self.arr(p1), dx, dy, invd, tol, maxiter, self.arr(self.parts), self.arr(self.scals), sy)
+        launch = emu.emu_cg_tmad_multi if kernel == "tmad" else emu.emu_cg_persistent_multi
+        launch(R, self.nx, self.ny, tile_rows, self.arr(bs), self.arr(xs), self.arr(rs), self.arr(p0),
+               self.arr(p1), dx, dy, invd, tol, maxiter, self.arr(self.parts), self.arr(self.scals), sy)
         assert all(int(s_.view(np.uint64)[3]) == 0 for s_ in self.syncs), "a bounded wait timed out"
         info = {int(sc[emu.emu_slot(b"S_INFO")]) for sc in self.scals}
         iters = {int(sc[emu.emu_slot(b"S_ITERS")]) for sc in self.scals}
@@ -894,3 +984,30 @@ def test_multi_gpu_tma_kernel_with_concurrent_ranks_vs_single_domain_oracle(emu,
         assert np.linalg.norm(x.ravel() - xo) <= (1e-10 if iters == to else 1e-6) * np.linalg.norm(xo)
     epochs = {int(s_.view(np.uint64)[2]) for s_ in ranks.syncs}
     assert len(epochs) == 1 and epochs.pop() > 0                       # same number of exchanges on every rank
+
+
+@pytest.mark.parametrize("R,ny,nx,unit,jacobi,maxiter", [
+    (2, 16, 70, True, True, 5), (2, 10, 17, False, True, 6), (3, 12, 130, True, False, 5), (4, 8, 200, True, True, 4),
+    (2, 4, 6, True, True, 300),              # runs to convergence
+])
+def test_multi_gpu_register_window_kernel_with_concurrent_ranks_vs_single_domain_oracle(emu, R, ny, nx, unit, jacobi,
+                                                                                        maxiter):
+    """k_cg_persistent_multi -- the peer-memory path for widths that are not a multiple of 1024 -- with R ranks running
+    at once: same checks as for the TMA-fed kernel above."""
+    if not emu.emu_thread_probe(256 * R):
+        pytest.skip("this machine cannot run 256 OS threads per rank at once")
+    rng = np.random.default_rng(R * 7927 + ny * 31 + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.5, 0.25)
+    ranks = Ranks(emu, R, ny, nx)
+    A = lambda z: orc.neg_laplacian_pinned(z, nx, ny, dx, dy)        # noqa: E731
+    inv = orc.jacobi_inverse_diagonal(nx, ny, dx, dy) if jacobi else None
+    for _repeat in range(2):
+        b = rng.standard_normal((ny, nx))
+        b -= b.mean()
+        b[0, 0] = 0.0
+        x, info, iters = ranks.solve(b, dx, dy, jacobi, 1e-10, maxiter, 4, kernel="register-window")
+        xo, io, to = orc.pcg(A, b.ravel().copy(), 1e-10, maxiter, inv)
+        assert info == io and abs(iters - to) <= 1
+        assert np.linalg.norm(x.ravel() - xo) <= (1e-10 if info else 1e-9) * np.linalg.norm(xo)
+    epochs = {int(s_.view(np.uint64)[2]) for s_ in ranks.syncs}
+    assert len(epochs) == 1 and epochs.pop() > 0
