@@ -36,6 +36,19 @@ for what in "$@"; do
           > gpurun_out/sanitizer_$tool.log 2>&1
         echo "$tool rc=$?" | tee -a gpurun_out/sanitizer_summary.txt
       done ;;
-    *) echo "unknown target $what (tests bench launches full4096 full512 sanitize)"; exit 2 ;;
+    scaling)      # configs 4 and 5 at every GPU count the box has (`gpurun --gpus 8 -- 'bash profiles/capture.sh scaling'`)
+      ngpu=$(nvidia-smi -L | wc -l)
+      for wl in cavity4096 strong8192 weak16384; do
+        for n in 1 2 4 8; do
+          [ "$n" -le "$ngpu" ] || continue
+          steps=10; [ "$wl" = weak16384 ] && steps=5
+          timeout 900 python bench.py --gpus $n --workload $wl --steps $steps --warmup 3 --no-cpu-baseline \
+            > gpurun_out/bench_${wl}_${n}gpu.json 2> gpurun_out/bench_${wl}_${n}gpu.err
+          echo "$wl x$n rc=$?" | tee -a gpurun_out/scaling_summary.txt
+        done
+      done ;;
+    reference)    # the CPU arm on the box's host cores
+      python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_arm.json ;;
+    *) echo "unknown target $what (tests bench launches full4096 full512 sanitize scaling reference)"; exit 2 ;;
   esac
 done
