@@ -53,6 +53,9 @@ def build_parser() -> argparse.ArgumentParser:
     run_p.add_argument("--checkpoint", type=str, default=None)
     run_p.add_argument("--restart", type=str, default=None)
     run_p.add_argument("--allow-hash-mismatch", action="store_true")
+    # new: restore the dt controller's memory saved in the checkpoint, so the resumed run
+    # continues the interrupted one instead of restarting the dt ramp (the reference's, and the default, behaviour)
+    run_p.add_argument("--exact-restart", action="store_true")
     run_p.add_argument("--json-stream", action="store_true")
     run_p.add_argument("--continuity-threshold", type=float, default=None)
     run_p.add_argument("--progress", action="store_true")
@@ -119,6 +122,9 @@ def main(argv: list[str] | None = None) -> int:
                       "(use --allow-hash-mismatch to override)")
                 return 3
             start_it = int(meta.get("iteration", 0)) + 1
+            from .io.checkpoint import exact_restart_requested, restore_step_state
+            if exact_restart_requested(args.exact_restart):
+                restore_step_state(state, meta)
         except Exception as exc:
             print(f"Failed to load checkpoint {args.restart}: {exc}")
             state, start_it = None, 0

@@ -7,9 +7,17 @@
                 (sha1[:16] of each array's raw bytes), seed, schema_version=1
   field_<name>  float64 (ny+2, nx+2) array INCLUDING the ghost ring
 
-written atomically (temp file + fsync + ``os.replace``).  ``state.meta`` is not
-persisted (the reference drops ``dt_prev`` / ``divergence_history`` too, so a
-restart resets dt -- kept for interchangeability).
+written atomically (temp file + fsync + ``os.replace``).
+
+New: the time-step controller's memory -- ``dt_prev``,
+``divergence_history``, ``prev_div_norm`` of ``state.meta`` -- rides along under
+ONE extra meta key, ``step_state``.  The reference drops it, so its restarts
+begin a fresh dt ramp; that stays the default here (``load_checkpoint`` returns a
+State with empty ``meta`` exactly like the reference's).  ``restore_step_state``
+(``pyflow run --restart ... --exact-restart`` or ``PYFLOW_B200_EXACT_RESTART=1``)
+puts it back, and the resumed run continues the uninterrupted one: same dt
+sequence, same fields.  Old readers, the reference's included, ignore unknown
+meta keys, so files stay interchangeable both ways.
 
 Device note: fields are pulled from HBM with the read-only accessor, so writing
 a checkpoint does not force a re-upload on the next step.
@@ -61,6 +69,40 @@ def _host_fields(state) -> dict[str, np.ndarray]:
     return dict(f.items())
 
 
+STEP_STATE_KEYS = ("dt_prev", "divergence_history", "prev_div_norm")
+
+
+def _step_state(state) -> dict[str, Any] | None:
+    """The dt controller's memory (solver.py:27-62 of the reference keeps it in ``state.meta``) as plain JSON
+    values; floats survive ``json`` exactly (shortest round-trip repr, NaN / Infinity literals)."""
+    src = getattr(state, "meta", None)
+    if not isinstance(src, dict):
+        return None
+    out: dict[str, Any] = {}
+    for key in STEP_STATE_KEYS:
+        if key in src:
+            v = src[key]
+            out[key] = [float(t) for t in v] if isinstance(v, (list, tuple)) else float(v)
+    return out or None
+
+
+def restore_step_state(state, meta: dict[str, Any]) -> bool:
+    """Copy a checkpoint's ``step_state`` into ``state.meta`` (opt-in exact restart).  False when the file has
+    none (written by the reference or by an older version): the run then restarts the dt ramp as before."""
+    saved = meta.get("step_state") if isinstance(meta, dict) else None
+    if not isinstance(saved, dict):
+        return False
+    for key in STEP_STATE_KEYS:
+        if key in saved:
+            v = saved[key]
+            state.meta[key] = [float(t) for t in v] if isinstance(v, list) else float(v)
+    return True
+
+
+def exact_restart_requested(flag: bool = False) -> bool:
+    return bool(flag) or os.environ.get("PYFLOW_B200_EXACT_RESTART", "0") == "1"
+
+
 def _meta(state, fields, iteration, sim_time, cfg, structured: bool) -> dict[str, Any]:
     meta: dict[str, Any] = {
         "iteration": iteration, "time": sim_time, "nx": state.nx, "ny": state.ny,
@@ -77,6 +119,9 @@ def _meta(state, fields, iteration, sim_time, cfg, structured: bool) -> dict[str
     meta["field_hashes"] = {k: _hash_array(v) for k, v in fields.items()}
     meta["seed"] = getattr(cfg, "seed", None)
     meta["schema_version"] = 1
+    step_state = _step_state(state)
+    if step_state is not None:                      # new key, after the reference's own (see the module docstring)
+        meta["step_state"] = step_state
     return meta
 
 
@@ -145,13 +190,13 @@ class BackgroundCheckpointWriter:
         self.wait()                                    # one write in flight; its buffers are free again
         fields = self._snapshot(state)
         from types import SimpleNamespace
-        shape = SimpleNamespace(nx=state.nx, ny=state.ny)
-        head = _meta(shape, {}, iteration, sim_time, cfg, structured=True)     # config hashes taken now, not later
+        shape = SimpleNamespace(nx=state.nx, ny=state.ny, meta=dict(getattr(state, "meta", None) or {}))
+        head = _meta(shape, {}, iteration, sim_time, cfg, structured=True)     # config hashes, step state: taken now
 
         def work():
             try:
-                meta = dict(head)
-                meta["field_hashes"] = {k: _hash_array(v) for k, v in fields.items()}
+                hashes = {k: _hash_array(v) for k, v in fields.items()}
+                meta = {k: (hashes if k == "field_hashes" else v) for k, v in head.items()}   # key order kept
                 _write_npz(path, meta, fields)
                 self.written += 1
             except BaseException as exc:           # surfaced by wait()
@@ -194,4 +239,4 @@ def load_checkpoint_bytes(buf: bytes) -> tuple[State, dict[str, Any]]:
 
 
 __all__ = ["save_checkpoint", "load_checkpoint", "save_checkpoint_bytes", "load_checkpoint_bytes",
-           "BackgroundCheckpointWriter"]
+           "BackgroundCheckpointWriter", "restore_step_state", "exact_restart_requested", "STEP_STATE_KEYS"]

@@ -414,6 +414,74 @@ def test_cli_run_json_stream_checkpoint_restart(slab_cls, tmp_path, capsys):
     assert rc == 3
 
 
+def test_exact_restart_continues_the_uninterrupted_run(slab_cls, tmp_path):
+    """SURVEY 8f item 3 (optional part): the dt controller's memory (dt_prev, divergence_history, prev_div_norm)
+    is saved under the extra meta key ``step_state``; restored on request, the resumed run continues the
+    uninterrupted one -- same dt sequence through the safeguard halving, same fields bit for bit.  Without the
+    request a restart begins a fresh dt ramp, as in the reference."""
+    import os
+    import subprocess
+    import sys
+    from pyflow.config.model import SimulationConfig
+    from pyflow.drivers.simulation_driver import SimulationDriver
+    from pyflow.io.checkpoint import STEP_STATE_KEYS, load_checkpoint, restore_step_state
+    cfg = SimulationConfig(nx=20, ny=16, Re=100.0, advection_scheme="quick", lin_maxiter=300, diagnostics=False)
+    total, cut = 9, 5
+    full = SimulationDriver(cfg)
+    full_dt = [d["dt"] for _s, _r, d in full.run(max_steps=total)]
+    assert any(b < a for a, b in zip(full_dt, full_dt[1:]))          # the ramp is not monotone: history matters
+    for mode in ("sync", "async"):
+        ck = str(tmp_path / f"{mode}.npz")
+        part = SimulationDriver(cfg)
+        part.async_checkpoint = mode == "async"
+        for _ in part.run(max_steps=cut, checkpoint_path=ck, checkpoint_interval=1):
+            pass
+        st, meta = load_checkpoint(ck)
+        assert meta["iteration"] == cut - 1 and st.meta == {}        # loading alone restores nothing (reference)
+        saved = meta["step_state"]
+        assert set(saved) == set(STEP_STATE_KEYS) and list(meta)[-1] == "step_state"
+        assert saved["dt_prev"] == part.state.meta["dt_prev"] == full_dt[cut - 1]
+        assert saved["divergence_history"] == part.state.meta["divergence_history"]
+        assert restore_step_state(st, meta) and st.meta["dt_prev"] == full_dt[cut - 1]
+        resumed = SimulationDriver(cfg, st)
+        dts = [d["dt"] for _s, _r, d in resumed.run(max_steps=total, start_iteration=cut)]
+        assert dts == full_dt[cut:]
+        for f in ("u", "v", "p"):
+            assert np.array_equal(st.fields[f], full.state.fields[f])
+    # default restart: fresh ramp, different dt
+    st, meta = load_checkpoint(ck)
+    plain = [d["dt"] for _s, _r, d in SimulationDriver(cfg, st).run(max_steps=total, start_iteration=cut)]
+    assert plain != full_dt[cut:] and plain[0] <= 1e-2 * cfg.cfl_growth
+    # files written before this key existed / by the reference: nothing to restore, not an error
+    assert restore_step_state(st, {k: v for k, v in meta.items() if k != "step_state"}) is False
+    # the reference's own loader reads the file (unknown meta keys are ignored) -- build container only
+    if os.path.isdir("/root/reference/src/pyflow"):
+        code = ("import sys; from pyflow.io.checkpoint import load_checkpoint; st, m = load_checkpoint(sys.argv[1]); "
+                "print(m['iteration'], m['schema_version'], sorted(st.fields), st.fields['u'].shape)")
+        r = subprocess.run([sys.executable, "-c", code, ck], capture_output=True, text=True,
+                           env=dict(os.environ, PYTHONPATH="/root/reference/src"), timeout=300)
+        assert r.returncode == 0 and r.stdout.split()[:2] == [str(cut - 1), "1"], r.stdout + r.stderr
+
+
+def test_cli_exact_restart_flag(slab_cls, tmp_path, capsys, monkeypatch):
+    from pyflow import cli
+    ck = str(tmp_path / "ck.npz")
+    common = ["--nx", "16", "--ny", "12", "--json-stream", "--checkpoint", ck, "--checkpoint-interval", "1"]
+
+    def dts(argv):
+        assert cli.main(argv) == 0
+        return [json.loads(line)["dt"] for line in capsys.readouterr().out.splitlines() if line.startswith("{")]
+
+    full = dts(["run", "--steps", "8", *common])
+    assert len(dts(["run", "--steps", "5", *common])) == 5
+    assert dts(["run", "--steps", "8", "--restart", ck, "--exact-restart", *common]) == full[5:]
+    dts(["run", "--steps", "5", *common])                            # checkpoint of iteration 4 again
+    assert dts(["run", "--steps", "8", "--restart", ck, *common]) != full[5:]       # reference behaviour: fresh ramp
+    dts(["run", "--steps", "5", *common])
+    monkeypatch.setenv("PYFLOW_B200_EXACT_RESTART", "1")
+    assert dts(["run", "--steps", "8", "--restart", ck, *common]) == full[5:]
+
+
 # ------------------------------------------------------------------ alternate dict-payload driver
 def test_alternate_driver_runs_on_the_device_statistics(slab_cls):
     import pyflow.driver.simulation_driver as alt

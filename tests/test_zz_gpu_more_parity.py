@@ -167,3 +167,26 @@ def test_assembled_matrix_jacobi_runs_on_the_device():
         p, diag = solve_pressure_poisson(st, 0.01, dx, dy, cfg, preconditioner=pre)
         out.append((p, diag["Rp_residual"]))
     assert bits_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+
+def test_exact_restart_on_the_device_path(tmp_path):
+    """SURVEY 8f item 3 (optional part): checkpoint after 5 steps, load, restore the saved dt-controller memory
+    (``step_state``), run 4 more: the same dt sequence as the uninterrupted 9 steps (through the safeguard halving)
+    and the same fields, to the bar of the reference's own restart test (tests/test_checkpoint_restart.py:49-51,
+    atol 1e-12)."""
+    from pyflow.config.model import SimulationConfig
+    from pyflow.drivers.simulation_driver import SimulationDriver
+    from pyflow.io.checkpoint import load_checkpoint, restore_step_state
+    cfg = SimulationConfig(nx=96, ny=80, Re=100.0, advection_scheme="quick", lin_maxiter=300, diagnostics=False)
+    total, cut = 9, 5
+    full = SimulationDriver(cfg)
+    full_dt = [d["dt"] for _s, _r, d in full.run(max_steps=total)]
+    ck = str(tmp_path / "ck.npz")
+    for _ in SimulationDriver(cfg).run(max_steps=cut, checkpoint_path=ck, checkpoint_interval=1):
+        pass
+    st, meta = load_checkpoint(ck)
+    assert meta["iteration"] == cut - 1 and restore_step_state(st, meta)
+    dts = [d["dt"] for _s, _r, d in SimulationDriver(cfg, st).run(max_steps=total, start_iteration=cut)]
+    assert dts == full_dt[cut:]
+    for f in ("u", "v", "p"):
+        assert np.allclose(st.fields[f], full.state.fields[f], rtol=0.0, atol=1e-12), f
