@@ -161,6 +161,15 @@ int pf_op_cg_generic(pf_ctx* ctx, int mode, const double* b, double* x, double d
                      double inv_diag_interior, double tol, int maxiter, int* info, int* true_iters,
                      double* rnorm, double* bnorm, void* stream);
 
+/* BiCGSTAB on the pinned Neumann operator: the `method='bicgstab'` branch (and default) of the reference's
+ * linear-solve seam, linear_solvers/interface.py:23,44-45 -> scipy.sparse.linalg.bicgstab with x0 = 0.  Same
+ * conventions as pf_op_pcg; *info is scipy's exit code (0 converged, maxiter exhausted, -10 rho breakdown,
+ * -11 omega / rtilde.v breakdown), *true_iters the completed iterations, *rnorm = ||b - A x||.  Off the time-step
+ * path; overwrites the context's p field and the dead previous-step velocity buffer.  */
+int pf_op_bicgstab(pf_ctx* ctx, const double* b, double* x, double dx, double dy,
+                   int jacobi, double inv_diag_interior, double tol, int maxiter,
+                   int* info, int* true_iters, double* rnorm, void* stream);
+
 /* Multi-GPU slabs (no reference counterpart: SURVEY.md section 8e).  One
  * process per GPU; rank 0 makes the id, the host side broadcasts the 128
  * bytes (torch.distributed), every rank calls pf_comm_init.                  */

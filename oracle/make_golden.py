@@ -9,7 +9,7 @@ Runs only where ``/root/reference`` exists (the build container).  It
      which travel to the GPU box where the reference itself cannot.
 
 Usage:  python oracle/make_golden.py [part ...]   (exit code != 0 on any mismatch; parts: operators,
-        legacy_ops, pressure, trajectories, config, config2, tiny -- default all)
+        legacy_ops, pressure, trajectories, config, config2, tiny, bicgstab -- default all)
 """
 from __future__ import annotations
 
@@ -395,10 +395,70 @@ def config_vectors():
                                            "meta": meta}}, fh, indent=1, sort_keys=True)
 
 
+BICG_CASES = [   # tag, nx, ny, dx, dy, jacobi, tol, maxiter
+    ("24x20_plain", 24, 20, 1.0, 1.0, False, 1e-10, 2000),
+    ("24x20_jacobi", 24, 20, 1.0, 1.0, True, 1e-10, 2000),
+    ("33x17_jacobi_nonunit", 33, 17, 0.5, 0.25, True, 1e-10, 4000),
+    ("40x28_truncated7", 40, 28, 1.0, 1.0, True, 1e-10, 7),
+    ("16x16_default_tol", 16, 16, 1.0, 1.0, False, 1e-8, 500),
+    ("12x10_zero_rhs", 12, 10, 1.0, 1.0, True, 1e-10, 50),
+]
+
+
+def bicgstab_rhs(tag, nx, ny):
+    """Projection-like right-hand side: mean-free, pinned entry zero (pressure_solver.py:124-128)."""
+    if "zero_rhs" in tag:
+        return np.zeros(nx * ny)
+    b = np.random.default_rng(nx * 100 + ny).standard_normal(nx * ny)
+    b -= b.mean()
+    b[0] = 0.0
+    return b
+
+
+def bicgstab_vectors():
+    """`method='bicgstab'` -- the DEFAULT of the reference's linear_solvers.interface.solve (interface.py:23,44-45)
+    -- on the pinned Neumann operator (pressure_solver.py:97-105, rebuilt here around the reference's own
+    laplacian_coherent because the class is local to solve_pressure_poisson), with the reference's own Jacobi
+    operator.  The oracle restatement must equal it bitwise; inputs and outputs become tests/golden/bicgstab.npz."""
+    import scipy.sparse as sp
+    from pyflow.linear_solvers.interface import solve as ref_solve
+    print("bicgstab through the reference's interface.solve")
+    out = {}
+    for tag, nx, ny, dx, dy, jac, tol, maxiter in BICG_CASES:
+        class Pinned(spla.LinearOperator):
+            def __init__(self):
+                super().__init__(dtype=np.float64, shape=(nx * ny, nx * ny))
+
+            def _matvec(self, x):
+                o = (-ref_coh.laplacian_coherent(x.reshape(ny, nx), dx, dy)).reshape(-1)
+                o[0] = x[0]
+                return o
+        b = bicgstab_rhs(tag, nx, ny)
+        kw = {}
+        if jac:
+            kw["M"] = jacobi_preconditioner(sp.csr_matrix(ref_ps.assemble_negative_laplacian(nx, ny, dx, dy)))
+        n = [0]
+        res = ref_solve(Pinned(), b.copy(), tol=tol, maxiter=maxiter, callback=lambda _x: n.__setitem__(0, n[0] + 1), **kw)
+        assert res.method == "bicgstab"
+        x, conv, its, rnorm, info = orc.interface_solve(b.copy(), nx, ny, dx, dy, "bicgstab", tol, maxiter, jac)
+        _, _, true_its = orc.bicgstab(lambda t: orc.neg_laplacian_pinned(t, nx, ny, dx, dy), b.copy(), tol, maxiter,
+                                      orc.jacobi_inverse_diagonal(nx, ny, dx, dy) if jac else None)
+        check(f"bicgstab {tag} x", x, res.x)
+        check(f"bicgstab {tag} bookkeeping", [conv, its, rnorm], [res.converged, res.iterations, res.residual_norm])
+        check(f"bicgstab {tag} completed iterations", true_its, n[0])
+        print(f"    {tag}: converged={res.converged} iterations={res.iterations} callbacks={n[0]} rnorm={res.residual_norm:.3e}")
+        out[f"{tag}/b"] = b
+        out[f"{tag}/x"] = np.asarray(res.x)
+        out[f"{tag}/result"] = np.array([float(res.converged), float(res.iterations), res.residual_norm, float(n[0])])
+        out[f"{tag}/params"] = np.array([nx, ny, dx, dy, float(jac), tol, maxiter])
+    np.savez_compressed(os.path.join(GOLD, "bicgstab.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     parts = {"operators": operator_vectors, "legacy_ops": legacy_ops_vectors, "pressure": pressure_vectors,
-             "trajectories": trajectory_vectors, "config": config_vectors, "config2": config2_vectors, "tiny": tiny_vectors}
+             "trajectories": trajectory_vectors, "config": config_vectors, "config2": config2_vectors, "tiny": tiny_vectors,
+             "bicgstab": bicgstab_vectors}
     only = sys.argv[1:]                      # e.g. `make_golden.py legacy_ops` regenerates one fixture file
     for name, fn in parts.items():
         if not only or name in only:

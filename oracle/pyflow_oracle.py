@@ -264,6 +264,74 @@ def pcg(matvec, b, tol, maxiter, inv_diag=None, dot=np.dot):
     return x, maxiter, iters
 
 
+def bicgstab(matvec, b, tol, maxiter, inv_diag=None, dot=np.dot):
+    """scipy.sparse.linalg.bicgstab (scipy/sparse/linalg/_isolve/iterative.py; third-party, pinned
+    scipy==1.13.1 in the reference's pyproject.toml:20, same loop in the 1.18 installed here) with x0 = 0, the
+    way ``linear_solvers/interface.py:33,44-45`` calls it for ``method='bicgstab'`` (the default of ``solve``).
+    Restated statement for statement; pinned bitwise against scipy itself in tests/test_oracle_golden.py.
+    Returns (x, info, completed_iterations); info: 0 converged, maxiter exhausted, -10 / -11 breakdown."""
+    bnorm = float(np.sqrt(dot(b, b)))
+    atol = max(0.0, float(tol) * bnorm)
+    if bnorm == 0:
+        return b, 0, 0
+    x = np.zeros_like(b)
+    rhotol = np.finfo(b.dtype.char).eps ** 2
+    omegatol = rhotol
+    rho_prev = omega = alpha = p = v = None
+    r = b.copy()
+    rtilde = r.copy()
+    s = np.empty_like(r)
+    iters = 0
+    for it in range(maxiter):
+        if np.sqrt(dot(r, r)) < atol:
+            return x, 0, iters
+        rho = dot(rtilde, r)
+        if np.abs(rho) < rhotol:
+            return x, -10, iters
+        if it > 0:
+            if np.abs(omega) < omegatol:
+                return x, -11, iters
+            beta = (rho / rho_prev) * (alpha / omega)
+            p -= omega * v
+            p *= beta
+            p += r
+        else:
+            p = r.copy()
+        phat = p if inv_diag is None else inv_diag * p
+        v = matvec(phat)
+        rv = dot(rtilde, v)
+        if rv == 0:
+            return x, -11, iters
+        alpha = rho / rv
+        r -= alpha * v
+        s[:] = r[:]
+        if np.sqrt(dot(s, s)) < atol:
+            x += alpha * phat
+            return x, 0, iters
+        shat = s if inv_diag is None else inv_diag * s
+        t = matvec(shat)
+        omega = dot(t, s) / dot(t, t)
+        x += alpha * phat
+        x += omega * shat
+        r -= omega * t
+        rho_prev = rho
+        iters += 1
+    return x, maxiter, iters
+
+
+def interface_solve(b, nx, ny, dx, dy, method="bicgstab", tol=1e-8, maxiter=500, jacobi=False, dot=np.dot):
+    """``linear_solvers/interface.py:solve`` (:23-53) on the pinned operator: the Krylov solve, then
+    ``rnorm = ||b - A x||``, ``converged = (info == 0 and rnorm <= tol*||b||)``, ``iterations = info if info > 0
+    else 0``.  Returns (x, converged, iterations, rnorm, info)."""
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    A = lambda t: neg_laplacian_pinned(t, nx, ny, dx, dy)                        # noqa: E731
+    M = jacobi_inverse_diagonal(nx, ny, dx, dy) if jacobi else None
+    x, info, _ = (pcg if method == "cg" else bicgstab)(A, b, tol, maxiter, M, dot)
+    rnorm = float(np.linalg.norm(b - A(x)))
+    bnorm = float(np.linalg.norm(b)) or 1.0
+    return x, bool(info == 0 and rnorm <= tol * bnorm), (info if info > 0 else 0), rnorm, info
+
+
 # --------------------------------------------------------------------------
 # Pressure projection -- src/pyflow/solvers/pressure_solver.py:42-219
 # (normal projection mode only; manufactured mode is SURVEY 8f "next")

@@ -10,6 +10,7 @@
 
 #include "pf_cg.cuh"
 #include "pf_cg_generic.cuh"
+#include "pf_bicgstab.cuh"
 #include "pf_cg_small.cuh"
 #include "pf_cg_tma.cuh"
 #include "pf_comm.h"
@@ -868,6 +869,36 @@ int pf_op_cg_generic(pf_ctx* c, int mode, const double* b, double* x, double dx,
   if (true_iters) *true_iters = (int)c->h_scal[S_ITERS];
   if (rnorm) *rnorm = sqrt(c->h_scal[S_RES_SUMSQ]);
   if (bnorm) *bnorm = sqrt(c->h_scal[S_BB]);
+  return PF_OK;
+}
+
+int pf_op_bicgstab(pf_ctx* c, const double* b, double* x, double dx, double dy, int jacobi, double inv_diag_interior,
+                   double tol, int maxiter, int* info, int* true_iters, double* rnorm, void* stream) {
+  PF_OP_PROLOGUE();
+  if (!b || !x || maxiter < 0) return PF_ERR_ARG;
+  // this seam overwrites the p field (x) of the context; t lives in the previous-step velocity buffer, which
+  // holds nothing between time steps (k_predict rewrites it before anything reads it)
+  PF_TRY(h2d_field(c, c->b, b, nxs, st));
+  BiArgs a{};
+  a.s = s; a.b = c->b; a.x = c->x; a.r = c->r; a.p = c->p0; a.v = c->p1; a.t = c->uo;
+  a.part = c->cg_part; a.scal = c->scal;
+  a.dx = dx; a.dy = dy; a.invd = jacobi ? inv_diag_interior : 1.0; a.tol = tol; a.maxiter = maxiter;
+  void* args[] = {&a};
+  const void* fn = is_unit(dx, dy) ? (const void*)k_bicgstab<true> : (const void*)k_bicgstab<false>;
+  int occ = 0;
+  PF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, CG_THREADS, 0));
+  if (occ < 1) return fail(c, PF_ERR_UNSUPPORTED, "pf_op_bicgstab", "kernel does not fit on an SM");
+  const long long ncell = (long long)s.nx * s.nyl;
+  const long long resident = std::min((long long)c->sm_count * occ, (long long)CG_MAX_GRID);
+  const int grid = (int)std::max(1LL, std::min(resident, (ncell + CG_THREADS - 1) / CG_THREADS));
+  PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CG_THREADS), args, 0, st));
+  c->launches++;
+  c->center_valid = false;
+  PF_TRY(d2h_field(c, x, c->x, nxs, st));
+  PF_TRY(read_scalars(c, st, false));
+  if (info) *info = (int)c->h_scal[S_INFO];
+  if (true_iters) *true_iters = (int)c->h_scal[S_ITERS];
+  if (rnorm) *rnorm = sqrt(c->h_scal[S_RES_SUMSQ]);
   return PF_OK;
 }
 

@@ -243,6 +243,19 @@ class DeviceSlab:
                                        C.byref(iters), C.byref(rnorm), self._stream()), self.ctx, "pf_op_pcg")
         return x, info.value, iters.value, rnorm.value
 
+    def bicgstab(self, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=None):
+        """Solve (_NegLaplacianPinned) x = b with scipy's BiCGSTAB recurrence on the device (k_bicgstab).
+        Returns (x (ny,nx), info, completed_iterations, ||b - A x||); info is scipy's exit code."""
+        b = self._dense(b)
+        x = np.empty_like(b)
+        if inv_diag_interior is None:
+            inv_diag_interior = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)
+        info, iters, rnorm = C.c_int(), C.c_int(), C.c_double()
+        _lib.check(self._lib.pf_op_bicgstab(self.ctx, _ptr(b), _ptr(x), float(dx), float(dy), int(bool(jacobi)),
+                                            float(inv_diag_interior), float(tol), int(maxiter), C.byref(info),
+                                            C.byref(iters), C.byref(rnorm), self._stream()), self.ctx, "pf_op_bicgstab")
+        return x, info.value, iters.value, rnorm.value
+
     def cg_generic(self, mode: str, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=1.0, want_x=True):
         """Reference-order CG with the plain (q stored) kernel.  mode 'pinned' | 'dirichlet'.
         The solution stays in the context's p field.  Returns (x|None, info, iters, ||b-Ax||, ||b||)."""

@@ -7,8 +7,10 @@ The B200 path accelerates the one operator the hot path uses -- the matrix-free
 pinned Neumann ``-laplacian_coherent`` of pressure_solver.py:97-105 -- so
 ``solve`` accepts its descriptor ``NegLaplacianPinned`` and runs scipy's CG
 recurrence (x0 = 0, strict ``||r|| < tol*||b||`` test at the top of each
-iteration, info = maxiter when exhausted) on the device.  Anything else raises:
-there is no CPU fallback.
+iteration, info = maxiter when exhausted) on the device; ``method='bicgstab'``
+(the signature's default, interface.py:23,44-45; no call site in the reference
+asks for it) runs scipy's BiCGSTAB recurrence, exit codes included, in
+``k_bicgstab``.  Anything else raises: there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -57,8 +59,6 @@ def solve(A, b, method: Literal["cg", "bicgstab"] = "bicgstab", tol: float = 1e-
           **kwargs) -> LinearSolveResult:
     if not isinstance(A, NegLaplacianPinned):
         raise NotImplementedError("the device solve handles the matrix-free NegLaplacianPinned operator only")
-    if method != "cg":
-        raise NotImplementedError("only method='cg' runs on the device (bicgstab: SURVEY.md 8f item 2)")
     M = kwargs.pop("M", None)
     if kwargs:
         raise TypeError(f"unsupported solver arguments: {sorted(kwargs)}")
@@ -66,8 +66,10 @@ def solve(A, b, method: Literal["cg", "bicgstab"] = "bicgstab", tol: float = 1e-
         M = resolve(M, A.nx, A.ny)          # RingJacobi, or the diagonal of assemble_negative_laplacian; else raises
     b = np.asarray(b, dtype=np.float64)
     slab = slab_for_shape(A.ny, A.nx)
-    x, info, _iters, rnorm = slab.pcg(b.reshape(A.ny, A.nx), A.dx, A.dy, tol, maxiter, jacobi=M is not None,
-                                      inv_diag_interior=(M.inv_diag_interior if M is not None else 1.0))
+    # like the reference, anything that is not 'cg' takes the bicgstab branch (interface.py:42-45)
+    run = slab.pcg if method == "cg" else slab.bicgstab
+    x, info, _iters, rnorm = run(b.reshape(A.ny, A.nx), A.dx, A.dy, tol, maxiter, jacobi=M is not None,
+                                 inv_diag_interior=(M.inv_diag_interior if M is not None else 1.0))
     bnorm = float(np.linalg.norm(b)) or 1.0
     converged = (info == 0) and (rnorm <= tol * bnorm)
     iterations = info if info > 0 else 0

@@ -182,7 +182,7 @@ class CpuSlab:
         fn = {"upwind": orc.advect_upwind, "quick": orc.advect_quick}[scheme]
         return fn(self._dense(u), self._dense(v), self._dense(f), dx, dy)
 
-    def pcg(self, b, dx, dy, tol, maxiter, jacobi=True, inv_diag_interior=None):
+    def pcg(self, b, dx, dy, tol, maxiter, jacobi=True, inv_diag_interior=None, _krylov=None):
         b = self._dense(b)
         ny, nx = b.shape
         inv_diag = None
@@ -198,11 +198,14 @@ class CpuSlab:
             return orc.neg_laplacian_pinned(xv, nx, ny, dx, dy)
 
         rhs = b.reshape(-1).copy()
-        x, info, iters = orc.pcg(A, rhs, tol, maxiter, inv_diag)
+        x, info, iters = (_krylov or orc.pcg)(A, rhs, tol, maxiter, inv_diag)
         x = np.array(x, dtype=np.float64)
         rnorm = float(np.sqrt(_norm2(rhs - A(x))))
         self.p[:] = x.reshape(ny, nx)
         return x.reshape(ny, nx), int(info), int(iters), rnorm
+
+    def bicgstab(self, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=None):
+        return self.pcg(b, dx, dy, tol, maxiter, jacobi, inv_diag_interior, _krylov=orc.bicgstab)
 
     def cg_generic(self, mode, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=1.0, want_x=True):
         b = self._dense(b)

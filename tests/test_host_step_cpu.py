@@ -537,8 +537,11 @@ def test_operator_seams_signatures_and_shapes(slab_cls):
     assert np.linalg.norm(A.matvec(r.x) - b) <= 1e-9 * np.linalg.norm(b) and r.x.shape == b.shape
     r2 = solve(A, b, method="cg", tol=1e-10, maxiter=3)
     assert (not r2.converged) and r2.iterations == 3
-    with pytest.raises(NotImplementedError):
-        solve(A, b, method="bicgstab")
+    r3 = solve(A, b, tol=1e-10, maxiter=2000)                   # the signature's default method (interface.py:23)
+    assert r3.method == "bicgstab" and r3.converged and r3.iterations == 0
+    assert np.linalg.norm(A.matvec(r3.x) - b) <= 1e-10 * np.linalg.norm(b)
+    r4 = solve(A, b, method="bicgstab", tol=1e-10, maxiter=4, M=jacobi_preconditioner(A))
+    assert (not r4.converged) and r4.iterations == 4
     with pytest.raises(NotImplementedError):
         solve(np.eye(4), np.ones(4), method="cg")
 

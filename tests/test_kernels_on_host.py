@@ -327,6 +327,7 @@ def emu(tmp_path_factory):
     lib.emu_divc_stats.argtypes = [i, i, dp, dp, d, d, i, dp, dp]
     lib.emu_cg_generic.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     lib.emu_cg_persistent.argtypes = [i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp]
+    lib.emu_bicgstab.argtypes = [i, i, dp, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     lib.emu_cg_split.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp, dp]
     lib.emu_cg_small.argtypes = [i, i, i, dp, dp, dp, dp, dp, C.POINTER(C.c_ulonglong), d, d, d, d, i]
     lib.emu_cg_tmad.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp, C.POINTER(C.c_ulonglong)]
@@ -563,6 +564,45 @@ def test_plain_cg_kernel_follows_scipys_recurrence(emu, shape, unit, jacobi, max
     assert close(rnorm, float(np.linalg.norm(b.ravel() - A(x.ravel()))), 1e-6)
     zero = _cg_generic(emu, 0, np.zeros(shape), dx, dy, invd, 1e-10, 50)
     assert zero[1] == 0 and zero[2] == 0 and not zero[0].any()       # b = 0  =>  x = 0, no iterations
+
+
+@pytest.mark.parametrize("tag", ["24x20_plain", "24x20_jacobi", "33x17_jacobi_nonunit", "40x28_truncated7",
+                                 "16x16_default_tol", "12x10_zero_rhs"])
+def test_bicgstab_kernel_vs_reference_golden(emu, tag):
+    """k_bicgstab executed on the host against what the UNMODIFIED reference's interface.solve (default method,
+    scipy's bicgstab) returned for the same right-hand side (tests/golden/bicgstab.npz): the truncated solve is the
+    same iterate up to summation order; converged solves meet the reference's own convergence criterion and agree
+    with its solution to the accuracy the tolerance allows; exit bookkeeping (iterations = info if info > 0) equal."""
+    import os
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "bicgstab.npz")) as z:
+        g = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(tag + "/")}
+    nx, ny, dx, dy, jac, tol, maxiter = g["params"]
+    nx, ny, maxiter = int(nx), int(ny), int(maxiter)
+    b = g["b"].reshape(ny, nx)
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    x, r, p, v, t = (dev.put() for _ in range(5))
+    part = np.zeros(emu.emu_cg_part_doubles())
+    invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2) if jac else 1.0
+    emu.emu_bicgstab(nx, ny, ptr(dev.put(b)), ptr(x), ptr(r), ptr(p), ptr(v), ptr(t), dx, dy, invd, tol, maxiter,
+                     ptr(part), ptr(S.scal))
+    xs, info, iters, rnorm = dev.get(x).ravel(), int(S["S_INFO"]), int(S["S_ITERS"]), S["S_RES_SUMSQ"] ** 0.5
+    conv_ref, its_ref, rnorm_ref, done_ref = g["result"]
+    bnorm = float(np.linalg.norm(g["b"])) or 1.0
+    A = lambda z_: orc.neg_laplacian_pinned(z_, nx, ny, dx, dy)          # noqa: E731
+    assert close(rnorm, float(np.linalg.norm(g["b"] - A(xs))), 1e-6) or rnorm == 0.0
+    assert (info if info > 0 else 0) == int(its_ref)
+    assert bool(info == 0 and rnorm <= tol * bnorm) == bool(conv_ref)
+    if "truncated" in tag:
+        assert iters == int(done_ref) == maxiter
+        assert np.linalg.norm(xs - g["x"]) <= 1e-11 * np.linalg.norm(g["x"])
+    elif "zero_rhs" in tag:
+        assert iters == 0 and not xs.any()
+    else:
+        # both are solutions of the same system to ||b - A x|| <= tol ||b||: they differ by at most
+        # 2 tol ||b|| / sigma_min(A)  (sigma_min of the pinned operator on these grids > 1e-3)
+        assert np.linalg.norm(xs - g["x"]) <= 2.0 * tol * bnorm / 1e-3
+        assert abs(iters - int(done_ref)) <= max(3, int(0.25 * done_ref))
 
 
 def test_plain_cg_kernel_dirichlet_mode_vs_oracle(emu):

@@ -195,3 +195,41 @@ def test_tiny_grids_vs_reference(golden, impl):
                 assert np.array_equal(st.fields[f], g[f]), (tag, f)
             else:
                 assert rel(st.fields[f], g[f]) < 1e-9, (tag, f)
+
+
+# ---------------------------------------------------------------- method='bicgstab' (default of interface.solve)
+BICG_TAGS = ["24x20_plain", "24x20_jacobi", "33x17_jacobi_nonunit", "40x28_truncated7", "16x16_default_tol",
+             "12x10_zero_rhs"]
+
+
+@pytest.mark.parametrize("tag", BICG_TAGS)
+def test_bicgstab_oracle_vs_reference_golden(tag):
+    """oracle.interface_solve(method='bicgstab') against what the UNMODIFIED reference's interface.solve returned
+    (tests/golden/bicgstab.npz, oracle/make_golden.py bicgstab): same machine arithmetic -> bitwise."""
+    import os
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "bicgstab.npz")) as z:
+        g = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(tag + "/")}
+    nx, ny, dx, dy, jac, tol, maxiter = g["params"]
+    x, conv, its, rnorm, _info = orc.interface_solve(g["b"].copy(), int(nx), int(ny), dx, dy, "bicgstab", tol,
+                                                     int(maxiter), bool(jac))
+    assert np.array_equal(x, g["x"])
+    assert [float(conv), float(its), rnorm] == list(g["result"][:3])
+
+
+def test_bicgstab_oracle_is_scipys_recurrence():
+    """The restatement against scipy.sparse.linalg.bicgstab itself (present on every box), bit for bit, incl. the
+    preconditioned and the truncated case."""
+    import scipy.sparse.linalg as spla
+    nx, ny, dx, dy = 21, 14, 0.7, 1.3
+    b = np.random.default_rng(5).standard_normal(nx * ny)
+    b -= b.mean()
+    b[0] = 0.0
+    mv = lambda t: orc.neg_laplacian_pinned(t, nx, ny, dx, dy)                      # noqa: E731
+    A = spla.LinearOperator((nx * ny, nx * ny), matvec=mv, dtype=np.float64)
+    invd = orc.jacobi_inverse_diagonal(nx, ny, dx, dy)
+    M = spla.LinearOperator((nx * ny, nx * ny), matvec=lambda t: invd * t, dtype=np.float64)
+    for kw, inv, maxiter in (({}, None, 3000), ({"M": M}, invd, 3000), ({"M": M}, invd, 5)):
+        xs, infos = spla.bicgstab(A, b, x0=np.zeros_like(b), rtol=1e-10, maxiter=maxiter, **kw)
+        xo, infoo, _ = orc.bicgstab(mv, b.copy(), 1e-10, maxiter, inv)
+        assert infos == infoo and np.array_equal(xs, xo)
