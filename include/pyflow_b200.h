@@ -170,6 +170,14 @@ int pf_op_bicgstab(pf_ctx* ctx, const double* b, double* x, double dx, double dy
                    int jacobi, double inv_diag_interior, double tol, int maxiter,
                    int* info, int* true_iters, double* rnorm, void* stream);
 
+/* The same seam with a USER-SUPPLIED DIAGONAL preconditioner (`solve(A, b, M=...)`, interface.py:23,43-45, where M
+ * is any operator that turns out to be diagonal): inv_diag is a dense host array (ny, nx) of the entries M applies
+ * (z = inv_diag * r).  method 0: scipy's cg recurrence, method 1: scipy's bicgstab.  Outputs as pf_op_bicgstab.
+ * Non-diagonal operators have no device form and are refused on the host side (no CPU fallback).            */
+int pf_op_krylov_diag(pf_ctx* ctx, int method, const double* b, const double* inv_diag, double* x,
+                      double dx, double dy, double tol, int maxiter,
+                      int* info, int* true_iters, double* rnorm, void* stream);
+
 /* Multi-GPU slabs (no reference counterpart: SURVEY.md section 8e).  One
  * process per GPU; rank 0 makes the id, the host side broadcasts the 128
  * bytes (torch.distributed), every rank calls pf_comm_init.                  */

@@ -872,22 +872,28 @@ int pf_op_cg_generic(pf_ctx* c, int mode, const double* b, double* x, double dx,
   return PF_OK;
 }
 
-int pf_op_bicgstab(pf_ctx* c, const double* b, double* x, double dx, double dy, int jacobi, double inv_diag_interior,
-                   double tol, int maxiter, int* info, int* true_iters, double* rnorm, void* stream) {
+// BiCGSTAB (method 1) or CG with a caller-supplied diagonal (method 0, inv_diag != NULL) on the pinned operator.
+// These seams overwrite the p field (x) of the context; t and the diagonal live in the previous-step velocity
+// buffers, which hold nothing between time steps (k_predict rewrites them before anything reads them).
+static int krylov_generic(pf_ctx* c, int method, const double* b, const double* inv_diag, double* x, double dx,
+                          double dy, int jacobi, double inv_diag_interior, double tol, int maxiter, int* info,
+                          int* true_iters, double* rnorm, void* stream) {
   PF_OP_PROLOGUE();
-  if (!b || !x || maxiter < 0) return PF_ERR_ARG;
-  // this seam overwrites the p field (x) of the context; t lives in the previous-step velocity buffer, which
-  // holds nothing between time steps (k_predict rewrites it before anything reads it)
+  if (!b || !x || maxiter < 0 || (method != 0 && method != 1) || (method == 0 && !inv_diag)) return PF_ERR_ARG;
   PF_TRY(h2d_field(c, c->b, b, nxs, st));
+  if (inv_diag) PF_TRY(h2d_field(c, c->vo, inv_diag, nxs, st));
   BiArgs a{};
   a.s = s; a.b = c->b; a.x = c->x; a.r = c->r; a.p = c->p0; a.v = c->p1; a.t = c->uo;
   a.part = c->cg_part; a.scal = c->scal;
+  a.minv = inv_diag ? c->vo : nullptr;
   a.dx = dx; a.dy = dy; a.invd = jacobi ? inv_diag_interior : 1.0; a.tol = tol; a.maxiter = maxiter;
   void* args[] = {&a};
-  const void* fn = is_unit(dx, dy) ? (const void*)k_bicgstab<true> : (const void*)k_bicgstab<false>;
+  const bool unit = is_unit(dx, dy);
+  const void* fn = method == 1 ? (unit ? (const void*)k_bicgstab<true> : (const void*)k_bicgstab<false>)
+                               : (unit ? (const void*)k_cg_diag<true> : (const void*)k_cg_diag<false>);
   int occ = 0;
   PF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, CG_THREADS, 0));
-  if (occ < 1) return fail(c, PF_ERR_UNSUPPORTED, "pf_op_bicgstab", "kernel does not fit on an SM");
+  if (occ < 1) return fail(c, PF_ERR_UNSUPPORTED, "krylov_generic", "kernel does not fit on an SM");
   const long long ncell = (long long)s.nx * s.nyl;
   const long long resident = std::min((long long)c->sm_count * occ, (long long)CG_MAX_GRID);
   const int grid = (int)std::max(1LL, std::min(resident, (ncell + CG_THREADS - 1) / CG_THREADS));
@@ -900,6 +906,18 @@ int pf_op_bicgstab(pf_ctx* c, const double* b, double* x, double dx, double dy, 
   if (true_iters) *true_iters = (int)c->h_scal[S_ITERS];
   if (rnorm) *rnorm = sqrt(c->h_scal[S_RES_SUMSQ]);
   return PF_OK;
+}
+
+int pf_op_bicgstab(pf_ctx* c, const double* b, double* x, double dx, double dy, int jacobi, double inv_diag_interior,
+                   double tol, int maxiter, int* info, int* true_iters, double* rnorm, void* stream) {
+  return krylov_generic(c, 1, b, nullptr, x, dx, dy, jacobi, inv_diag_interior, tol, maxiter, info, true_iters, rnorm,
+                        stream);
+}
+
+int pf_op_krylov_diag(pf_ctx* c, int method, const double* b, const double* inv_diag, double* x, double dx, double dy,
+                      double tol, int maxiter, int* info, int* true_iters, double* rnorm, void* stream) {
+  if (!inv_diag) return PF_ERR_ARG;
+  return krylov_generic(c, method, b, inv_diag, x, dx, dy, 0, 1.0, tol, maxiter, info, true_iters, rnorm, stream);
 }
 
 int pf_comm_unique_id(void* out128) { return comm_unique_id(out128); }

@@ -14,7 +14,8 @@
 //          shat = M s;  t = A shat;  omega = (t.s)/(t.t);  x = x + alpha*phat;  x = x + omega*shat;  r = r - omega*t
 //   exhausted -> maxiter
 //
-// M is the ring-identity Jacobi diagonal (1 on the boundary ring, invd inside) or the identity (invd = 1):
+// M is the ring-identity Jacobi diagonal (1 on the boundary ring, invd inside), the identity (invd = 1), or any
+// diagonal the caller supplies as an array of inverse entries (minv; a user-supplied diagonal preconditioner):
 // phat / shat are never stored, the scaling is applied to the five stencil inputs (same roundings as a stored
 // product).  rtilde is b itself (x0 = 0), s aliases r.  Vectors: b, x, r, p, v, t -- t borrows the context's
 // previous-step velocity buffer, which is dead between time steps.
@@ -41,15 +42,22 @@ struct BiArgs {
   double* t;
   double* part;       // [7][CG_MAX_GRID]
   double* scal;
+  const double* minv; // general inverse diagonal (device field layout) or nullptr = ring identity / invd
   double dx, dy, invd, tol;
   int maxiter;
 };
 
+// M[cell]: the caller's diagonal if there is one, else 1 on the boundary ring and invd inside
+__device__ __forceinline__ double bi_scale(const BiArgs& a, bool ring, size_t o) {
+  return a.minv ? a.minv[o] : (ring ? 1.0 : a.invd);
+}
+
 static_assert(7 * CG_MAX_GRID <= PF_TRACE_OFFSET, "seven partial slots fit in front of the trace region");
 
-// (A (M w))[jl, i] for the pinned operator: -(laplacian_coherent(M w)), row 0 replaced by the identity
-template <bool UNIT>
-__device__ __forceinline__ double bi_apply_scaled(const BiArgs& a, const double* w, int jl, int i, double invd) {
+// (A (M w))[jl, i] for the pinned operator: -(laplacian_coherent(M w)), row 0 replaced by the identity;
+// SCALED = false: plain (A w)[jl, i]
+template <bool UNIT, bool SCALED>
+__device__ __forceinline__ double bi_apply_scaled(const BiArgs& a, const double* w, int jl, int i) {
   const Slab& s = a.s;
   const int jg = s.row0 + jl;
   const bool hw = i > 0, he = i < s.nx - 1, hs = jg > 0, hn = jg < s.nyg - 1;
@@ -59,11 +67,19 @@ __device__ __forceinline__ double bi_apply_scaled(const BiArgs& a, const double*
   const bool ring_e = (i + 1 == s.nx - 1) || !hs || !hn;
   const bool ring_s = (jg - 1 == 0) || !hw || !he;
   const bool ring_n = (jg + 1 == s.nyg - 1) || !hw || !he;
-  const double c = (ring_c ? 1.0 : invd) * w[cell(s, jl, i)];
-  const double ww = hw ? (ring_w ? 1.0 : invd) * w[cell(s, jl, i - 1)] : 0.0;
-  const double e = he ? (ring_e ? 1.0 : invd) * w[cell(s, jl, i + 1)] : 0.0;
-  const double so = hs ? (ring_s ? 1.0 : invd) * w[cell(s, jl - 1, i)] : 0.0;
-  const double n = hn ? (ring_n ? 1.0 : invd) * w[cell(s, jl + 1, i)] : 0.0;
+  const size_t oc = cell(s, jl, i);
+  double c = w[oc];
+  double ww = hw ? w[cell(s, jl, i - 1)] : 0.0;
+  double e = he ? w[cell(s, jl, i + 1)] : 0.0;
+  double so = hs ? w[cell(s, jl - 1, i)] : 0.0;
+  double n = hn ? w[cell(s, jl + 1, i)] : 0.0;
+  if (SCALED) {
+    c = bi_scale(a, ring_c, oc) * c;
+    if (hw) ww = bi_scale(a, ring_w, cell(s, jl, i - 1)) * ww;
+    if (he) e = bi_scale(a, ring_e, cell(s, jl, i + 1)) * e;
+    if (hs) so = bi_scale(a, ring_s, cell(s, jl - 1, i)) * so;
+    if (hn) n = bi_scale(a, ring_n, cell(s, jl + 1, i)) * n;
+  }
   const double nl = neg_lap<UNIT>(c, ww, e, so, n, hw, he, hs, hn, a.dx, a.dy);
   return (jg == 0 && i == 0) ? c : nl;
 }
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_bicgstab(BiArgs a) {
       double rv = 0.0;
       for (long long k = first_cell; k < ncell; k += stride) {       // v = A (M p);  rtilde.v
         const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
-        const double vv = bi_apply_scaled<UNIT>(a, a.p, jl, i, a.invd);
+        const double vv = bi_apply_scaled<UNIT, true>(a, a.p, jl, i);
         a.v[cell(s, jl, i)] = vv;
         rv += a.b[cell(s, jl, i)] * vv;
       }
@@ -155,7 +171,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_bicgstab(BiArgs a) {
           const int jg = s.row0 + jl;
           const bool ring = (i == 0) || (i == s.nx - 1) || (jg == 0) || (jg == s.nyg - 1);
           const size_t o = cell(s, jl, i);
-          a.x[o] = a.x[o] + alpha * ((ring ? 1.0 : a.invd) * a.p[o]);
+          a.x[o] = a.x[o] + alpha * (bi_scale(a, ring, o) * a.p[o]);
         }
         rr = ss;
         info = 0;
@@ -164,7 +180,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_bicgstab(BiArgs a) {
       double ts = 0.0, tt = 0.0;
       for (long long k = first_cell; k < ncell; k += stride) {       // t = A (M s);  t.s, t.t
         const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
-        const double tv = bi_apply_scaled<UNIT>(a, a.r, jl, i, a.invd);
+        const double tv = bi_apply_scaled<UNIT, true>(a, a.r, jl, i);
         a.t[cell(s, jl, i)] = tv;
         ts += tv * a.r[cell(s, jl, i)];
         tt += tv * tv;
@@ -181,8 +197,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_bicgstab(BiArgs a) {
         const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
         const int jg = s.row0 + jl;
         const bool ring = (i == 0) || (i == s.nx - 1) || (jg == 0) || (jg == s.nyg - 1);
-        const double m = ring ? 1.0 : a.invd;
         const size_t o = cell(s, jl, i);
+        const double m = bi_scale(a, ring, o);
         const double sv = a.r[o];
         double xv = a.x[o] + alpha * (m * a.p[o]);
         xv = xv + omega * (m * sv);
@@ -207,7 +223,121 @@ __global__ void __launch_bounds__(CG_THREADS) k_bicgstab(BiArgs a) {
   double res = 0.0;
   for (long long k = first_cell; k < ncell; k += stride) {
     const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
-    const double d = a.b[cell(s, jl, i)] - bi_apply_scaled<UNIT>(a, a.x, jl, i, 1.0);   // plain A x (1.0 * w is exact)
+    const double d = a.b[cell(s, jl, i)] - bi_apply_scaled<UNIT, false>(a, a.x, jl, i);   // plain A x
+    res += d * d;
+  }
+  res = block_sum(res, sm);
+  if (tid == 0) P6[bid] = res;
+  grid.sync();
+  res = fold_partials(P6, G, sm);
+  if (bid == 0 && tid == 0) {
+    a.scal[S_INFO] = (double)info;
+    a.scal[S_ITERS] = (double)iters;
+    a.scal[S_RR] = rr;
+    a.scal[S_BB] = bb;
+    a.scal[S_RES_SUMSQ] = res;
+    a.scal[S_X0] = a.x[cell(s, 0, 0)];
+  }
+}
+
+// ---- CG on the pinned operator with a caller-supplied diagonal preconditioner ------------------------------
+// scipy's cg recurrence exactly as in pf_cg_generic.cuh (x0 = 0, strict test at the top of the loop, info =
+// maxiter when exhausted), z = minv * r read from an array instead of the analytic ring-identity diagonal:
+// `solve(A, b, method='cg', M=<any diagonal operator>)` of the linear-solve seam (interface.py:43).  q = A p is
+// stored in a.v; a.t is unused.
+template <bool UNIT>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_diag(BiArgs a) {
+  namespace cgr = cooperative_groups;
+  cgr::grid_group grid = cgr::this_grid();
+  __shared__ double sm[32];
+  const Slab& s = a.s;
+  const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+  const long long ncell = (long long)s.nx * s.nyl;
+  const long long stride = (long long)G * CG_THREADS;
+  const long long first_cell = (long long)bid * CG_THREADS + tid;
+  double* const P0 = a.part;
+  double* const P1 = a.part + 1 * CG_MAX_GRID;
+  double* const P2 = a.part + 2 * CG_MAX_GRID;
+  double* const P5 = a.part + 5 * CG_MAX_GRID;
+  double* const P6 = a.part + 6 * CG_MAX_GRID;
+
+  double v0 = 0.0, v1 = 0.0;                            // x = 0, r = b, ||b||^2, b.(M b)
+  for (long long k = first_cell; k < ncell; k += stride) {
+    const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
+    const int jg = s.row0 + jl;
+    const bool ring = (i == 0) || (i == s.nx - 1) || (jg == 0) || (jg == s.nyg - 1);
+    const size_t o = cell(s, jl, i);
+    const double bv = a.b[o];
+    a.x[o] = 0.0;
+    a.r[o] = bv;
+    v0 += bv * bv;
+    v1 += bv * (bi_scale(a, ring, o) * bv);
+  }
+  v0 = block_sum(v0, sm);
+  v1 = block_sum(v1, sm);
+  if (tid == 0) { P6[bid] = v0; P5[bid] = v1; }
+  grid.sync();
+  const double bb = fold_partials(P6, G, sm);
+  double rho = fold_partials(P5, G, sm);
+  const double bnorm = sqrt(bb);
+  const double t0 = a.tol * bnorm;
+  const double atol = (t0 > 0.0) ? t0 : 0.0;
+  double rr = bb, rho_prev = 0.0;
+  int iters = 0, info = a.maxiter;
+  if (bnorm == 0.0) {
+    info = 0;
+  } else {
+    for (int it = 0; it < a.maxiter; ++it) {
+      if (sqrt(rr) < atol) { info = 0; break; }
+      const double beta = (it == 0) ? 0.0 : rho / rho_prev;
+      for (long long k = first_cell; k < ncell; k += stride) {       // p = z (first) | p = p*beta + z
+        const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
+        const int jg = s.row0 + jl;
+        const bool ring = (i == 0) || (i == s.nx - 1) || (jg == 0) || (jg == s.nyg - 1);
+        const size_t o = cell(s, jl, i);
+        const double z = bi_scale(a, ring, o) * a.r[o];
+        a.p[o] = (it == 0) ? z : (a.p[o] * beta) + z;
+      }
+      grid.sync();
+      double pq = 0.0;
+      for (long long k = first_cell; k < ncell; k += stride) {       // q = A p ; p.q
+        const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
+        const double qv = bi_apply_scaled<UNIT, false>(a, a.p, jl, i);
+        a.v[cell(s, jl, i)] = qv;
+        pq += a.p[cell(s, jl, i)] * qv;
+      }
+      pq = block_sum(pq, sm);
+      if (tid == 0) P0[bid] = pq;
+      grid.sync();
+      pq = fold_partials(P0, G, sm);
+      const double alpha = rho / pq;
+      double arr = 0.0, arz = 0.0;
+      for (long long k = first_cell; k < ncell; k += stride) {       // x += alpha p ; r -= alpha q
+        const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
+        const int jg = s.row0 + jl;
+        const bool ring = (i == 0) || (i == s.nx - 1) || (jg == 0) || (jg == s.nyg - 1);
+        const size_t o = cell(s, jl, i);
+        a.x[o] = a.x[o] + alpha * a.p[o];
+        const double rn = a.r[o] - alpha * a.v[o];
+        a.r[o] = rn;
+        arr += rn * rn;
+        arz += rn * (bi_scale(a, ring, o) * rn);
+      }
+      arr = block_sum(arr, sm);
+      arz = block_sum(arz, sm);
+      if (tid == 0) { P1[bid] = arr; P2[bid] = arz; }
+      grid.sync();
+      rr = fold_partials(P1, G, sm);
+      rho_prev = rho;
+      rho = fold_partials(P2, G, sm);
+      ++iters;
+    }
+  }
+  grid.sync();
+  double res = 0.0;                                      // true residual ||b - A x||^2 (interface.py:48-49)
+  for (long long k = first_cell; k < ncell; k += stride) {
+    const int jl = (int)(k / s.nx), i = (int)(k % s.nx);
+    const double d = a.b[cell(s, jl, i)] - bi_apply_scaled<UNIT, false>(a, a.x, jl, i);
     res += d * d;
   }
   res = block_sum(res, sm);

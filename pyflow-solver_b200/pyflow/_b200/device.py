@@ -256,6 +256,19 @@ class DeviceSlab:
                                             C.byref(iters), C.byref(rnorm), self._stream()), self.ctx, "pf_op_bicgstab")
         return x, info.value, iters.value, rnorm.value
 
+    def krylov_diag(self, method: str, b, inv_diag, dx, dy, tol, maxiter):
+        """CG ('cg') or BiCGSTAB (anything else, as in the reference) on the pinned operator with a caller-supplied
+        diagonal preconditioner: ``inv_diag`` (ny, nx) are the entries M applies.  Returns like ``pcg``."""
+        b = self._dense(b)
+        d = self._dense(inv_diag)
+        x = np.empty_like(b)
+        info, iters, rnorm = C.c_int(), C.c_int(), C.c_double()
+        _lib.check(self._lib.pf_op_krylov_diag(self.ctx, 0 if method == "cg" else 1, _ptr(b), _ptr(d), _ptr(x),
+                                               float(dx), float(dy), float(tol), int(maxiter), C.byref(info),
+                                               C.byref(iters), C.byref(rnorm), self._stream()),
+                   self.ctx, "pf_op_krylov_diag")
+        return x, info.value, iters.value, rnorm.value
+
     def cg_generic(self, mode: str, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=1.0, want_x=True):
         """Reference-order CG with the plain (q stored) kernel.  mode 'pinned' | 'dirichlet'.
         The solution stays in the context's p field.  Returns (x|None, info, iters, ||b-Ax||, ||b||)."""

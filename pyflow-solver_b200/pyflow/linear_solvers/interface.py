@@ -10,7 +10,11 @@ recurrence (x0 = 0, strict ``||r|| < tol*||b||`` test at the top of each
 iteration, info = maxiter when exhausted) on the device; ``method='bicgstab'``
 (the signature's default, interface.py:23,44-45; no call site in the reference
 asks for it) runs scipy's BiCGSTAB recurrence, exit codes included, in
-``k_bicgstab``.  Anything else raises: there is no CPU fallback.
+``k_bicgstab``.  ``M`` may be the ring-identity Jacobi descriptor, any diagonal
+(``DiagonalJacobi``), or a foreign operator object that proves to be diagonal
+(``preconditioners.probe_diagonal``); general diagonals run in ``k_cg_diag`` /
+``k_bicgstab`` from an array of inverse entries.  Anything else raises: there is
+no CPU fallback.
 """
 from __future__ import annotations
 
@@ -20,7 +24,7 @@ from typing import Literal
 import numpy as np
 
 from .._b200.device import slab_for_shape
-from .preconditioners import resolve
+from .preconditioners import RingJacobi, classify
 
 
 @dataclass(slots=True)
@@ -63,13 +67,17 @@ def solve(A, b, method: Literal["cg", "bicgstab"] = "bicgstab", tol: float = 1e-
     if kwargs:
         raise TypeError(f"unsupported solver arguments: {sorted(kwargs)}")
     if M is not None:
-        M = resolve(M, A.nx, A.ny)          # RingJacobi, or the diagonal of assemble_negative_laplacian; else raises
+        M = classify(M, A.nx, A.ny)         # RingJacobi (analytic) or a general diagonal; non-diagonal operators raise
     b = np.asarray(b, dtype=np.float64)
     slab = slab_for_shape(A.ny, A.nx)
     # like the reference, anything that is not 'cg' takes the bicgstab branch (interface.py:42-45)
-    run = slab.pcg if method == "cg" else slab.bicgstab
-    x, info, _iters, rnorm = run(b.reshape(A.ny, A.nx), A.dx, A.dy, tol, maxiter, jacobi=M is not None,
-                                 inv_diag_interior=(M.inv_diag_interior if M is not None else 1.0))
+    if M is None or isinstance(M, RingJacobi):
+        run = slab.pcg if method == "cg" else slab.bicgstab
+        x, info, _iters, rnorm = run(b.reshape(A.ny, A.nx), A.dx, A.dy, tol, maxiter, jacobi=M is not None,
+                                     inv_diag_interior=(M.inv_diag_interior if M is not None else 1.0))
+    else:
+        x, info, _iters, rnorm = slab.krylov_diag(method, b.reshape(A.ny, A.nx), M.inv_diag.reshape(A.ny, A.nx),
+                                                  A.dx, A.dy, tol, maxiter)
     bnorm = float(np.linalg.norm(b)) or 1.0
     converged = (info == 0) and (rnorm <= tol * bnorm)
     iterations = info if info > 0 else 0

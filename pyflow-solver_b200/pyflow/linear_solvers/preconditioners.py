@@ -15,8 +15,16 @@ preconditioner is a DESCRIPTOR, not an operator:
   ``DiagonalJacobi``; at solve time it is accepted if it IS the ring-identity
   diagonal of the grid being solved (checked value by value), i.e. for the
   matrix ``assemble_negative_laplacian`` returns;
-* any other diagonal, and arbitrary ``LinearOperator`` objects, raise
-  ``NotImplementedError``: there is no host path to fall back to.
+* a foreign operator object (``scipy.sparse.linalg.LinearOperator``, e.g. what the
+  reference's own ``jacobi_preconditioner`` returns, or anything with ``matvec``
+  and ``shape``) is PROBED: ``d = M(1)``, then ``M(v) == d * v`` bit for bit on two
+  fixed pseudo-random vectors.  A diagonal operator becomes a ``DiagonalJacobi``;
+* the linear-solve seam (``interface.solve``) runs ANY diagonal on the device
+  (``k_cg_diag`` / ``k_bicgstab`` read the inverse entries from an array);
+  ``solve_pressure_poisson`` -- the fused time-step path -- applies the
+  ring-identity diagonal only and refuses the others;
+* operators that are not diagonal raise ``NotImplementedError``: they exist only
+  as host callables and there is no host path to fall back to.
 """
 from __future__ import annotations
 
@@ -95,18 +103,56 @@ def jacobi_preconditioner(A):
         "general LinearOperators have no diagonal to read and there is no CPU fallback")
 
 
-def resolve(preconditioner, nx: int, ny: int) -> RingJacobi:
-    """What the device can apply for ``preconditioner`` on an ``ny x nx`` grid, or NotImplementedError."""
+def probe_diagonal(op, n: int) -> DiagonalJacobi | None:
+    """``DiagonalJacobi`` of a foreign operator object if it acts as a diagonal matrix on R^n, else ``None``.
+    The entries are ``op(1)``; diagonality is accepted when ``op(v) == op(1) * v`` BIT FOR BIT on two fixed
+    pseudo-random vectors (what ``lambda x: invD * x`` -- the reference's preconditioners.py:20-21 -- satisfies;
+    an operator with any off-diagonal coupling does not)."""
+    apply = getattr(op, "matvec", None) or (op if callable(op) else None)
+    shape = getattr(op, "shape", None)
+    if apply is None or shape is None or tuple(shape) != (n, n):
+        return None
+    try:
+        d = np.asarray(apply(np.ones(n)), dtype=np.float64).reshape(-1)
+        if d.shape != (n,):
+            return None
+        rng = np.random.default_rng(20250117)
+        for _ in range(2):
+            v = rng.standard_normal(n) * np.exp(rng.uniform(-3.0, 3.0, n))
+            got = np.asarray(apply(v.copy()), dtype=np.float64).reshape(-1)
+            if got.shape != (n,) or not np.array_equal(got, d * v, equal_nan=True):
+                return None
+    except Exception:
+        return None
+    return DiagonalJacobi(d)
+
+
+def classify(preconditioner, nx: int, ny: int) -> RingJacobi | DiagonalJacobi:
+    """The device form of ``preconditioner`` on an ``ny x nx`` grid: ``RingJacobi`` (analytic, every CG kernel),
+    or a general ``DiagonalJacobi`` (array form, the generic Krylov kernels of the linear-solve seam).
+    NotImplementedError for operators that are not diagonal."""
     if isinstance(preconditioner, RingJacobi):
         return preconditioner
-    if isinstance(preconditioner, DiagonalJacobi):
-        ring = preconditioner.as_ring(nx, ny)
-        if ring is not None:
-            return ring
-        raise NotImplementedError(
-            "this diagonal preconditioner is not the ring-identity Jacobi diagonal of the grid being solved "
-            "(1 on the boundary ring, one value inside); only that one is applied on the device")
+    if not isinstance(preconditioner, DiagonalJacobi):
+        found = probe_diagonal(preconditioner, nx * ny)
+        if found is None:
+            raise NotImplementedError(
+                "this preconditioner is not a diagonal operator on the grid being solved; only diagonal "
+                "preconditioners have a device form (there is no CPU fallback)")
+        preconditioner = found
+    if preconditioner.inv_diag.shape != (nx * ny,):
+        raise NotImplementedError(f"diagonal preconditioner of size {preconditioner.inv_diag.shape[0]} on a "
+                                  f"{ny} x {nx} grid")
+    return preconditioner.as_ring(nx, ny) or preconditioner
+
+
+def resolve(preconditioner, nx: int, ny: int) -> RingJacobi:
+    """The ring-identity Jacobi descriptor of ``preconditioner`` -- what the fused time-step path applies -- or
+    NotImplementedError."""
+    found = classify(preconditioner, nx, ny)
+    if isinstance(found, RingJacobi):
+        return found
     raise NotImplementedError(
-        "only the ring-identity Jacobi preconditioner (jacobi_preconditioner of the pinned operator or of "
-        "assemble_negative_laplacian) or None runs on the device; arbitrary LinearOperator preconditioners are "
-        "not supported (SURVEY.md 8f item 2)")
+        "this diagonal preconditioner is not the ring-identity Jacobi diagonal of the grid being solved "
+        "(1 on the boundary ring, one value inside); the projection step applies only that one "
+        "(linear_solvers.solve runs general diagonals)")

@@ -204,6 +204,19 @@ class CpuSlab:
         self.p[:] = x.reshape(ny, nx)
         return x.reshape(ny, nx), int(info), int(iters), rnorm
 
+    def krylov_diag(self, method, b, inv_diag, dx, dy, tol, maxiter):
+        b, d = self._dense(b), self._dense(inv_diag)
+        ny, nx = b.shape
+
+        def A(xv):
+            return orc.neg_laplacian_pinned(xv, nx, ny, dx, dy)
+
+        rhs = b.reshape(-1).copy()
+        x, info, iters = (orc.pcg if method == "cg" else orc.bicgstab)(A, rhs, tol, maxiter, d.reshape(-1).copy())
+        x = np.array(x, dtype=np.float64)
+        self.p[:] = x.reshape(ny, nx)
+        return x.reshape(ny, nx), int(info), int(iters), float(np.sqrt(_norm2(rhs - A(x))))
+
     def bicgstab(self, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=None):
         return self.pcg(b, dx, dy, tol, maxiter, jacobi, inv_diag_interior, _krylov=orc.bicgstab)
 

@@ -592,7 +592,8 @@ def test_cli_keyboard_interrupt_writes_final_checkpoint_and_returns_130(slab_cls
 def test_reference_recipe_for_the_jacobi_preconditioner_is_recognised(slab_cls):
     """pressure_solver.py:139-143 builds M as jacobi_preconditioner(csr(assemble_negative_laplacian(...))): that
     object (a diagonal read off the assembled matrix) is accepted when it IS the ring-identity diagonal of the grid
-    being solved; other diagonals and generic operators are refused -- there is no host path."""
+    being solved.  Foreign operator objects are probed for diagonality; general diagonals run through the array-form
+    kernels of the linear-solve seam; operators that are not diagonal are refused -- there is no host path."""
     import scipy.sparse as sp
     from pyflow.core.ghost_fields import allocate_state, interior_view
     from pyflow.linear_solvers.interface import NegLaplacianPinned, solve
@@ -607,10 +608,15 @@ def test_reference_recipe_for_the_jacobi_preconditioner_is_recognised(slab_cls):
     assert M.as_ring(ny, nx) is None and M.as_ring(nx, ny + 1) is None
     assert np.array_equal(M.inv_diag, orc.jacobi_inverse_diagonal(nx, ny, dx, dy))
     cfg = SimpleNamespace(lin_tol=1e-10, lin_maxiter=300, diagnostics=False, enable_jacobi_pc=False)
+
+    def _seeded(nx_, ny_):
+        st_ = allocate_state(nx_, ny_)
+        interior_view(st_.fields["u"])[ny_ // 3, nx_ // 3] = 1.0
+        return st_
+
     results = []
     for pre in (M, None):
-        st = allocate_state(nx, ny)
-        interior_view(st.fields["u"])[ny // 3, nx // 3] = 1.0
+        st = _seeded(nx, ny)
         c = cfg if pre is not None else SimpleNamespace(**{**vars(cfg), "enable_jacobi_pc": True})
         results.append(solve_pressure_poisson(st, 0.01, dx, dy, c, preconditioner=pre)[0])
     assert np.array_equal(results[0], results[1])
@@ -627,7 +633,33 @@ def test_reference_recipe_for_the_jacobi_preconditioner_is_recognised(slab_cls):
     with pytest.raises(NotImplementedError):
         solve_pressure_poisson(allocate_state(nx, ny), 0.01, dx, dy, cfg, preconditioner=other)
     with pytest.raises(NotImplementedError):
-        solve(op, b, method="cg", M=jacobi_preconditioner(sp.identity(nx * ny, format="csr") * 2.0))
-    with pytest.raises(NotImplementedError):
         jacobi_preconditioner(lambda x: x)
+    # ---- user-supplied operators ("accepts external M LinearOperator") are probed for diagonality
+    import scipy.sparse.linalg as spla
+    from pyflow.linear_solvers.preconditioners import RingJacobi as Ring, classify, probe_diagonal
+    n = nx * ny
+    invd = orc.jacobi_inverse_diagonal(nx, ny, dx, dy)
+    ref_style = spla.LinearOperator((n, n), matvec=lambda x: invd * x)        # reference preconditioners.py:20-25
+    assert isinstance(classify(ref_style, nx, ny), Ring)
+    r3 = solve(op, b, method="cg", tol=1e-10, maxiter=3000, M=ref_style)
+    assert np.array_equal(r3.x, r2.x)                                         # ring diagonal -> the tuned CG kernels
+    p3 = solve_pressure_poisson(_seeded(nx, ny), 0.01, dx, dy, cfg, preconditioner=ref_style)[0]
+    assert np.array_equal(p3, results[0])
+    # a general diagonal runs through the array-form kernels of the seam (both methods)
+    gen = spla.LinearOperator((n, n), matvec=lambda x: other.inv_diag * x)
+    for method, krylov in (("cg", orc.pcg), ("bicgstab", orc.bicgstab)):
+        for Mx in (other, gen, jacobi_preconditioner(sp.diags(1.0 / other.inv_diag, format="csr"))):
+            rg = solve(op, b, method=method, tol=1e-10, maxiter=9, M=Mx)
+            xo, info, _ = krylov(lambda t: orc.neg_laplacian_pinned(t, nx, ny, dx, dy), b.copy(), 1e-10, 9,
+                                 probe_diagonal(gen, n).inv_diag)
+            assert rg.iterations == info == 9 and np.linalg.norm(rg.x - xo) <= 1e-12 * np.linalg.norm(xo)
+    # operators that are not diagonal have no device form
+    coupled = sp.diags([np.full(n - 1, 0.1), np.ones(n)], [1, 0], format="csr")
+    for bad in (spla.aslinearoperator(coupled), spla.LinearOperator((n, n), matvec=lambda x: np.roll(x, 1)),
+                spla.LinearOperator((n - 1, n - 1), matvec=lambda x: x)):
+        assert probe_diagonal(bad, n) is None
+        with pytest.raises(NotImplementedError):
+            solve(op, b, method="cg", M=bad)
+        with pytest.raises(NotImplementedError):
+            solve_pressure_poisson(allocate_state(nx, ny), 0.01, dx, dy, cfg, preconditioner=bad)
     assert jacobi_preconditioner(sp.identity(4, format="csr")).as_ring(2, 2).inv_diag_interior == 0.25

@@ -327,7 +327,7 @@ def emu(tmp_path_factory):
     lib.emu_divc_stats.argtypes = [i, i, dp, dp, d, d, i, dp, dp]
     lib.emu_cg_generic.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     lib.emu_cg_persistent.argtypes = [i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp]
-    lib.emu_bicgstab.argtypes = [i, i, dp, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
+    lib.emu_krylov.argtypes = [i, i, i, dp, dp, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     lib.emu_cg_split.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp, dp]
     lib.emu_cg_small.argtypes = [i, i, i, dp, dp, dp, dp, dp, C.POINTER(C.c_ulonglong), d, d, d, d, i]
     lib.emu_cg_tmad.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp, C.POINTER(C.c_ulonglong)]
@@ -584,8 +584,8 @@ def test_bicgstab_kernel_vs_reference_golden(emu, tag):
     x, r, p, v, t = (dev.put() for _ in range(5))
     part = np.zeros(emu.emu_cg_part_doubles())
     invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2) if jac else 1.0
-    emu.emu_bicgstab(nx, ny, ptr(dev.put(b)), ptr(x), ptr(r), ptr(p), ptr(v), ptr(t), dx, dy, invd, tol, maxiter,
-                     ptr(part), ptr(S.scal))
+    emu.emu_krylov(1, nx, ny, ptr(dev.put(b)), None, ptr(x), ptr(r), ptr(p), ptr(v), ptr(t), dx, dy, invd, tol,
+                   maxiter, ptr(part), ptr(S.scal))
     xs, info, iters, rnorm = dev.get(x).ravel(), int(S["S_INFO"]), int(S["S_ITERS"]), S["S_RES_SUMSQ"] ** 0.5
     conv_ref, its_ref, rnorm_ref, done_ref = g["result"]
     bnorm = float(np.linalg.norm(g["b"])) or 1.0
@@ -603,6 +603,34 @@ def test_bicgstab_kernel_vs_reference_golden(emu, tag):
         # 2 tol ||b|| / sigma_min(A)  (sigma_min of the pinned operator on these grids > 1e-3)
         assert np.linalg.norm(xs - g["x"]) <= 2.0 * tol * bnorm / 1e-3
         assert abs(iters - int(done_ref)) <= max(3, int(0.25 * done_ref))
+
+
+@pytest.mark.parametrize("method,shape,unit,maxiter", [(0, (9, 13), True, 9), (1, (9, 13), True, 9),
+                                                       (0, (12, 7), False, 3000), (1, (12, 7), False, 3000)])
+def test_krylov_kernels_with_a_user_supplied_diagonal(emu, method, shape, unit, maxiter):
+    """k_cg_diag / k_bicgstab reading the preconditioner's inverse entries from an array (a user-supplied diagonal
+    M of the linear-solve seam) against the oracle recurrences with the same diagonal."""
+    ny, nx = shape
+    rng = np.random.default_rng(17 * ny + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.5, 0.25)
+    b = rng.standard_normal(shape)
+    b -= b.mean()
+    b[0, 0] = 0.0
+    minv = rng.uniform(0.05, 1.0, shape)
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    x, r, p, v, t = (dev.put() for _ in range(5))
+    part = np.zeros(emu.emu_cg_part_doubles())
+    emu.emu_krylov(method, nx, ny, ptr(dev.put(b)), ptr(dev.put(minv)), ptr(x), ptr(r), ptr(p), ptr(v), ptr(t), dx, dy,
+                   1.0, 1e-10, maxiter, ptr(part), ptr(S.scal))
+    xs, info, iters, rnorm = dev.get(x).ravel(), int(S["S_INFO"]), int(S["S_ITERS"]), S["S_RES_SUMSQ"] ** 0.5
+    A = lambda z_: orc.neg_laplacian_pinned(z_, nx, ny, dx, dy)          # noqa: E731
+    xo, io, to = (orc.bicgstab if method else orc.pcg)(A, b.ravel().copy(), 1e-10, maxiter, minv.ravel().copy())
+    assert info == io and close(rnorm, float(np.linalg.norm(b.ravel() - A(xs))), 1e-6)
+    if maxiter < 100:
+        assert iters == to == maxiter and np.linalg.norm(xs - xo) <= 1e-11 * np.linalg.norm(xo)
+    else:
+        assert info == 0 and rnorm <= 1e-10 * np.linalg.norm(b)
+        assert np.linalg.norm(xs - xo) <= 1e-6 * np.linalg.norm(xo) and abs(iters - to) <= max(3, to // 4)
 
 
 def test_plain_cg_kernel_dirichlet_mode_vs_oracle(emu):
