@@ -47,7 +47,9 @@ struct Team {                       // one block executing with one OS thread pe
 extern Team team;                   // the block of a one-block-at-a-time launch
 extern thread_local Team* mine;     // the block this OS thread belongs to
 inline void block_sync() { if (mine->threaded) pthread_barrier_wait(&mine->block); }
-inline void grid_sync() { block_sync(); }          // cg::grid_group: only used on grids of one block here
+extern pthread_barrier_t* grid_barrier;   // all threads of ALL blocks of a concurrently running grid, or null
+// cg::grid_group::sync(): a real grid-wide barrier when the launcher set one up, else the grid is one block
+inline void grid_sync() { if (grid_barrier) pthread_barrier_wait(grid_barrier); else block_sync(); }
 inline double shuffle(double v, int src_lane) {
   Team& t_ = *mine;
   if (!t_.threaded) return v;

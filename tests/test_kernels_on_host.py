@@ -290,6 +290,29 @@ def generate_multi_kernel_copy(dest_dir):
         fh.write(MULTI_HEAD + sec + "\n}  // namespace emu_multi\n}  // namespace pf\n")
 
 
+def generate_bicgstab_kernel_copy(dest_dir):
+    """pf_bicgstab.cuh again, in namespace pf::emu_bi with per-block storage for its `__shared__` arrays, so that
+    several CTAs of k_bicgstab / k_cg_diag can run at once in one process (emu_krylov_grid)."""
+    import re
+    src = open(os.path.join(ROOT, "pyflow-solver_b200", "csrc", "pf_bicgstab.cuh")).read()
+    for old, new in (("#pragma once", ""), ("namespace pf {", "namespace pf {\nnamespace emu_bi {"),
+                     ("}  // namespace pf", "}  // namespace emu_bi\n}  // namespace pf")):
+        assert src.count(old) == 1, f"pf_bicgstab.cuh changed: {old!r} occurs {src.count(old)} times"
+        src = src.replace(old, new)
+    counter = [0]
+
+    def per_block(m):
+        counter[0] += 1
+        indent, ctype, name, dims, rest = m.groups()
+        return (f"{indent}auto& {name} = *reinterpret_cast<{ctype}(*){dims}>"
+                f"(emu::shared_slot({counter[0]}, sizeof({ctype}{dims})));{rest}")
+
+    src = re.sub(r"^(\s*)__shared__\s+([A-Za-z_][\w ]*?)\s+(\w+)((?:\[[^\]]+\])*);(.*)$", per_block, src, flags=re.M)
+    assert "__shared__" not in src and counter[0] == 2, counter[0]
+    with open(os.path.join(dest_dir, "pf_bicgstab_emu.cuh"), "w") as fh:
+        fh.write(src)
+
+
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     build = str(tmp_path_factory.mktemp("hostemu"))
@@ -297,8 +320,9 @@ def emu(tmp_path_factory):
     generate_small_kernel_copy(build)
     generate_tma_kernel_copy(build)
     generate_multi_kernel_copy(build)
+    generate_bicgstab_kernel_copy(build)
     cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DPF_HOST_EMULATION", "-DPF_EMU_WITH_SMALL",
-           "-DPF_EMU_WITH_TMA", "-DPF_EMU_WITH_MULTI", "-pthread",
+           "-DPF_EMU_WITH_TMA", "-DPF_EMU_WITH_MULTI", "-DPF_EMU_WITH_BICG", "-pthread",
            "-fPIC", "-shared", "-I", build,
            "-I", os.path.join(ROOT, "tests", "hostemu"), "-I", os.path.join(ROOT, "pyflow-solver_b200", "csrc"),
            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "hostemu", "emu_kernels.cpp"), "-o", out]
@@ -328,6 +352,7 @@ def emu(tmp_path_factory):
     lib.emu_cg_generic.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     lib.emu_cg_persistent.argtypes = [i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp]
     lib.emu_krylov.argtypes = [i, i, i, dp, dp, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
+    lib.emu_krylov_grid.argtypes = [i] + lib.emu_krylov.argtypes
     lib.emu_cg_split.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp, dp]
     lib.emu_cg_small.argtypes = [i, i, i, dp, dp, dp, dp, dp, C.POINTER(C.c_ulonglong), d, d, d, d, i]
     lib.emu_cg_tmad.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp, C.POINTER(C.c_ulonglong)]
@@ -631,6 +656,39 @@ def test_krylov_kernels_with_a_user_supplied_diagonal(emu, method, shape, unit, 
     else:
         assert info == 0 and rnorm <= 1e-10 * np.linalg.norm(b)
         assert np.linalg.norm(xs - xo) <= 1e-6 * np.linalg.norm(xo) and abs(iters - to) <= max(3, to // 4)
+
+
+@pytest.mark.parametrize("method,jacobi", [(1, True), (0, False), (1, False)])
+def test_krylov_kernels_on_three_ctas_at_once(emu, method, jacobi):
+    """k_bicgstab / k_cg_diag on a cooperative grid of THREE blocks executing concurrently (768 OS threads, a real
+    grid-wide barrier): per-CTA partials folded in CTA order by every CTA, single-use partial slots, identical
+    exits in all CTAs.  Truncated solves against the oracle recurrences (summation order only); the analytic ring
+    diagonal (minv = NULL) for BiCGSTAB, a user-supplied diagonal array otherwise."""
+    ny, nx = 24, 37                                        # 888 cells on 768 threads: ragged last stride
+    rng = np.random.default_rng(91 + method)
+    b = rng.standard_normal((ny, nx))
+    b -= b.mean()
+    b[0, 0] = 0.0
+    dx, dy = 0.5, 0.25
+    if jacobi:
+        minv, invd = None, 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)
+        diag = orc.jacobi_inverse_diagonal(nx, ny, dx, dy)
+    else:
+        minv, invd = rng.uniform(0.05, 1.0, (ny, nx)), 1.0
+        diag = minv.ravel().copy()
+    if not emu.emu_thread_probe(3 * 256):
+        pytest.skip("this machine cannot run 768 OS threads at once")
+    dev, S = Dev(emu, ny, nx), Scalars(emu)
+    x, r, p, v, t = (dev.put() for _ in range(5))
+    part = np.full(emu.emu_cg_part_doubles(), np.nan)      # a slot read before it was written would poison the sums
+    emu.emu_krylov_grid(3, method, nx, ny, ptr(dev.put(b)), None if minv is None else ptr(dev.put(minv)), ptr(x),
+                        ptr(r), ptr(p), ptr(v), ptr(t), dx, dy, invd, 1e-10, 8, ptr(part), ptr(S.scal))
+    xs, info, iters = dev.get(x).ravel(), int(S["S_INFO"]), int(S["S_ITERS"])
+    A = lambda z_: orc.neg_laplacian_pinned(z_, nx, ny, dx, dy)          # noqa: E731
+    xo, io, to = (orc.bicgstab if method else orc.pcg)(A, b.ravel().copy(), 1e-10, 8, diag)
+    assert info == io == 8 and iters == to == 8
+    assert np.linalg.norm(xs - xo) <= 1e-11 * np.linalg.norm(xo)
+    assert close(S["S_RES_SUMSQ"] ** 0.5, float(np.linalg.norm(b.ravel() - A(xs))), 1e-6)
 
 
 def test_plain_cg_kernel_dirichlet_mode_vs_oracle(emu):
