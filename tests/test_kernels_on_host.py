@@ -600,6 +600,8 @@ def test_bicgstab_kernel_vs_reference_golden(emu, tag):
     with its solution to the accuracy the tolerance allows; exit bookkeeping (iterations = info if info > 0) equal."""
     import os
     from conftest import GOLDEN
+    if tag == "33x17_jacobi_nonunit" and os.environ.get("PYFLOW_SLOW_HOSTEMU") != "1":
+        pytest.skip("688 emulated iterations (45 s): PYFLOW_SLOW_HOSTEMU=1 runs it; the GPU and oracle suites keep the case")
     with np.load(os.path.join(GOLDEN, "bicgstab.npz")) as z:
         g = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(tag + "/")}
     nx, ny, dx, dy, jac, tol, maxiter = g["params"]
