@@ -9,6 +9,8 @@ for what in "$@"; do
   case "$what" in
     tests)        # parity suite
       python -m pytest tests -m gpu -x -q 2>&1 | tee gpurun_out/gpu_tests.log | tail -5 ;;
+    newtests)     # the -m gpu tests written after round 1's GPU minutes were spent: first run on a B200, verbose
+      python -m pytest tests/test_zz_gpu_more_parity.py -m gpu -v -k "not legacy" 2>&1 | tee gpurun_out/gpu_new_tests.log | tail -40 ;;
     bench)        # headline line + config 2 alone
       python bench.py > gpurun_out/bench_cavity4096.json 2> gpurun_out/bench_cavity4096.err
       python bench.py --workload cavity512 --steps 50 --no-cpu-baseline > gpurun_out/bench_cavity512.json ;;
@@ -49,6 +51,6 @@ for what in "$@"; do
       done ;;
     reference)    # the CPU arm on the box's host cores
       python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_arm.json ;;
-    *) echo "unknown target $what (tests bench launches full4096 full512 sanitize scaling reference)"; exit 2 ;;
+    *) echo "unknown target $what (tests newtests bench launches full4096 full512 sanitize scaling reference)"; exit 2 ;;
   esac
 done
