@@ -5,17 +5,20 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 Metric (BASELINE.json): MLUPS per projection step = nx * ny_global * steps / seconds / 1e6.
-A "step" is one full projection time step (predictor, RHS, <=300 Jacobi-PCG
+A "step" is one full projection time step (predictor, RHS, <= lin_maxiter Jacobi-PCG
 iterations, correction, lid BC, residual pass) of the lid-driven cavity started
 from rest -- no RNG anywhere on this path, so the data are "synthetic" by
 construction.
 
 Workloads (BASELINE.json configs):
-  cavity4096  4096 x 4096 rows PER GPU, Re=1000, QUICK, lin_maxiter=300  (config 3; default;
-              with N GPUs the global grid is 4096 x 4096N row slabs: weak scaling)
-  cavity512   512 x 512, Re=1000 (config 2; L2-resident, latency-bound)
-  strong8192  8192 x 8192 total, Re=5000, rows split over N GPUs (config 4; strong)
-  weak16384   16384 x 16384 rows per GPU, Re=1000 (config 5; weak)
+  cavity4096       4096 x 4096 rows PER GPU, Re=1000, QUICK, lin_maxiter=300  (config 3; default;
+                   with N GPUs the global grid is 4096 x 4096N row slabs: weak scaling)
+  cavity512        512 x 512, Re=1000 (config 2; shared-memory resident, latency-bound)
+  strong8192       8192 x 8192 total, Re=5000, rows split over N GPUs (config 4; strong)
+  weak16384        16384 x 16384 rows per GPU, Re=1000, lin_maxiter=300 (config 5 geometry; weak)
+  weak16384_tight  the same slabs with the spec's tight-tolerance regime: lin_tol=1e-10 and
+                   lin_maxiter=10000 (the model cap, reference config/model.py:28) -- 20 000
+                   exchanges per step
 
 One JSON line on stdout from rank 0.  `value` is device-resident stepping
 through the public `step()`; `e2e` is the same metric through
@@ -24,12 +27,17 @@ back on the host, copies inside the timed region.  `roofline` is the CG kernel:
 algorithmic bytes (64 B per cell per CG iteration) / its CUDA-event
 duration, against MEASURED_PEAKS.json.  `cpu_baseline` (and `--impl reference`)
 is the C / OpenMP restatement of the reference algorithm (oracle/pyflow_oracle.c)
-on a bounded sample on all of this box's host cores; the single-threaded numpy
-oracle is reported beside it.
+on every host core of this box.  `parity` is an UNTIMED block after the timed
+regions: the CUDA path against that oracle on the workload's own grid (one GPU)
+and on slab cases at every GPU count; a failed parity check makes the exit code 1.
+`other_configs` carries BASELINE configs 2, 4 and 5 (device-resident, few steps)
+at the same GPU count, so that a 1/2/4/8 sweep of the default command records the
+strong- and weak-scaling lines as well.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -44,11 +52,12 @@ for _p in (os.path.join(ROOT, "pyflow-solver_b200"), os.path.join(ROOT, "oracle"
         sys.path.insert(0, _p)
 
 WORKLOADS = {
-    # name: (nx, ny_per_gpu or total, Re, scaling, description)
+    # name: nx, ny (per GPU or total), Re, scaling
     "cavity4096": dict(nx=4096, ny=4096, Re=1000.0, scaling="weak", per_gpu=True),
     "cavity512": dict(nx=512, ny=512, Re=1000.0, scaling="weak", per_gpu=True),
     "strong8192": dict(nx=8192, ny=8192, Re=5000.0, scaling="strong", per_gpu=False),
     "weak16384": dict(nx=16384, ny=16384, Re=1000.0, scaling="weak", per_gpu=True),
+    "weak16384_tight": dict(nx=16384, ny=16384, Re=1000.0, scaling="weak", per_gpu=True, lin_maxiter=10000),
 }
 CG_BYTES_PER_CELL_ITER = 64.0     # SURVEY.md 8d contract figure
 STEP_BYTES_PER_CELL = 200.0
@@ -58,6 +67,10 @@ def make_cfg(nx, ny, Re, lin_maxiter=300, lin_tol=1e-10):
     return SimpleNamespace(nx=nx, ny=ny, Re=Re, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05,
                            lin_tol=lin_tol, lin_maxiter=lin_maxiter, advection_scheme="quick",
                            disable_advection=False, diagnostics=False)
+
+
+def lin_maxiter_of(args, wl):
+    return int(getattr(args, "lin_maxiter", 0) or wl.get("lin_maxiter", 300))
 
 
 # ------------------------------------------------------------------ clocks
@@ -120,19 +133,62 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def kernel_source_hash() -> str:
+    """sha256 over the CUDA / C-ABI sources the library is built from (csrc/*, include/*.h, build.py).  Recorded
+    next to every ncu traffic figure in profiles/cg_traffic.json, so that bench.py only quotes a `traffic` number
+    that was captured from the kernels it is timing."""
+    h = hashlib.sha256()
+    files = [os.path.join(ROOT, "include", "pyflow_b200.h"), os.path.join(ROOT, "pyflow-solver_b200", "build.py")]
+    csrc = os.path.join(ROOT, "pyflow-solver_b200", "csrc")
+    files += [os.path.join(csrc, f) for f in sorted(os.listdir(csrc))]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def recorded_traffic(workload, kernel):
+    """(bytes per launch or None, provenance note) from profiles/cg_traffic.json."""
+    tpath = os.path.join(ROOT, "profiles", "cg_traffic.json")
+    try:
+        rec = json.load(open(tpath)).get(workload)
+    except Exception:
+        return None, "no profiles/cg_traffic.json"
+    if not isinstance(rec, dict):
+        return None, "no ncu capture recorded for this workload"
+    now = kernel_source_hash()
+    if rec.get("source_hash") != now:
+        return None, (f"ncu capture in profiles/cg_traffic.json is of source hash {rec.get('source_hash')}, the running "
+                      f"library is built from {now}: not quoted")
+    if rec.get("kernel", "").split("<")[0] != kernel.split("<")[0]:
+        return None, f"ncu capture is of {rec.get('kernel')}, the timed kernel is {kernel}: not quoted"
+    return float(rec["dram_bytes_per_launch"]), (f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                                 f"{rec.get('kernel')} launch ({rec.get('report')}), source hash {now}")
+
+
 # ------------------------------------------------------------------ CPU legs (oracle)
-def oracle_sample(n: int, Re: float, lin_maxiter: int, steps: int, warmup: int, impl: str = "c"):
-    """Times `steps` oracle steps (after `warmup`) of an n x n cavity from rest.
+def use_all_host_threads():
+    """The C oracle on every host core, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
+    import pyflow_oracle_c as orc_c
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    orc_c.set_threads(n)
+    return orc_c.threads()
+
+
+def oracle_sample(nx: int, ny: int, Re: float, lin_maxiter: int, steps: int, warmup: int, impl: str = "c"):
+    """Times `steps` oracle steps (after `warmup`) of an nx x ny cavity from rest.
     impl "c": oracle/pyflow_oracle.c on every host core (OpenMP); "numpy": oracle/pyflow_oracle.py.
     Returns (mlups, seconds_per_step, true CG iterations per step)."""
     import pyflow_oracle as orc
     stepper = orc.step
     if impl == "c":
         import pyflow_oracle_c as orc_c
-        ws = orc_c.Workspace(n, n)
+        ws = orc_c.Workspace(nx, ny)
         stepper = lambda cfg, st, it: orc_c.step(cfg, st, it, ws)          # noqa: E731
-    cfg = make_cfg(n, n, Re, lin_maxiter)
-    st = orc.allocate_state(n, n)
+    cfg = make_cfg(nx, ny, Re, lin_maxiter)
+    st = orc.allocate_state(nx, ny)
     it = 0
     for _ in range(max(1, warmup)):          # step 0 from rest has b = 0 (no CG work): never timed
         stepper(cfg, st, it)
@@ -144,63 +200,79 @@ def oracle_sample(n: int, Re: float, lin_maxiter: int, steps: int, warmup: int, 
         iters.append(d["true_iterations"])
         it += 1
     dt = time.perf_counter() - t0
-    return n * n * steps / dt / 1e6, dt / steps, iters
+    return nx * ny * steps / dt / 1e6, dt / steps, iters
 
 
-def cpu_threads():
-    """Host threads the C / OpenMP oracle runs on."""
-    import pyflow_oracle_c as orc_c
-    return orc_c.threads()
-
-
-def sized_oracle_grid(n_max: int, total_steps: int, budget_s: float):
-    """Largest power-of-two-scaled grid <= n_max whose `total_steps` C-oracle steps fit the time budget, from a
-    calibration step at 512^2 (cost scales with cells x CG iterations; large grids leave the caches, hence x2)."""
-    _m, sps, _it = oracle_sample(512, 1000.0, 300, 1, 1)
-    per_cell = sps / (512 * 512) * 2.0
-    n = n_max
-    while n > 512 and n * n * per_cell * total_steps > budget_s:
-        n //= 2
-    return n
+def sized_oracle_rows(nx: int, ny_max: int, Re: float, lin_maxiter: int, total_steps: int, budget_s: float):
+    """Rows of the CPU sample: the workload's own row length always; as many rows (ny_max, ny_max/2, ... >= 256)
+    as `total_steps` C-oracle steps fit into the time budget, from a calibration step on nx x 256 (cost scales
+    with cells x CG iterations; x1.5 because the larger grid leaves the last-level cache)."""
+    cal_rows = min(256, ny_max)
+    cal_it = min(lin_maxiter, 300)
+    _m, sps, _it = oracle_sample(nx, cal_rows, Re, cal_it, 1, 1)
+    per_cell = sps / (nx * cal_rows) * 1.5 * (lin_maxiter / cal_it)
+    rows = ny_max
+    while rows > 256 and nx * rows * per_cell * total_steps > budget_s:
+        rows //= 2
+    return rows
 
 
 def run_reference_arm(args, wl, rank):
     """`--impl reference`: the reference's CPU algorithm for the path on this box's host cores.  The reference
     itself is Python and cannot travel to the box; its restatement oracle/pyflow_oracle.c (pinned through the
-    numpy oracle and the golden vectors) runs on all host threads, same metric / config keys."""
+    numpy oracle and the golden vectors) runs on ALL host threads, same metric / config as the GPU arm.  Each step
+    is a bounded sample of the workload: the workload's own row length, Re, scheme and solver settings on the rows of
+    one GPU's slab (the whole grid at N = 1), halved only if K + W steps would not fit a few minutes."""
     if rank != 0:
         return
+    cores = use_all_host_threads()
+    maxit = lin_maxiter_of(args, wl)
     total_steps = args.steps + max(1, args.warmup)
-    n = args.ref_grid or sized_oracle_grid(min(wl["nx"], 4096), total_steps, 150.0)
-    mlups, sps, iters = oracle_sample(n, wl["Re"], 300, args.steps, args.warmup)
-    cores = cpu_threads()
-    sample = (f"{args.steps} steps (after {max(1, args.warmup)} warm-up) of a {n}x{n} cavity from rest, Re={wl['Re']}, "
-              f"QUICK, lin_maxiter=300 ({int(statistics.mean(iters))} true CG iterations/step); C/OpenMP restatement "
-              f"of the reference algorithm on {cores} threads (the unmodified reference is single-threaded "
-              "Python/numpy/scipy and far slower)")
+    ny_global = wl["ny"] * args.gpus if wl["per_gpu"] else wl["ny"]
+    rows_max = wl["ny"] if wl["per_gpu"] else max(256, wl["ny"] // args.gpus)
+    if args.ref_grid:
+        nx, rows = args.ref_grid, args.ref_grid
+    else:
+        nx = wl["nx"]
+        rows = sized_oracle_rows(nx, rows_max, wl["Re"], maxit, total_steps, getattr(args, 'ref_budget', 200.0))
+    mlups, sps, iters = oracle_sample(nx, rows, wl["Re"], maxit, args.steps, args.warmup)
+    whole = (nx == wl["nx"] and rows == ny_global)
+    sample = (f"{args.steps} steps (after {max(1, args.warmup)} warm-up) of a {nx}x{rows} cavity from rest "
+              f"({'the whole workload grid' if whole else f'a bounded sample of the {wl_nx_ny(wl, args.gpus)} workload: same row length, Re, scheme and solver settings'}), "
+              f"Re={wl['Re']:g}, QUICK, lin_maxiter={maxit} ({int(statistics.mean(iters))} true CG iterations/step); C/OpenMP "
+              f"restatement of the reference algorithm on {cores} threads (the unmodified reference is single-threaded "
+              "Python/numpy/scipy and 20-50x slower, profiles/r1_reference_cpu_timings.json)")
     line = {
         "impl": "reference", "metric": "MLUPS per projection step", "value": mlups, "unit": "MLUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
         "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args.workload, wl, args.gpus),
-        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": workload_config(args.workload, wl, args.gpus, maxit),
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample,
+                         "sample_grid": {"nx": nx, "ny": rows}},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, wl, n_gpus):
+def wl_nx_ny(wl, n_gpus):
+    return f"{wl['nx']}x{wl['ny'] * n_gpus if wl['per_gpu'] else wl['ny']}"
+
+
+def workload_config(name, wl, n_gpus, lin_maxiter=300):
+    """`config` of the JSON line: identical in the GPU arm and in the reference arm."""
     ny_global = wl["ny"] * n_gpus if wl["per_gpu"] else wl["ny"]
     return {
-        "workload": f"lid-driven cavity {wl['nx']}x{ny_global} Re={wl['Re']:g} QUICK Jacobi-PCG lin_maxiter=300 "
+        "workload": f"lid-driven cavity {wl['nx']}x{ny_global} Re={wl['Re']:g} QUICK Jacobi-PCG lin_maxiter={lin_maxiter} "
                     f"lin_tol=1e-10 from rest ({name})",
         "nx": wl["nx"], "ny": ny_global, "rows_per_gpu": ny_global // n_gpus, "Re": wl["Re"],
-        "advection_scheme": "quick", "lin_maxiter": 300, "lin_tol": 1e-10,
-        "parallelism": "single GPU" if n_gpus == 1 else f"row slabs x{n_gpus} (NCCL halo rows + scalar all-reduce)",
+        "advection_scheme": "quick", "lin_maxiter": lin_maxiter, "lin_tol": 1e-10,
+        "parallelism": "single GPU" if n_gpus == 1 else
+                       f"row slabs x{n_gpus}: one persistent CG kernel per rank, halo rows + dot-product partials through "
+                       "NVLink peer memory inside the kernel; NCCL only for the per-step halo rows and step scalars",
         "l2": "no flush needed: every CG sweep streams >= 3 vectors of nx*ny*8 B each, far larger than the 126 MB L2"
               if wl["nx"] * (ny_global // n_gpus) * 8 * 3 > 3 * 126e6 else
-              "working set is L2-resident by nature of this workload (latency-bound; HBM roofline informational)",
+              "working set is shared-memory / L2-resident by nature of this workload (latency-bound; HBM roofline informational)",
     }
 
 
@@ -210,14 +282,13 @@ def cg_kernel_name(nx, ny_local, world, sm_count=148):
     if (world == 1 and nx % 2 == 0 and nx <= 2048 and rows * (nx // 2) <= 8 * 512
             and 8 * nx * ((rows + 2) * 2 + rows) <= 200 * 1024):
         return "k_cg_small<unit> (shared-memory-resident CG; L2/latency-bound workload, HBM roofline informational)"
-    if nx % 1024 == 0:
+    if nx % 1024 == 0 and ny_local >= 2:
         return "k_cg_tmad<unit> (TMA-fed persistent CG)"
     return "k_cg_persistent<unit> (register-window persistent CG)"
 
 
 # ------------------------------------------------------------------ GPU arm
 def run_gpu_arm(args, wl, rank, world):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -231,50 +302,66 @@ def run_gpu_arm(args, wl, rank, world):
     from pyflow.residuals.manager import ResidualManager
     from pyflow.solvers.solver import step
 
-    nx = wl["nx"]
-    ny_global = wl["ny"] * world if wl["per_gpu"] else wl["ny"]
-    cfg = make_cfg(nx, ny_global, wl["Re"])
-    if world > 1:
-        from pyflow._b200.distributed import allocate_slab_state
-        state = allocate_slab_state(nx, ny_global, rank, world)
-    else:
-        state = allocate_state(nx, ny_global)
-    tracker = ResidualManager()
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return float(x)
+
+    def new_state(nx, ny_global):
+        if world > 1:
+            from pyflow._b200.distributed import allocate_slab_state
+            return allocate_slab_state(nx, ny_global, rank, world)
+        return allocate_state(nx, ny_global)
+
+    def timed_steps(cfg, state, tracker, it, warm, steps):
+        """`warm` untimed + `steps` timed device-resident steps; CUDA events, barrier + synchronize on both sides,
+        max over ranks."""
+        for _ in range(warm):
+            step(cfg, state, tracker, it)
+            it += 1
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        cg_ms, cg_iters, step_ms = [], [], []
+        for _ in range(steps):
+            step(cfg, state, tracker, it)
+            it += 1
+            cg_ms.append(state.meta["cg_ms"])
+            cg_iters.append(state.meta["cg_true_iterations"])
+            step_ms.append(state.meta["step_ms"])
+        ev1.record()
+        barrier()
+        return it, max_over_ranks(ev0.elapsed_time(ev1)), cg_ms, cg_iters, step_ms
+
+    nx = wl["nx"]
+    ny_global = wl["ny"] * world if wl["per_gpu"] else wl["ny"]
+    maxit = lin_maxiter_of(args, wl)
+    cfg = make_cfg(nx, ny_global, wl["Re"], maxit)
+    state = new_state(nx, ny_global)
+    tracker = ResidualManager()
+    warm = max(3, args.warmup)
     it = 0
-    for _ in range(max(3, args.warmup)):
+    step(cfg, state, tracker, it)               # creates the device context (counted in the warm-up)
+    it += 1
+    slab = state.fields._slab
+    sampler = ClockSampler(local_rank)
+    for _ in range(warm - 1):
         step(cfg, state, tracker, it)
         it += 1
-    slab = state.fields._slab
     launches0 = slab.launch_count()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     # ---- timed region: K device-resident steps ---------------------------------
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    cg_ms, cg_iters, step_ms = [], [], []
-    for _ in range(args.steps):
-        step(cfg, state, tracker, it)
-        it += 1
-        cg_ms.append(state.meta["cg_ms"])
-        cg_iters.append(state.meta["cg_true_iterations"])
-        step_ms.append(state.meta["step_ms"])
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    it, elapsed_ms, cg_ms, cg_iters, step_ms = timed_steps(cfg, state, tracker, it, 0, args.steps)
     launches = slab.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
     cells = nx * ny_global
     value = cells * args.steps / (elapsed_ms * 1e-3) / 1e6
 
@@ -290,11 +377,7 @@ def run_gpu_arm(args, wl, rank, world):
         last = (res["continuity"], diag["u_centerline"][1][0])
     fields_back = [state.fields[name] for name in ("u", "v", "p")]       # D2H inside the timed region
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     it += args.steps
     field_bytes = sum(a[1:-1, 1:-1].nbytes for a in fields_back) * world
     per_step_scalars = (32 * 8) * world + ny_global * 8
@@ -333,83 +416,118 @@ def run_gpu_arm(args, wl, rank, world):
     if os.environ.get("PF_BENCH_VERBOSE"):
         print(f"[rank {rank}] cg_ms mean {statistics.mean(cg_ms):.3f} min {min(cg_ms):.3f} max {max(cg_ms):.3f} "
               f"step_ms mean {statistics.mean(step_ms):.3f}", file=sys.stderr, flush=True)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    # ---- roofline of the dominant kernel (persistent CG) -------------------------
+    del drv, fields_back, state, slab
+    torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel (persistent CG), rank 0's launches -----------------
     peak, peak_src = measured_peak()
-    local_cells = nx * (ny_global // world)
-    cg_bytes = sum(local_cells * CG_BYTES_PER_CELL_ITER * k for k in cg_iters)
-    cg_s = sum(cg_ms) * 1e-3
-    achieved = cg_bytes / cg_s / 1e9 if cg_s > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "cg_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload)
-        except Exception:
-            traffic = None
+
+    def cg_roofline(nx_, nyl_, cg_ms_, cg_iters_):
+        local_cells = nx_ * nyl_
+        cg_bytes = sum(local_cells * CG_BYTES_PER_CELL_ITER * k for k in cg_iters_)
+        cg_s = sum(cg_ms_) * 1e-3
+        achieved = cg_bytes / cg_s / 1e9 if cg_s > 0 else 0.0
+        return achieved, cg_bytes, cg_s
+
+    achieved, cg_bytes, cg_s = cg_roofline(nx, ny_global // world, cg_ms, cg_iters)
+    kernel = cg_kernel_name(nx, ny_global // world, world)
+    traffic, traffic_src = recorded_traffic(args.workload, kernel) if world == 1 else (None, "single-GPU captures only")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": cg_kernel_name(nx, ny_global // world, world),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": kernel, "kernel_source_hash": kernel_source_hash(),
                 "algorithmic_bytes_per_launch": cg_bytes / max(1, len(cg_iters)),
                 "avg_launch_ms": statistics.mean(cg_ms) if cg_ms else None,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "cg_share_of_step": sum(cg_ms) / sum(step_ms) if step_ms else None}
+    local_cells = nx * (ny_global // world)
     step_bytes = sum(local_cells * (CG_BYTES_PER_CELL_ITER * k + STEP_BYTES_PER_CELL) for k in cg_iters)
+
+    # ---- the other BASELINE configs at this GPU count (device-resident, few steps, all ranks) ----------
+    other = None
+    if not getattr(args, 'no_extra', False) and args.workload == "cavity4096":
+        other = {}
+        extra = [("cavity512", 3, 50)] if world == 1 else []
+        extra += [("strong8192", 2, 4), ("weak16384", 2, 2), ("weak16384_tight", 1, 1)]
+        for name, w2, n2 in extra:
+            wl2 = WORKLOADS[name]
+            ny2 = wl2["ny"] * world if wl2["per_gpu"] else wl2["ny"]
+            if ny2 % world or ny2 // world < 2:
+                continue
+            try:
+                cfg2 = make_cfg(wl2["nx"], ny2, wl2["Re"], wl2.get("lin_maxiter", 300))
+                st2, tr2 = new_state(wl2["nx"], ny2), ResidualManager()
+                _it, ms2, cg2, its2, _sm = timed_steps(cfg2, st2, tr2, 0, w2, n2)
+                ach2, _b, cgs2 = cg_roofline(wl2["nx"], ny2 // world, cg2, its2)
+                other[name] = {
+                    "config": workload_config(name, wl2, world, wl2.get("lin_maxiter", 300))["workload"],
+                    "scaling": wl2["scaling"], "steps": n2, "warmup": w2, "ms_per_step": ms2 / n2,
+                    "MLUPS": wl2["nx"] * ny2 * n2 / (ms2 * 1e-3) / 1e6,
+                    "cg_iters_per_step": statistics.mean(its2), "cg_iters_per_s": sum(its2) / cgs2 if cgs2 > 0 else None,
+                    "cg_kernel": cg_kernel_name(wl2["nx"], ny2 // world, world).split(" ")[0],
+                    "cg_hbm_gbs_algorithmic_per_gpu": ach2, "cg_frac_of_measured_peak_per_gpu": ach2 / peak,
+                    "peer_kernel": bool(getattr(st2.fields._slab, "peer_mode", False))}
+                st2.fields._slab.close()
+                del st2
+                torch.cuda.empty_cache()
+            except Exception as exc:          # an extra figure must never cost the headline line
+                other[name] = {"error": repr(exc)}
+
+    # ---- parity (UNTIMED): the CUDA path against the C oracle, at this GPU count -------------------------
+    parity = None
+    if not getattr(args, 'no_parity', False):
+        import parity as parity_mod
+        try:
+            parity = parity_mod.run_bench_block(args.workload, nx, ny_global // world, wl["Re"], rank, world)
+        except Exception as exc:
+            parity = {"ok": False, "error": repr(exc)}
+
+    if rank != 0:
+        if world > 1:
+            ok = torch.tensor([1], device="cuda")
+            dist.broadcast(ok, src=0)
+            dist.destroy_process_group()
+            return 0 if int(ok.item()) == 1 else 1
+        return 0
     # ---- CPU baseline: bounded oracle sample on this box ---------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        n = sized_oracle_grid(min(wl["nx"], 4096), 3, 25.0)
-        mlups, sps, iters = oracle_sample(n, wl["Re"], 300, 2, 1)
-        np_mlups, np_sps, _ = oracle_sample(min(n, 512), wl["Re"], 300, 1, 1, impl="numpy")
-        cpu = {"value": mlups, "unit": "MLUPS", "cores": cpu_threads(), "kind": "port",
-               "sample": f"2 steps (#1-#2 from rest, {int(statistics.mean(iters))} true CG iterations each) of a {n}x{n} "
+        cores = use_all_host_threads()
+        rows = sized_oracle_rows(nx, wl["ny"], wl["Re"], maxit, 3, 25.0)
+        mlups, sps, iters = oracle_sample(nx, rows, wl["Re"], maxit, 2, 1)
+        npn = min(nx, 512)
+        np_mlups, np_sps, _ = oracle_sample(npn, npn, wl["Re"], 300, 1, 1, impl="numpy")
+        cpu = {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port",
+               "sample": f"2 steps (#1-#2 from rest, {int(statistics.mean(iters))} true CG iterations each) of a {nx}x{rows} "
                          f"cavity, same Re/scheme/solver settings, {sps:.2f} s/step; C/OpenMP restatement of the "
                          "reference algorithm (oracle/pyflow_oracle.c) on all host threads",
+               "sample_grid": {"nx": nx, "ny": rows},
                "numpy_port_mlups": np_mlups,
-               "numpy_port_sample": f"1 step of a {min(n, 512)}x{min(n, 512)} cavity with the single-threaded numpy "
+               "numpy_port_sample": f"1 step of a {npn}x{npn} cavity with the single-threaded numpy "
                                     "oracle (the unmodified reference is slower still: Python loops for advection)"}
-    # ---- BASELINE config 2 (512^2, L2-resident, latency-bound) beside the headline, N = 1 only -------
-    other = None
-    if world == 1 and args.workload == "cavity4096":
-        cfg2 = make_cfg(512, 512, 1000.0)
-        st2, tr2 = allocate_state(512, 512), ResidualManager()
-        for k in range(3):
-            step(cfg2, st2, tr2, k)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        n2, its2, cg2 = 50, 0, 0.0
-        for k in range(3, 3 + n2):
-            step(cfg2, st2, tr2, k)
-            its2 += st2.meta["cg_true_iterations"]
-            cg2 += st2.meta["cg_ms"]
-        e1.record()
-        torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1) / n2
-        other = {"cavity512 (BASELINE config 2: 512x512 Re=1000, 300 CG its/step, L2-resident)": {
-            "ms_per_step": ms2, "MLUPS": 512 * 512 / (ms2 * 1e-3) / 1e6, "cg_iters_per_s": its2 / (cg2 * 1e-3),
-            "steps": n2}}
     line = {
         "metric": "MLUPS per projection step", "value": value, "unit": "MLUPS", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps,
+        "steps": args.steps, "warmup": warm, "ms_per_step": elapsed_ms / args.steps,
         "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": dict(workload_config(args.workload, wl, world),
-                                            cg_comm=("single GPU" if world == 1 else
-                                                     "one persistent kernel per rank, halo rows + dot-product partials over NVLink peer memory"
-                                                     if peer_mode else "NCCL send/recv + all-reduce between phase kernels")),
+        "data": "synthetic", "config": workload_config(args.workload, wl, world, maxit),
+        "cg_comm": ("single GPU" if world == 1 else
+                    "one persistent kernel per rank, halo rows + dot-product partials over NVLink peer memory"
+                    if peer_mode else "NCCL send/recv + all-reduce between phase kernels"),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "cg_iters_per_s": sum(cg_iters) / cg_s if cg_s > 0 else None,
         "cg_iters_per_step": statistics.mean(cg_iters) if cg_iters else None,
         "step_hbm_gbs_algorithmic": step_bytes / (sum(step_ms) * 1e-3) / 1e9 if step_ms else None,
         "other_configs": other,
     }
     print(json.dumps(line), flush=True)
+    good = parity is None or bool(parity.get("ok"))
     if world > 1:
+        ok = torch.tensor([1 if good else 0], device="cuda")
+        dist.broadcast(ok, src=0)
         dist.destroy_process_group()
+    if not good:
+        print("bench.py: PARITY FAILED (see the `parity` object of the JSON line)", file=sys.stderr, flush=True)
+    return 0 if good else 1
 
 
 def main():
@@ -419,8 +537,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cavity4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--lin-maxiter", type=int, default=0, help="override the workload's CG iteration cap")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity block")
+    ap.add_argument("--no-extra", action="store_true", help="skip `other_configs` (BASELINE configs 2, 4, 5)")
     ap.add_argument("--ref-grid", type=int, default=0, help="reference arm: force the sample grid size (tests)")
+    ap.add_argument("--ref-budget", type=float, default=200.0, help="reference arm: seconds for K + W oracle steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -435,8 +557,7 @@ def main():
                    "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
             return subprocess.call(cmd)
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    run_gpu_arm(args, wl, rank, world)
-    return 0
+    return run_gpu_arm(args, wl, rank, world)
 
 
 if __name__ == "__main__":

@@ -50,6 +50,8 @@ def load():
     if _lib is None:
         lib = C.CDLL(build())
         lib.pfo_threads.restype = C.c_int
+        lib.pfo_set_threads.argtypes = [C.c_int]
+        lib.pfo_set_threads.restype = None
         lib.pfo_divc_sumsq.restype = C.c_double
         lib.pfo_divc_sumsq.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, _dp]
         lib.pfo_absmax.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
@@ -69,6 +71,11 @@ def load():
 
 def threads() -> int:
     return int(load().pfo_threads())
+
+
+def set_threads(n: int) -> None:
+    """OpenMP thread count of the C oracle (results are independent of it: per-row partials, serial fold)."""
+    load().pfo_set_threads(int(n))
 
 
 def _p(a):

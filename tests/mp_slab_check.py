@@ -19,7 +19,7 @@ for p in (os.path.join(ROOT, "pyflow-solver_b200"), os.path.join(ROOT, "oracle")
 import torch
 import torch.distributed as dist
 
-from pyflow._b200.distributed import allocate_slab_state, gather_field, scatter_state, slab_rows
+from pyflow._b200.distributed import allocate_slab_state, gather_field, scatter_state, slab_rows  # noqa: E402
 from pyflow.core.ghost_fields import allocate_state
 
 
@@ -82,44 +82,29 @@ def main():
     # MODE nccl : CG with NCCL halo + all-reduce calls per phase
     # MODE peer : CG as one persistent kernel per rank over NVLink peer memory
     os.environ["PYFLOW_B200_CG_COMM"] = "nccl" if mode == "nccl" else "peer"
+    import parity
     import pyflow_oracle as orc
-    from pyflow.residuals.manager import ResidualManager
-    from pyflow.solvers.solver import step
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    if rank == 0:
+        parity.use_all_host_threads()
     ok = True
-    cases = [
-        dict(nx=96, ny=80, Re=100.0, advection_scheme="quick", lin_maxiter=10000, steps=4),   # converged regime
-        dict(nx=128, ny=128, Re=100.0, advection_scheme="quick", lin_maxiter=300, steps=5),   # truncated early
-        dict(nx=70, ny=61, Re=400.0, advection_scheme="upwind", lin_maxiter=100, steps=4, lx=2.0, ly=1.0),  # ragged, non-unit, truncated early
-        dict(nx=200, ny=48 * world, Re=1000.0, advection_scheme="quick", lin_maxiter=300, steps=4),           # equal slabs, several strips
-        dict(nx=1024, ny=36 * world, Re=1000.0, advection_scheme="quick", lin_maxiter=300, steps=3),          # TMA-fed kernel (nx % 1024 == 0)
-        dict(nx=2048, ny=20 * world, Re=1000.0, advection_scheme="upwind", lin_maxiter=200, steps=3),         # TMA-fed kernel, 2 column chunks
-    ]
+    # the slab cases of bench.py's untimed parity block (ragged, non-unit, converged and truncated solves, the
+    # register-window and the TMA-fed peer kernels) plus a 4096-wide slab: config 3's row length, 256 rows per GPU
+    cases = parity.bench_cases("cavity4096", 4096, 4096, 1000.0, world)
+    if mode == "nccl":                  # split-phase path: launch-bound (5 launches + 4 NCCL calls per iteration); skip the long solves
+        cases = [c for c in cases if "converged (lin_maxiter 10000)" not in c[0] or c[1].nx < 1024]
     used_peer = []
-    for case in cases:
-        steps = case.pop("steps")
-        cfg = SimpleNamespace(lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
-                              disable_advection=False, diagnostics=False, **case)
-        st = allocate_slab_state(cfg.nx, cfg.ny, rank, world)
-        tr = ResidualManager()
-        dts, iters = [], []
-        for it in range(steps):
-            _, res, diag = step(cfg, st, tr, it)
-            dts.append(diag["dt"])
-            iters.append(st.meta["cg_true_iterations"])
-        used_peer.append(bool(st.fields._slab.peer_mode))
-        fields = {k: gather_field(st, k) for k in ("u", "v", "p")}
+    for name, cfg, steps in cases:
+        r = parity.check_case(name, cfg, steps, rank, world)
         if rank == 0:
-            ost, od = orc.run(cfg, steps)
-            errs = {k: rel(fields[k][1:-1, 1:-1], orc.interior(ost.fields[k])) for k in ("u", "v", "p")}
-            same_dt = dts == [d["dt"] for d in od]
-            dit = max(abs(a - d["true_iterations"]) for a, d in zip(iters, od))
-            good = same_dt and all(e < 1e-8 for e in errs.values()) and dit <= 2
-            print(f"PARITY mode={mode} peer_kernel={used_peer[-1]} world={world} {cfg.nx}x{cfg.ny} errs={errs} dt_equal={same_dt} iters={iters} max_iter_diff={dit} "
-                  f"{'OK' if good else 'FAIL'}", flush=True)
-            ok = ok and good
+            used_peer.append(r["peer_kernel"])
+            print(f"PARITY mode={mode} peer_kernel={r['peer_kernel']} world={world} {cfg.nx}x{cfg.ny} [{name}] errs={r['rel_l2']} "
+                  f"dt_equal={r['dt_equal']} iters={r['iters']} max_iter_diff={r['max_iter_diff']} "
+                  f"{'OK' if r['ok'] else 'FAIL'}", flush=True)
+            ok = ok and r["ok"]
+    from types import SimpleNamespace
     # the drop-in driver on slab states: every rank yields, the centre line is the concatenation of the slabs
     from pyflow.drivers.simulation_driver import SimulationDriver
     cfg = SimpleNamespace(nx=64, ny=16 * world, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,

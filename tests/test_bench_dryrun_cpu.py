@@ -55,6 +55,10 @@ def test_gpu_arm_runs_end_to_end_on_stand_ins(monkeypatch, capsys):
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert r["algorithmic_bytes_per_launch"] == 24 * 20 * 64.0 * line["cg_iters_per_step"]
     assert r["kernel"].startswith("k_cg_small")
+    assert r["traffic"] is None and "traffic_source" in r and len(r["kernel_source_hash"]) == 16
+    par = line["parity"]                                   # untimed block: stand-in (numpy oracle) vs the C oracle
+    assert par["ok"] and par["cases"] == 2 and par["dt_equal"] and par["max_iter_diff"] <= 1 and par["max_rel_l2"] < 1e-9
+    assert [d["case"] for d in par["details"]] == ["tiny: 24x256 slab (256 rows per GPU), 300 its", "tiny: full 24x20 grid, 300 its"]
     assert bench.cg_kernel_name(4096, 4096, 1).startswith("k_cg_tmad") and bench.cg_kernel_name(513, 513, 1).startswith("k_cg_persistent")
 
 
@@ -73,3 +77,25 @@ def test_reference_arm_prints_on_rank_zero_only(rank, capsys):
         line = json.loads(out.splitlines()[-1])
         assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["e2e"]["value"] == line["value"]
         assert line["cpu_baseline"]["value"] == line["value"] and line["config"]["ny"] == 8192
+        assert line["cpu_baseline"]["sample_grid"] == {"nx": 32, "ny": 32} and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+        # same `config` object as the GPU arm prints for this workload and GPU count
+        assert line["config"] == bench.workload_config("cavity4096", bench.WORKLOADS["cavity4096"], 2, 300)
+
+
+def test_reference_arm_uses_every_host_core_even_under_torchrun(monkeypatch):
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must not inherit that."""
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    import pyflow_oracle_c as orc_c
+    orc_c.set_threads(1)
+    assert bench.use_all_host_threads() == (os.cpu_count() or 1)
+
+
+def test_reference_sample_keeps_the_row_length_and_fits_the_budget():
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.sized_oracle_rows(256, 1024, 100.0, 20, 3, 1e9) == 1024          # fits: the whole slab
+    assert bench.sized_oracle_rows(256, 1024, 100.0, 20, 3, 0.0) == 256           # never below 256 rows
