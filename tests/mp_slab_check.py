@@ -104,7 +104,6 @@ def main():
                   f"dt_equal={r['dt_equal']} iters={r['iters']} max_iter_diff={r['max_iter_diff']} "
                   f"{'OK' if r['ok'] else 'FAIL'}", flush=True)
             ok = ok and r["ok"]
-    from types import SimpleNamespace
     # the drop-in driver on slab states: every rank yields, the centre line is the concatenation of the slabs
     from pyflow.drivers.simulation_driver import SimulationDriver
     cfg = SimpleNamespace(nx=64, ny=16 * world, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
