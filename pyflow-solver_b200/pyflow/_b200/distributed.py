@@ -63,6 +63,32 @@ def gather_field(state: State, name: str):
     return out
 
 
+def gather_centerline(segment: np.ndarray, state: State) -> np.ndarray:
+    """Concatenation of every rank's column segment (u[:, nx//2] of its slab), on every rank: one tensor
+    all-gather of ny_local doubles per rank (CUDA tensors under NCCL, host tensors under gloo)."""
+    import torch
+    import torch.distributed as dist
+    spec = state.slab
+    world = spec["world"]
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    rows = [slab_rows(spec["ny_global"], r, world)[1] for r in range(world)]
+    width = max(rows)                                    # ragged slabs: pad to the tallest one, cut after the gather
+    mine = torch.zeros(width, dtype=torch.float64)
+    mine[:len(segment)] = torch.from_numpy(np.ascontiguousarray(segment, dtype=np.float64))
+    mine = mine.to(dev)
+    parts = [torch.empty(width, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return torch.cat([p[:n] for p, n in zip(parts, rows)]).cpu().numpy()
+
+
+def gathered_state(state: State) -> State:
+    """Full-grid host State assembled from the slabs (every rank gets it; used for checkpoints, which only
+    rank 0 writes).  `meta` is shared by reference: the dt-controller memory is identical on every rank."""
+    full = State(nx=state.nx, ny=state.slab["ny_global"], fields={k: gather_field(state, k) for k in ("u", "v", "p")})
+    full.meta = state.meta
+    return full
+
+
 def _symmetric_allocator(nbytes: int, device: int):
     """Workspace in torch symmetric memory: every rank allocates the same size
     and the buffers are peer-mapped across the GPUs of the box (NVLink)."""
@@ -108,6 +134,9 @@ def make_slab(state: State) -> DeviceSlab:
             dist.barrier()                     # all workspaces are zero-initialised before anyone writes remotely
             slab.set_peers(list(hdl.buffer_ptrs))
             slab._symm_handle = hdl
-        elif want_peer:
-            raise RuntimeError("ranks disagree on the CG communication mode")
+        elif any(flags):
+            # symmetric memory came up on some ranks only: EVERY rank stays on the NCCL split-phase path (leaving
+            # set_peers unset everywhere keeps the collectives matched; raising on a subset would hang the others)
+            warnings.warn("symmetric memory is not available on every rank; all ranks use NCCL halo / all-reduce "
+                          "calls per CG phase")
     return slab

@@ -162,6 +162,7 @@ def main(argv: list[str] | None = None) -> int:
             path = args.checkpoint or "interrupt_final_checkpoint.npz"
             try:
                 from .io.checkpoint import save_checkpoint
+                driver.wait_checkpoints()        # a periodic checkpoint still in flight must not land after this one
                 save_checkpoint(path, last[0], last[1].get("iteration", 0), last[1].get("wall_time", 0.0), cfg)
                 if not json_mode:
                     print(f"Final checkpoint written: {path}")

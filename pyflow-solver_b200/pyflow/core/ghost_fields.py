@@ -98,6 +98,67 @@ class SyncedFields(dict):
     def copy(self):
         return {k: self[k] for k in dict.keys(self)}
 
+    # every mutating entry point of dict goes through __setitem__ / the stale + touched bookkeeping:
+    # the inherited C implementations would bypass it (a replaced field would be overwritten by the
+    # next download and ignored by the next step)
+    def update(self, *a, **k):
+        for name, value in dict(*a, **k).items():
+            self[name] = value
+
+    def setdefault(self, name, default=None):
+        if not dict.__contains__(self, name):
+            self[name] = default
+        return self[name]
+
+    def pop(self, name, *default):
+        if dict.__contains__(self, name):
+            self._materialise(name)
+            self._stale.discard(name)
+            self._touched.discard(name)
+        return dict.pop(self, name, *default)
+
+    def popitem(self):
+        name = next(reversed(dict.keys(self)))
+        return name, self.pop(name)
+
+    def __delitem__(self, name):
+        dict.__delitem__(self, name)
+        self._stale.discard(name)
+        self._touched.discard(name)
+
+    def clear(self):
+        dict.clear(self)
+        self._stale.clear()
+        self._touched.clear()
+
+    def __ior__(self, other):
+        self.update(other)
+        return self
+
+    def __or__(self, other):
+        out = self.copy()
+        out.update(other)
+        return out
+
+    # copies are plain host snapshots: they never share the GPU context (one pf_destroy per context)
+    def _snapshot(self):
+        out = SyncedFields({k: np.array(self[k]) if isinstance(self[k], np.ndarray) else self[k]
+                            for k in dict.keys(self)})
+        out.eager = self.eager
+        return out
+
+    def __copy__(self):
+        return self._snapshot()
+
+    def __deepcopy__(self, memo):
+        out = self._snapshot()
+        memo[id(self)] = out
+        return out
+
+    def __reduce__(self):
+        return (SyncedFields, ({k: np.array(self[k]) if isinstance(self[k], np.ndarray) else self[k]
+                                for k in dict.keys(self)},))
+
 
 @dataclass
 class State:

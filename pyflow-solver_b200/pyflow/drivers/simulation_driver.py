@@ -43,6 +43,14 @@ class SimulationDriver:
         self._t0 = None
         self.iteration = 0
         self.async_checkpoint = False
+        self._writer: BackgroundCheckpointWriter | None = None
+
+    def wait_checkpoints(self) -> None:
+        """Block until a checkpoint handed to the background writer is on disk (no-op otherwise).  Callers that
+        write the same path themselves (the CLI's Ctrl-C handler) call this first, so that the worker's rename
+        cannot land after -- and replace -- their newer file."""
+        if self._writer is not None:
+            self._writer.wait()
 
     def ensure_state(self, nx: int, ny: int) -> State:
         if self.state is None:
@@ -53,12 +61,9 @@ class SimulationDriver:
         f = state.fields
         if isinstance(f, SyncedFields) and f._slab is not None:
             u_center = f._slab.centerline()
-            if f._slab.nranks > 1:                 # concatenate the slabs' column segments
-                import numpy as np
-                import torch.distributed as dist
-                parts = [None] * f._slab.nranks
-                dist.all_gather_object(parts, u_center)
-                u_center = np.concatenate(parts)
+            if f._slab.nranks > 1:                 # concatenate the slabs' column segments (collective)
+                from .._b200.distributed import gather_centerline
+                u_center = gather_centerline(u_center, state)
             n = u_center.shape[0]
         else:
             ui = interior_view(f["u"])
@@ -77,11 +82,13 @@ class SimulationDriver:
         if checkpoint_path and (self.async_checkpoint or getattr(self.config, "async_checkpoint", False)
                                 or os.environ.get("PYFLOW_B200_ASYNC_CHECKPOINT", "0") == "1"):
             writer = BackgroundCheckpointWriter()
+        self._writer = writer
         try:
             yield from self._loop(max_steps, progress, checkpoint_path, checkpoint_interval, writer)
         finally:
             if writer is not None:
                 writer.wait()                  # the last checkpoint is on disk when the generator ends or is closed
+            self._writer = None
 
     def _loop(self, max_steps, progress, checkpoint_path, checkpoint_interval, writer):
         while True:
@@ -94,10 +101,14 @@ class SimulationDriver:
                     raise ValueError("SimulationDriver requires either an initial State or config.nx & config.ny for allocation")
                 self.state = self.allocate_fn(nx, ny)
             state, residuals, diagnostics = step(self.config, self.state, self.tracker, self.iteration)
-            try:
+            if getattr(state, "slab", None) is not None:
+                # row slabs: the gather is a collective -- a swallowed failure on one rank would hang the others
                 diagnostics["u_centerline"] = self._centerline(state)
-            except Exception:  # pragma: no cover
-                pass
+            else:
+                try:
+                    diagnostics["u_centerline"] = self._centerline(state)
+                except Exception:  # pragma: no cover
+                    pass
             diagnostics["wall_time"] = time.time() - self._t0
             if progress:
                 print(f"iter={self.iteration} dt={diagnostics.get('dt'):.3g} CFL={diagnostics.get('CFL'):.3g} "
@@ -105,6 +116,22 @@ class SimulationDriver:
             yield state, residuals, diagnostics
             if checkpoint_path and checkpoint_interval and checkpoint_interval > 0:
                 if self.iteration % checkpoint_interval == 0:
+                    spec = getattr(state, "slab", None)
+                    if spec is not None and spec["world"] > 1:
+                        # row slabs: ONE file of the whole grid, written by rank 0 (every rank takes part in the
+                        # gather; per-rank files under the same path would overwrite each other)
+                        from .._b200.distributed import gathered_state
+                        full = gathered_state(state)
+                        written = True
+                        if spec["rank"] == 0:
+                            try:
+                                save_checkpoint(checkpoint_path, full, self.iteration,
+                                                diagnostics.get("time", diagnostics.get("wall_time", 0.0)), self.config)
+                            except Exception:  # pragma: no cover
+                                written = False
+                        diagnostics["checkpoint_written"] = written
+                        self.iteration += 1
+                        continue
                     try:
                         sim_time = diagnostics.get("time", diagnostics.get("wall_time", 0.0))
                         if writer is not None:

@@ -64,8 +64,18 @@ def main():
                               lin_tol=1e-10, lin_maxiter=40, advection_scheme="quick", disable_advection=False,
                               diagnostics=False)
         st = allocate_slab_state(cfg.nx, cfg.ny, rank, world)
-        diags = [dict(d) for _s, _r, d in SimulationDriver(cfg, st).run(max_steps=4)]
-        assert st.fields._slab.nranks == world and st.fields._slab.downloads == []
+        import tempfile
+        box = [tempfile.mkdtemp() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ckpt = os.path.join(box[0], "slab.npz")
+        diags = [dict(d) for _s, _r, d in SimulationDriver(cfg, st).run(max_steps=4, checkpoint_path=ckpt,
+                                                                         checkpoint_interval=3)]
+        assert st.fields._slab.nranks == world
+        # ONE checkpoint of the WHOLE grid, written by rank 0 after step 3 (per-rank files would overwrite each other)
+        dist.barrier()
+        from pyflow.io.checkpoint import load_checkpoint
+        back, meta = load_checkpoint(ckpt)
+        assert (back.nx, back.ny) == (cfg.nx, cfg.ny) and meta["iteration"] == 3 and sorted(os.listdir(box[0])) == ["slab.npz"]
         ost, od = orc.run(cfg, 4)
         assert [d["dt"] for d in diags] == [d["dt"] for d in od]                 # identical on EVERY rank
         assert [d["Rp_residual"] for d in diags] == [d["Rp_residual"] for d in od]
@@ -73,6 +83,7 @@ def main():
         assert len(line[0]) == cfg.ny and line[1] == orc.interior(ost.fields["u"])[:, cfg.nx // 2].tolist()
         for k in ("u", "v", "p"):
             assert np.array_equal(gather_field(st, k), ost.fields[k]), k
+            assert np.array_equal(back.fields[k], ost.fields[k]), k
         if rank == 0:
             print("GLOO_OK")
         dist.destroy_process_group()

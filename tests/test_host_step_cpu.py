@@ -141,6 +141,49 @@ def test_eager_mode_gives_live_array_semantics(slab_cls, monkeypatch):
     assert allocate_state(4, 4).fields.eager is True
 
 
+def test_every_mutating_dict_method_keeps_the_device_copy_coherent(slab_cls):
+    """``update``, ``setdefault``, ``pop``, ``del``, ``|=`` and copies of ``state.fields`` go through the same
+    stale / touched bookkeeping as ``__setitem__`` (the inherited dict methods would bypass it: a field replaced
+    with ``update`` would be overwritten by the next download and ignored by the next step); copies of a State are
+    host snapshots that never share the GPU context."""
+    import copy
+    import pickle
+    from pyflow.core.ghost_fields import allocate_state
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    cfg = make_cfg(nx=12, ny=9, lin_maxiter=8)
+    st, tr = allocate_state(12, 9), ResidualManager()
+    model = orc.allocate_state(12, 9)
+    for it in range(2):
+        step(cfg, st, tr, it)
+        orc.step(cfg, model, it)
+    new_u = model.fields["u"] * 0.5
+    st.fields.update(u=new_u.copy())                       # replaced through update(): must be uploaded, not lost
+    model.fields["u"] = new_u
+    assert "u" in st.fields.host_touched() and np.array_equal(st.fields["u"], new_u)
+    st.fields |= {"v": model.fields["v"] * 2.0}
+    model.fields["v"] = model.fields["v"] * 2.0
+    assert st.fields.setdefault("p") is st.fields.peek("p")
+    assert st.fields.setdefault("extra", 7) == 7 and st.fields.pop("extra") == 7 and "extra" not in st.fields
+    step(cfg, st, tr, 2)
+    orc.step(cfg, model, 2)
+    snap = copy.deepcopy(st)                               # device copy is newer than the host arrays here
+    assert snap.fields._slab is None and snap.fields is not st.fields
+    clone = pickle.loads(pickle.dumps(st.fields))
+    for f in ("u", "v", "p"):
+        assert np.array_equal(snap.fields[f], model.fields[f]) and np.array_equal(clone[f], model.fields[f])
+        assert np.array_equal(st.fields[f], model.fields[f])
+    popped = st.fields.pop("p")                            # pop of a stale field returns the current contents
+    assert np.array_equal(popped, model.fields["p"])
+    st.fields["p"] = popped
+    step(cfg, st, tr, 3)
+    orc.step(cfg, model, 3)
+    for f in ("u", "v", "p"):
+        assert np.array_equal(st.fields[f], model.fields[f])
+    del st.fields["p"]
+    assert "p" not in st.fields and "p" not in st.fields.host_touched()
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_lazy_state_protocol_random_walk(slab_cls, seed, tmp_path):
     """Random interleavings of steps, reads, in-place writes through freshly fetched arrays, whole-array
