@@ -10,16 +10,19 @@ os.environ["PYFLOW_B200_OPTIONS"] = "cg_sync_opt=4"
 from pyflow._b200.distributed import allocate_slab_state
 from pyflow.residuals.manager import ResidualManager
 from pyflow.solvers.solver import step
-cfg = SimpleNamespace(nx=4096, ny=4096*world, Re=1000.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10, lin_maxiter=300, advection_scheme="quick", disable_advection=False, diagnostics=False)
-st = allocate_slab_state(4096, 4096*world, rank, world); tr = ResidualManager()
-for it in range(5): step(cfg, st, tr, it)
+NX = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+ROWS = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+MAXIT = int(sys.argv[3]) if len(sys.argv) > 3 else 300
+cfg = SimpleNamespace(nx=NX, ny=ROWS*world, Re=1000.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10, lin_maxiter=MAXIT, advection_scheme="quick", disable_advection=False, diagnostics=False)
+st = allocate_slab_state(NX, ROWS*world, rank, world); tr = ResidualManager()
+for it in range(4): step(cfg, st, tr, it)
 slab = st.fields._slab
-buf = np.zeros(64); slab._lib.pf_debug_read_partials(slab.ctx, buf.ctypes.data_as(C.POINTER(C.c_double)), 16384, 64)
+buf = np.zeros(64); slab._lib.pf_debug_read_partials(slab.ctx, buf.ctypes.data_as(C.POINTER(C.c_double)), 2 * 16384, 64)
 t = buf.view(np.uint64).reshape(8, 8).astype(np.int64)
 for r in range(world):
     dist.barrier()
     if r == rank:
-        print(f"rank {rank} cg_ms {st.meta['cg_ms']:.2f}")
+        print(f"rank {rank} grid {NX}x{ROWS}/gpu cg_ms {st.meta['cg_ms']:.2f}  ({st.meta['cg_ms']*1e3/MAXIT:.1f} us per iteration)")
         prev_exit = None
         for k in range(8):
             first, last, fold, pub, seen0, seen1, b0 = t[k][:7]

@@ -40,8 +40,8 @@ struct pf_ctx {
   int gen_grid = 0;                // co-resident CTAs of k_cg_generic
   int tma_grid = 0;                // co-resident CTAs of k_cg_tma (0: unavailable)
   bool small_ok = false;           // k_cg_small usable (dynamic shared memory attribute set)
-  double* small_halo = nullptr;    // [SM_MAX_GRID][2][packets per row][4] boundary rows of r as tagged packets (k_cg_small)
-  double* small_part = nullptr;    // [2][SM_MAX_GRID][4] reduction packets, double-buffered by epoch parity
+  double* small_halo = nullptr;    // [SM_MAX_GRID][2][nx/2][4] boundary rows of r as LL packets, one per column pair (k_cg_small)
+  double* small_part = nullptr;    // [2][SM_MAX_GRID] reduction packets, SM_SLOT_DOUBLES apart, double-buffered by epoch parity
   long long launches = 0;          // kernels of this library launched so far
   bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
   dim3 sgrid;                      // grid of the simple kernels
@@ -54,6 +54,9 @@ struct pf_ctx {
   int opt_multi_single = 0;        // debug/tuning: run the multi-GPU persistent kernel with one rank
   int opt_sync = 0;
   int opt_rows_min = 4;            // minimum rows per warp tile of the register-window kernel
+  int opt_tile_rows = 0;           // TMA kernel: force the big-tile height (0: automatic)
+  int opt_small_rows = -1;         // TMA kernel: force the small-tile height (-1: automatic, 0: uniform tiles)
+  int opt_nb_small = -1;           // TMA kernel: force the number of small bands at each end (-1: automatic)
   int opt_kernel = 3;              // 3: auto = shared-memory-resident kernel for small grids, TMA-fed dynamically scheduled
                                    //    kernel when nx % 1024 == 0, else the register-window kernels; 2: static TMA tiles;
                                    //    1: register-window only
@@ -102,10 +105,10 @@ SmallLayout small_layout(int64_t nyl, int64_t nx = 0) {
   L.red_counter = o; o = align_up(o + sizeof(unsigned) * 4, ALIGN);
   L.scal = o;        o = align_up(o + sizeof(double) * S_COUNT, ALIGN);
   L.cg_part = o;     o = align_up(o + sizeof(double) * PF_PART_DOUBLES, ALIGN);
-  L.sync = o;        o = align_up(o + 1024, ALIGN);
+  L.sync = o;        o = align_up(o + 2048, ALIGN);
   L.center = o;      o = align_up(o + sizeof(double) * (size_t)nyl, ALIGN);
   L.small_halo = o;  o = align_up(o + sizeof(double) * 2 * SM_MAX_GRID * (size_t)(nx <= 2048 ? 4 * small_row_packets((int)nx) : 0), ALIGN);
-  L.small_part = o;  o = align_up(o + sizeof(double) * 2 * 256 * 4, ALIGN);
+  L.small_part = o;  o = align_up(o + sizeof(double) * 2 * SM_MAX_GRID * SM_SLOT_DOUBLES, ALIGN);
   L.total = o;
   return L;
 }
@@ -140,8 +143,8 @@ void cg_geometry(const pf_ctx* c, CgArgs& a) {
   a.ntiles = a.nchunks * a.nbands;
 }
 
-// Sync block layout (1 KiB, zeroed at creation): u64 arrive, release, epoch, err, pad[4], flags[8];
-// then 64 doubles of mailbox ([2][8][4]) and 8 doubles of folded sums.
+// Sync block layout (2 KiB, zeroed at creation): u64 arrive, release, epoch, err, tickets, ticket_base, pad, small-kernel
+// epoch, flags[8]; then the mailbox ([2][CG_MAX_RANKS] 64-byte LL slots = 1 KiB) and one 64-byte LL slot of folded sums.
 void fill_sync(const pf_ctx* c, CgSync& y) {
   auto u64 = [](char* p, int i) { return (unsigned long long*)p + i; };
   char* mine = c->ws_base + c->sync_off;
@@ -153,7 +156,7 @@ void fill_sync(const pf_ctx* c, CgSync& y) {
   y.ticket_base = u64(mine, 5);
   y.flags = u64(mine, 8);
   y.mbox = (double*)(mine + 128);
-  y.gsum = (double*)(mine + 128 + 64 * sizeof(double));
+  y.gsum = (double*)(mine + 128 + 2 * CG_MAX_RANKS * LL_SLOT_BYTES);
   y.opt = c->opt_sync;
   y.rank = c->comm ? comm_rank(c->comm) : 0;
   y.nranks = c->comm ? comm_nranks(c->comm) : 1;
@@ -184,6 +187,16 @@ int reset_trace(pf_ctx* c, cudaStream_t st) {
   for (int k = 0; k < 8; ++k)
     PF_CUDA(c, cudaMemsetAsync(c->cg_part + PF_TRACE_OFFSET + 8 * k, 0xff, sizeof(double), st));
   return PF_OK;
+}
+
+// k_cg_small instantiation for `np` column pairs per thread (1, 2, 4 or 8)
+const void* small_kernel(bool unit, int np) {
+  switch (np) {
+    case 1: return unit ? (const void*)k_cg_small<true, 1> : (const void*)k_cg_small<false, 1>;
+    case 2: return unit ? (const void*)k_cg_small<true, 2> : (const void*)k_cg_small<false, 2>;
+    case 4: return unit ? (const void*)k_cg_small<true, 4> : (const void*)k_cg_small<false, 4>;
+    default: return unit ? (const void*)k_cg_small<true, 8> : (const void*)k_cg_small<false, 8>;
+  }
 }
 
 template <bool UNIT>
@@ -217,10 +230,11 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
   cg_geometry(c, a);
   const bool unit = is_unit(dx, dy);
   const int small_rows = (s.nyl + c->sm_count - 1) / c->sm_count;
-  const size_t small_smem = sizeof(double) * (size_t)s.nx * ((size_t)(small_rows + 2) * 2 + small_rows);
+  const size_t small_smem = small_smem_bytes(s.nx, small_rows);
+  const long long small_pairs = (long long)small_rows * (s.nx / 2);          // column pairs per CTA
   if (c->opt_kernel == 3 && !c->comm && c->small_ok && s.nx % 2 == 0 && s.nx <= 2048 && c->sm_count <= SM_MAX_GRID &&
-      (long long)small_rows * (s.nx / 2) <= (long long)SM_PAIRS * SM_THREADS && small_smem <= (size_t)SM_MAX_SMEM) {
-    // shared-memory-resident solve for small grids (config 2): x, r, p never leave the SMs
+      small_pairs <= (long long)SM_PAIRS * SM_THREADS && small_smem <= (size_t)SM_MAX_SMEM) {
+    // on-chip solve for small grids (config 2): x, r, q, p in registers, p + halo rows in shared memory
     SmallArgs sa{};
     sa.s = s; sa.b = c->b; sa.x = c->x; sa.rhalo = c->small_halo; sa.part = c->small_part; sa.scal = c->scal;
     sa.epoch = (unsigned long long*)(c->ws_base + c->sync_off) + 7;
@@ -229,21 +243,17 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     PF_CUDA(c, cudaMemsetAsync(sa.err, 0, sizeof(unsigned long long), st));
     const int grid = (s.nyl + small_rows - 1) / small_rows;
     void* args[] = {&sa};
-    const void* fn = unit ? (const void*)k_cg_small<true> : (const void*)k_cg_small<false>;
+    const int np = small_pairs <= SM_THREADS ? 1 : small_pairs <= 2 * SM_THREADS ? 2 : small_pairs <= 4 * SM_THREADS ? 4 : 8;
+    const void* fn = small_kernel(unit, np);
     PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SM_THREADS), args, small_smem, st));
     c->launches++;
   } else if (c->opt_kernel == 3 && (!c->comm || c->peers) && c->tma_grid > 0 && s.nx % TM_CW == 0 && s.nyl >= 2) {
     // TMA-fed sweeps, dynamically scheduled 1024-column tiles (16 rows, more for huge slabs), one CTA per SM;
     // with several ranks: halo rows + dot-product partials over NVLink peer memory inside the same kernel
-    a.nchunks = s.nx / TM_CW;
-    a.tile_rows = TD_ROWS;
-    while ((long long)a.nchunks * ((s.nyl + a.tile_rows - 1) / a.tile_rows) > CG_MAX_TILES) a.tile_rows *= 2;
-    // short slabs (strong scaling): keep >= ~6 tiles per CTA so the dynamic schedule can balance
-    while (a.tile_rows > 4 && (long long)a.nchunks * ((s.nyl + a.tile_rows - 1) / a.tile_rows) < 6LL * c->tma_grid)
-      a.tile_rows /= 2;
-    a.nbands = (s.nyl + a.tile_rows - 1) / a.tile_rows;
-    a.ntiles = a.nchunks * a.nbands;
-    a.wx = TM_WARPS; a.wy = 1;
+    // tile geometry: 16-row tiles (taller on huge slabs, shorter on short ones) with a few bands of quarter-height
+    // tiles at both ends of the slab, so that both sweeps end on short tiles (pf_cg_tma.cuh)
+    tmad_geometry(a, c->tma_grid, c->opt_tile_rows, c->opt_small_rows, c->opt_nb_small);
+    PF_CUDA(c, cudaMemsetAsync(c->cg_part + PF_GCOUNT_OFFSET, 0, sizeof(unsigned) * CG_MAX_GROUPS, st));
     if (c->comm) {
       PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_BB, 2, 0, st, c->err));
       PF_TRY(comm_halo(c->comm, c->r, 1, 1, st, c->err));
@@ -495,8 +505,11 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
     }
     (void)cudaGetLastError();
   }
-  c->small_ok = cudaFuncSetAttribute(k_cg_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_SMEM) == cudaSuccess &&
-                cudaFuncSetAttribute(k_cg_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_SMEM) == cudaSuccess;
+  c->small_ok = true;
+  for (int np = 1; np <= SM_PAIRS; np *= 2)
+    for (int unit = 0; unit < 2; ++unit)
+      c->small_ok = c->small_ok && cudaFuncSetAttribute(small_kernel(unit != 0, np), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         SM_MAX_SMEM) == cudaSuccess;
   (void)cudaGetLastError();
   c->gen_grid = std::min(c->sm_count * std::max(1, std::min(occ_gen_u, occ_gen_g)), CG_MAX_GRID);
 #undef PF_CREATE_CUDA
@@ -530,6 +543,9 @@ int pf_set_option(pf_ctx* c, const char* key, int value) {
   if (strcmp(key, "cg_sync_opt") == 0) { c->opt_sync = value; return PF_OK; }
   if (strcmp(key, "cg_kernel") == 0) { c->opt_kernel = value; return PF_OK; }
   if (strcmp(key, "cg_rows_min") == 0 && value >= 1) { c->opt_rows_min = value; return PF_OK; }
+  if (strcmp(key, "cg_tile_rows") == 0 && value >= 0) { c->opt_tile_rows = value; return PF_OK; }
+  if (strcmp(key, "cg_small_rows") == 0 && value >= -1) { c->opt_small_rows = value; return PF_OK; }
+  if (strcmp(key, "cg_nb_small") == 0 && value >= -1) { c->opt_nb_small = value; return PF_OK; }
   return fail(c, PF_ERR_ARG, "pf_set_option", key);
 }
 

@@ -64,8 +64,16 @@ constexpr int CG_UB = PF_CG_UB;   // ... in phase B (3 arrays)
 constexpr int CG_MAX_GRID = 2048;
 
 constexpr int CG_MAX_RANKS = 8;
-constexpr int PF_TRACE_OFFSET = 2 * 8192;   // doubles: behind the per-tile partials (2 x CG_MAX_TILES)
-constexpr int PF_PART_DOUBLES = 2 * 8192 + 64;
+// Layout of the CG partial-sum scratch (doubles): [2][CG_MAX_TILES] per-tile partials of the TMA kernels (the
+// other kernels use [3][CG_MAX_GRID] per-CTA partials in the same space), 64 doubles of barrier timeline,
+// [2][CG_MAX_GROUPS] per-group partials and CG_MAX_GROUPS u32 group counters (hierarchical fold, pf_cg_tma.cuh).
+constexpr int CG_MAX_TILES = 16384;         // per-tile partial sums of the dynamically scheduled kernel
+constexpr int CG_TILE_GROUP = 64;           // tiles per fold group
+constexpr int CG_MAX_GROUPS = CG_MAX_TILES / CG_TILE_GROUP;
+constexpr int PF_TRACE_OFFSET = 2 * CG_MAX_TILES;
+constexpr int PF_GPART_OFFSET = PF_TRACE_OFFSET + 64;
+constexpr int PF_GCOUNT_OFFSET = PF_GPART_OFFSET + 2 * CG_MAX_GROUPS;
+constexpr int PF_PART_DOUBLES = PF_GCOUNT_OFFSET + CG_MAX_GROUPS / 2;
 
 // Cross-GPU exchange state of the persistent kernel (multi-GPU slabs).  The
 // `peer_*` pointers are the SAME buffers of the other ranks, mapped into this
@@ -74,8 +82,8 @@ struct CgSync {
   unsigned long long* arrive;    // local: monotonic count of CTA arrivals
   unsigned long long* release;   // local: last epoch released to the local CTAs
   unsigned long long* flags;     // local, written by peers: epoch published by rank q
-  double* mbox;                  // local, written by peers: [2][CG_MAX_RANKS][4] partial sums
-  double* gsum;                  // local: [2][4] sums over all ranks for the local CTAs
+  double* mbox;                  // local, written by peers: [2][CG_MAX_RANKS] 64-byte LL slots of partial sums
+  double* gsum;                  // local: one 64-byte LL slot, sums over all ranks for the local CTAs
   unsigned long long* epoch;     // local: epoch counter persisted between launches
   unsigned long long* err;       // local: != 0 after a spin-wait timeout
   unsigned long long* tickets;   // local: monotonic tile-ticket counter (k_cg_tmad)
@@ -105,7 +113,9 @@ struct CgArgs {
   int maxiter;
   int wx, wy;         // warp arrangement inside a CTA tile, wx*wy == CG_WARPS
   int nchunks, nbands, ntiles;
-  int tile_rows;      // rows per tile of the dynamically scheduled TMA kernel
+  int tile_rows;      // rows per (big) tile of the dynamically scheduled TMA kernel
+  int small_rows;     // rows per small tile: nb_small bands of them at EACH end of the slab (0: uniform tiles), so that
+  int nb_small;       // the last tickets of both sweeps are short and the CTAs finish a phase close together
   CgSync y;           // only used by the multi-GPU persistent kernel
 };
 
@@ -631,11 +641,6 @@ __device__ __forceinline__ double ld_sys_f64(const double* p) {
 
 constexpr long long CG_SPIN_LIMIT = 20000000000LL;   // ~10 s of SM clocks: never hang the GPU
 
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -656,48 +661,14 @@ __device__ __forceinline__ unsigned long long* trace_slot(const CgArgs& a, unsig
   return (unsigned long long*)(a.part + PF_TRACE_OFFSET) + (k - 401) * 8;
 }
 
-// 32-byte packets {epoch, v0, v1, v2}: written with ONE 256-bit store and polled with
-// ONE 256-bit load (LDG/STG.256 on sm_100), so a reader that sees the new epoch sees
-// the values of the same store -- no fence and no second round trip between flag
-// and payload.  Packets are 32-byte aligned (one L2 sector).
-struct Packet {
-  unsigned long long epoch;
-  double v[3];
-};
-__device__ __forceinline__ Packet ld_packet_gpu(const void* p) {
-  Packet k;
-  unsigned long long b0, b1, b2, b3;
-  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(p) : "memory");
-  k.epoch = b0;
-  k.v[0] = __longlong_as_double((long long)b1);
-  k.v[1] = __longlong_as_double((long long)b2);
-  k.v[2] = __longlong_as_double((long long)b3);
-  return k;
-}
-__device__ __forceinline__ Packet ld_packet_sys(const void* p) {
-  Packet k;
-  unsigned long long b0, b1, b2, b3;
-  asm volatile("ld.relaxed.sys.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(p) : "memory");
-  k.epoch = b0;
-  k.v[0] = __longlong_as_double((long long)b1);
-  k.v[1] = __longlong_as_double((long long)b2);
-  k.v[2] = __longlong_as_double((long long)b3);
-  return k;
-}
-__device__ __forceinline__ void st_packet_gpu(void* p, unsigned long long e, double v0, double v1, double v2) {
-  asm volatile("st.relaxed.gpu.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(e), "l"(__double_as_longlong(v0)),
-               "l"(__double_as_longlong(v1)), "l"(__double_as_longlong(v2)) : "memory");
-}
-__device__ __forceinline__ void st_packet_sys(void* p, unsigned long long e, double v0, double v1, double v2) {
-  asm volatile("st.relaxed.sys.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(e), "l"(__double_as_longlong(v0)),
-               "l"(__double_as_longlong(v1)), "l"(__double_as_longlong(v2)) : "memory");
-}
-
+// Packets of the exchanges below: three doubles as six LL words (pf_common.cuh) in a 64-byte slot; a
+// reader accepts a packet when every word carries the tag of the epoch it waits for, so flag and payload
+// need no fence between them and no access wider than 64 bits has to be indivisible.
 // Ends a phase on 1..8 GPUs.  Returns false if a spin-wait timed out (error flag).
 // Chain after the last CTA arrives: fold the per-CTA partials (one pass, one block
-// reduction) -> (R > 1: one system fence, one 32-byte packet per peer, wait for the
-// peers' packets, sum in RANK order) -> one 32-byte release packet -> the other CTAs
-// see epoch and sums in the same load -> one acquire fence per CTA.
+// reduction) -> (R > 1: one system fence, one LL packet per peer, wait for the
+// peers' packets, sum in RANK order) -> one LL release packet -> the other CTAs
+// find tag and sums in the same words -> one acquire load per CTA.
 template <int NV>
 __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long long e, double (&vals)[NV],
                                               double (&out)[NV], double* sm, unsigned long long e0 = 0) {
@@ -739,25 +710,25 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
     block_sum_n<3>(loc, sm);
     if (tid == 0 && tr) tr[2] = gtime();
     if (R > 1) {
-      char* slot_of_me = (char*)0 + (size_t)(par * CG_MAX_RANKS + y.rank) * sizeof(Packet);
+      const size_t slot_of_me = (size_t)(par * CG_MAX_RANKS + y.rank) * LL_SLOT_BYTES;
       if (tid == 0) {
         __threadfence_system();      // the halo rows pushed by the other CTAs of this GPU go out before the packet
-        for (int q = 0; q < R; ++q) st_packet_sys((char*)y.peer_mbox[q] + (size_t)slot_of_me, e, loc[0], loc[1], loc[2]);
+        for (int q = 0; q < R; ++q) st_ll_triple<LL_SYS>((char*)y.peer_mbox[q] + slot_of_me, e, loc[0], loc[1], loc[2]);
         if (tr) tr[3] = gtime();
       }
       __shared__ double s_peer[CG_MAX_RANKS][3];
       if (tid < R) {
         const long long t0 = clock64();
-        Packet k;
-        const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * sizeof(Packet);
-        while ((k = ld_packet_sys(src)).epoch != e) {
+        double k[3];
+        const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * LL_SLOT_BYTES;
+        while (!ld_ll_triple<LL_SYS>(src, e, k)) {
           if (clock64() - t0 > CG_SPIN_LIMIT) {
             atomicExch(y.err, 1ULL);
             break;
           }
         }
         (void)ld_acquire_sys((const unsigned long long*)src);   // acquire: the peers' halo-row stores are visible now
-        s_peer[tid][0] = k.v[0]; s_peer[tid][1] = k.v[1]; s_peer[tid][2] = k.v[2];
+        s_peer[tid][0] = k[0]; s_peer[tid][1] = k[1]; s_peer[tid][2] = k[2];
       }
       __syncthreads();
       if (tid == 0) {
@@ -771,21 +742,21 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
     if (tid == 0) {
       if (tr) tr[4] = gtime();
       __threadfence();               // (R > 1) peers' halo rows, made visible to this thread, go before the release
-      st_packet_gpu(y.gsum, e, loc[0], loc[1], loc[2]);
+      st_ll_triple<LL_GPU>(y.gsum, e, loc[0], loc[1], loc[2]);
       if (tr) tr[5] = gtime();
     }
   }
   if (tid == 0) {
     const long long t0 = clock64();
-    Packet k;
-    while ((k = ld_packet_gpu(y.gsum)).epoch != e) {
+    double k[3];
+    while (!ld_ll_triple<LL_GPU>(y.gsum, e, k)) {
       if (clock64() - t0 > CG_SPIN_LIMIT) {
         atomicExch(y.err, 1ULL);
         break;
       }
     }
     (void)ld_acquire_gpu((const unsigned long long*)y.gsum);   // acquire: later loads (incl. halo rows written by peers) see fresh data
-    s_out[0] = k.v[0]; s_out[1] = k.v[1]; s_out[2] = k.v[2];
+    s_out[0] = k[0]; s_out[1] = k[1]; s_out[2] = k[2];
     s_out[3] = (ld_relaxed_u64(y.err) == 0ULL) ? 1.0 : 0.0;
     if (tr && blockIdx.x == 0) tr[6] = gtime();
   }

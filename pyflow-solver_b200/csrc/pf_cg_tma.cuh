@@ -26,8 +26,6 @@
 
 namespace pf {
 
-constexpr int CG_MAX_TILES = 8192;           // per-tile partial sums of the dynamically scheduled kernel
-static_assert(PF_TRACE_OFFSET == 2 * CG_MAX_TILES, "trace region sits behind the tile partials");
 
 constexpr int TM_WARPS = 16;
 constexpr int TM_THREADS = (TM_WARPS + 1) * 32;
@@ -464,13 +462,57 @@ struct DynShared {
   unsigned long long n_end, seq_end;   // producer's counters at the end of a phase
 };
 
+// Tile t = band * nchunks + chunk.  Bands: nb_small small ones (small_rows rows) at the bottom of the slab, then
+// big ones (tile_rows rows), then nb_small small ones at the top.  Phase A draws tiles in ascending and phase B
+// in descending order, so both sweeps END on small tiles: the spread between the first and the last CTA to
+// finish a phase is about one tile duration (10-12 us with uniform 16-row tiles at 4096^2, timeline in
+// profiles/r2_barrier_timeline_2gpu_v1.txt).
+__host__ __device__ __forceinline__ void tmad_band_rows(const CgArgs& a, int bd, int& j0, int& j1) {
+  const int nyl = a.s.nyl;
+  const int lo = a.nb_small * a.small_rows;           // rows covered by the small bands at each end
+  const int nbig = a.nbands - 2 * a.nb_small;
+  if (bd < a.nb_small) {
+    j0 = bd * a.small_rows;
+    j1 = j0 + a.small_rows;
+  } else if (bd < a.nb_small + nbig) {
+    j0 = lo + (bd - a.nb_small) * a.tile_rows;
+    j1 = j0 + a.tile_rows;
+    if (j1 > nyl - lo) j1 = nyl - lo;
+  } else {
+    j0 = nyl - lo + (bd - a.nb_small - nbig) * a.small_rows;
+    j1 = j0 + a.small_rows;
+  }
+}
+
+// Host side: tile geometry for a slab of nyl rows on a grid of G CTAs (pf_api.cu, tests/hostemu).
+// tile_rows_min > 0 forces the big-tile height (tests); small tiles only when the slab is tall enough.
+inline void tmad_geometry(CgArgs& a, int G, int force_tile_rows = 0, int force_small_rows = -1, int force_nb_small = -1) {
+  const int nyl = a.s.nyl;
+  a.nchunks = a.s.nx / TM_CW;
+  int hb = force_tile_rows > 0 ? force_tile_rows : 16;
+  if (force_tile_rows <= 0) {
+    while ((long long)a.nchunks * ((nyl + hb - 1) / hb) > CG_MAX_TILES / 2) hb *= 2;
+    // short slabs (strong scaling): keep >= ~6 tiles per CTA so the dynamic schedule can balance
+    while (hb > 4 && (long long)a.nchunks * ((nyl + hb - 1) / hb) < 6LL * G) hb /= 2;
+  }
+  int hs = force_small_rows >= 0 ? force_small_rows : (hb >= 8 ? hb / 4 : 0);
+  int ks = force_nb_small >= 0 ? force_nb_small : (hs > 0 ? (2 * G + a.nchunks - 1) / a.nchunks : 0);
+  if (hs <= 0 || ks <= 0 || 2LL * ks * hs > nyl / 2) { hs = 0; ks = 0; }
+  a.tile_rows = hb;
+  a.small_rows = hs;
+  a.nb_small = ks;
+  const int mid = nyl - 2 * ks * hs;
+  a.nbands = 2 * ks + (mid + hb - 1) / hb;
+  a.ntiles = a.nchunks * a.nbands;
+  a.wx = TM_WARPS; a.wy = 1;
+}
+
 __device__ __forceinline__ TmaTile tmad_tile(const CgArgs& a, int t) {
   TmaTile w;
   const int c = t % a.nchunks, bd = t / a.nchunks;
   w.active = true;
   w.i0 = c * TM_CW;
-  w.j0 = bd * a.tile_rows;
-  w.j1 = w.j0 + a.tile_rows > a.s.nyl ? a.s.nyl : w.j0 + a.tile_rows;
+  tmad_band_rows(a, bd, w.j0, w.j1);
   w.cs = w.i0 - TM_HALO < 0 ? 0 : w.i0 - TM_HALO;
   w.ce = w.i0 + TM_CW + TM_HALO > a.s.nx ? a.s.nx : w.i0 + TM_CW + TM_HALO;
   return w;
@@ -535,10 +577,17 @@ __device__ __forceinline__ bool tmad_produce(const CgArgs& a, const Ring& rg, Dy
   }
 }
 
-// Last compute warp to finish a tile adds the warp partials in warp order.
+// Last compute warp to finish a tile adds the warp partials in warp order.  Tiles are accounted in groups of
+// CG_TILE_GROUP consecutive ids: the warp that completes the last tile of a group in this phase folds the
+// group's tile partials (fixed shape: lane i adds tiles i and i + 32 of the group, then the xor tree) into one
+// group partial -- during the sweep, off the critical path -- so that the phase-end fold reads ntiles / 64
+// values instead of ntiles: with every CTA folding 1024 x 2 partials after the grid barrier the reads of the
+// whole grid landed on the few L2 slices 16 KiB map to (~1.2 us), and the last-arriving CTA of the multi-GPU
+// exchange spent 2.3 us (4096^2) to 10 us (16384^2) folding alone.  The result does not depend on which SM
+// processed which tile, nor on which warp folds a group.
 template <int NV>
 __device__ __forceinline__ void tmad_tile_partial(const CgArgs& a, DynShared* ds, int slot, int tile, int warp,
-                                                  double (&v)[NV], bool negate) {
+                                                  double (&v)[NV], bool negate, unsigned phase_seq) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
@@ -552,6 +601,10 @@ __device__ __forceinline__ void tmad_tile_partial(const CgArgs& a, DynShared* ds
   prev = __shfl_sync(0xffffffffu, prev, 0);
   if (prev == (unsigned)TM_WARPS - 1u) {              // every warp's partial of this tile is in shared memory
     __threadfence_block();
+    const int g = tile / CG_TILE_GROUP;
+    const int gfirst = g * CG_TILE_GROUP;
+    const int gsize = (a.ntiles - gfirst) < CG_TILE_GROUP ? (a.ntiles - gfirst) : CG_TILE_GROUP;
+    unsigned done = 0;
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
@@ -560,14 +613,50 @@ __device__ __forceinline__ void tmad_tile_partial(const CgArgs& a, DynShared* ds
         a.part[k * CG_MAX_TILES + tile] = negate ? -t : t;
       }
       ds->count[slot] = 0u;
+      __threadfence();                                // release: the tile partial goes before the group count
+      done = atomicAdd((unsigned*)(a.part + PF_GCOUNT_OFFSET) + g, 1u);
+      __threadfence();                                // acquire (when this was the group's last tile)
+    }
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done == phase_seq * (unsigned)gsize + (unsigned)gsize - 1u) {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+        if (lane < gsize) t += ld_cg(a.part + k * CG_MAX_TILES + gfirst + lane);
+        if (lane + 32 < gsize) t += ld_cg(a.part + k * CG_MAX_TILES + gfirst + lane + 32);
+        t = warp_sum(t);
+        if (lane == 0) a.part[PF_GPART_OFFSET + k * CG_MAX_GROUPS + g] = t;
+      }
     }
   }
+}
+
+// Phase-end fold of the group partials (<= CG_MAX_GROUPS values per sum) by warp 0; every thread of the CTA gets
+// the totals.  Same fixed order in every CTA of every GPU.  Call with all threads of the CTA.
+template <int NV>
+__device__ __forceinline__ void tmad_fold_groups(const CgArgs& a, double (&out)[NV], double* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ng = (a.ntiles + CG_TILE_GROUP - 1) / CG_TILE_GROUP;
+  __syncthreads();                                    // protect sm from a previous use
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = 0.0;
+      for (int q = lane; q < ng; q += 32) t += ld_cg(a.part + PF_GPART_OFFSET + k * CG_MAX_GROUPS + q);
+      t = warp_sum(t);
+      if (lane == 0) sm[k] = t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) out[k] = sm[k];
 }
 
 template <bool UNIT, int XE, bool MULTI>
 __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* pnew,
                                                double* peer_lo, double* peer_hi, bool first, double beta,
-                                               unsigned long long& n, unsigned long long& seq) {
+                                               unsigned long long& n, unsigned long long& seq, unsigned phase_seq) {
   const Slab& s = a.s;
   constexpr int DIR = +1;
   const int lane = threadIdx.x & 31;
@@ -651,7 +740,7 @@ __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, 
       cur = nw;
     }
     double v[1] = {acc};
-    tmad_tile_partial<1>(a, ds, slot, tile, warp, v, /*negate=*/true);     // p.q = -(sum p*lap)
+    tmad_tile_partial<1>(a, ds, slot, tile, warp, v, /*negate=*/true, phase_seq);     // p.q = -(sum p*lap)
     ++seq;
   }
 }
@@ -659,7 +748,7 @@ __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, 
 template <bool UNIT, int XE, bool MULTI>
 __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* x,
                                                double* r, double* peer_lo, double* peer_hi, double alpha, uint64_t pol,
-                                               unsigned long long& n, unsigned long long& seq) {
+                                               unsigned long long& n, unsigned long long& seq, unsigned phase_seq) {
   const Slab& s = a.s;
   constexpr int DIR = -1;
   const int lane = threadIdx.x & 31;
@@ -742,7 +831,7 @@ __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, 
       prev = cur;
       cur = nw;
     }
-    tmad_tile_partial<2>(a, ds, slot, tile, warp, v, /*negate=*/false);
+    tmad_tile_partial<2>(a, ds, slot, tile, warp, v, /*negate=*/false, phase_seq);
     ++seq;
   }
 }
@@ -750,7 +839,7 @@ __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, 
 // Phase end for several GPUs.  Every CTA arrives (gpu-scope release: its stores, peer halo rows
 // included, become visible to the CTA that arrives last); the last CTA folds the per-TILE partials,
 // issues ONE system fence (cumulative: it also publishes the halo rows pushed by the other CTAs) and
-// writes one 32-byte packet {epoch, v0, v1, v2} into the mailbox of EVERY rank, its own included.
+// writes one LL packet (three doubles as six self-validating words) into the mailbox of EVERY rank, its own included.
 // All CTAs of all ranks then poll their local mailbox directly -- no separate local release hop --
 // and add the packets in rank order, so every CTA of every GPU holds bit-identical sums.
 template <int NV>
@@ -771,27 +860,38 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
   }
   __syncthreads();
   if (s_last) {
-    if (tid == 0) __threadfence();
+    if (tid == 0) __threadfence();   // acquire: every CTA's group partials and peer halo stores happen-before what follows
     __syncthreads();
-    double loc[3] = {0.0, 0.0, 0.0};
-    for (int q = tid; q < a.ntiles; q += blockDim.x) {
+    // ONE system fence (cumulative: it also publishes the halo rows pushed by the other CTAs), issued by the
+    // thread that will write the packets, WHILE warp 0 folds the group partials: the two ~2 us steps overlap
+    const bool publisher = (tid == TM_WARPS * 32);
+    if (publisher) __threadfence_system();
+    if (tid < 32) {
+      const int ng = (a.ntiles + CG_TILE_GROUP - 1) / CG_TILE_GROUP;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) loc[k] += ld_cg(a.part + k * CG_MAX_TILES + q);
+      for (int k = 0; k < 3; ++k) {
+        double t = 0.0;
+        if (k < NV) {
+          for (int q = tid; q < ng; q += 32) t += ld_cg(a.part + PF_GPART_OFFSET + k * CG_MAX_GROUPS + q);
+          t = warp_sum(t);
+        }
+        if (tid == 0) s_out[k] = t;
+      }
+      if (tid == 0 && tr) tr[2] = gtime();
     }
-    block_sum_n<3>(loc, sm);
-    if (tid == 0) {
-      if (tr) tr[2] = gtime();
-      __threadfence_system();
-      const size_t slot = (size_t)(par * CG_MAX_RANKS + y.rank) * sizeof(Packet);
-      for (int q = 0; q < R; ++q) st_packet_sys((char*)y.peer_mbox[q] + slot, e, loc[0], loc[1], loc[2]);
+    __syncthreads();
+    if (publisher) {
+      const size_t slot = (size_t)(par * CG_MAX_RANKS + y.rank) * LL_SLOT_BYTES;
+      for (int q = 0; q < R; ++q) st_ll_triple<LL_SYS>((char*)y.peer_mbox[q] + slot, e, s_out[0], s_out[1], s_out[2]);
       if (tr) tr[3] = gtime();
     }
+    __syncthreads();                 // s_out is reused for the totals below
   }
   if (tid < R) {
     const long long t0 = clock64();
-    Packet k;
-    const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * sizeof(Packet);
-    while ((k = ld_packet_sys(src)).epoch != e) {
+    double k[3];
+    const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * LL_SLOT_BYTES;
+    while (!ld_ll_triple<LL_SYS>(src, e, k)) {
       if (clock64() - t0 > CG_SPIN_LIMIT) {
         atomicExch(y.err, 1ULL);
         break;
@@ -801,7 +901,7 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
     // acquire (LDG.STRONG.SYS + L1 invalidate; a full fence.sys = MEMBAR.ALL.SYS cost ~4 us here): the
     // field data of this GPU's other CTAs and the peers' halo rows are visible to what follows
     (void)ld_acquire_sys((const unsigned long long*)src);
-    s_peer[tid][0] = k.v[0]; s_peer[tid][1] = k.v[1]; s_peer[tid][2] = k.v[2];
+    s_peer[tid][0] = k[0]; s_peer[tid][1] = k[1]; s_peer[tid][2] = k[2];
   }
   __syncthreads();
   if (tid == 0) {
@@ -893,9 +993,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
           double* plo = (pnext == a.p0) ? a.y.below_p0 : a.y.below_p1;
           double* phi = (pnext == a.p0) ? a.y.above_p0 : a.y.above_p1;
           if (warp == 0 || warp == TM_WARPS - 1)
-            good = tmad_consume_A<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq);
+            good = tmad_consume_A<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase);
           else
-            good = tmad_consume_A<UNIT, X_IN, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq);
+            good = tmad_consume_A<UNIT, X_IN, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase);
         }
         if (!good) atomicExch(a.y.err, 1ULL);
         ++phase;
@@ -911,7 +1011,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
       } else {
         __threadfence();
         grid.sync();
-        pq = fold_partials(a.part, a.ntiles, sm);
+        double o1[1];
+        tmad_fold_groups<1>(a, o1, sm);
+        pq = o1[0];
       }
       const double alpha = rho / pq;
       // ---------------- phase B
@@ -925,9 +1027,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
           }
         } else {
           if (warp == 0 || warp == TM_WARPS - 1)
-            good = tmad_consume_B<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq);
+            good = tmad_consume_B<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase);
           else
-            good = tmad_consume_B<UNIT, X_IN, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq);
+            good = tmad_consume_B<UNIT, X_IN, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase);
         }
         if (!good) atomicExch(a.y.err, 1ULL);
         ++phase;
@@ -944,13 +1046,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
       } else {
         __threadfence();
         grid.sync();
-        {                                             // both sums in one pass, one block reduction
-          double f[2] = {0.0, 0.0};
-          for (int q = tid; q < a.ntiles; q += blockDim.x) {
-            f[0] += ld_cg(a.part + q);
-            f[1] += ld_cg(a.part + CG_MAX_TILES + q);
-          }
-          block_sum_n<2>(f, sm);
+        {
+          double f[2];
+          tmad_fold_groups<2>(a, f, sm);
           rr = f[0];
           rz = f[1];
         }

@@ -92,6 +92,7 @@ __device__ __forceinline__ void st2_hint(double* p, double a, double b, uint64_t
 __device__ __forceinline__ void st2(double* p, double a, double b) { p[0] = a; p[1] = b; }
 __device__ __forceinline__ void st1(double* p, double a) { p[0] = a; }
 __device__ __forceinline__ double ld_cg(const double* p) { return *(const volatile double*)p; }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
 #else
 __device__ __forceinline__ double2 ld2(const double* p) {
   double2 v;
@@ -147,7 +148,122 @@ __device__ __forceinline__ double ld_cg(const double* p) {  // L2-only (partials
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 #endif  // PF_HOST_EMULATION
+
+// ---- LL words: self-validating 64-bit flag+data words for the lock-free exchanges ------------------
+// Every value that crosses CTAs / GPUs without a fence between "flag" and "payload" travels as LL words
+// (the encoding of NCCL's LL protocol): a 64-bit word = {32-bit tag, 32 payload bits}; a double is two
+// words.  The PTX memory model guarantees single-copy atomicity for scalar accesses of up to 64 bits and
+// models a vector access as independent scalar accesses in unspecified order -- so a reader that finds
+// the expected tag in a word holds the payload of THAT store, whatever happens to the neighbouring words;
+// a packet is accepted only when every one of its words carries the tag.  No 128/256-bit atomicity is
+// assumed anywhere (round 1 relied on STG.256 / LDG.256 being indivisible, which is an implementation
+// property).  Tags are derived from the monotonic exchange epoch and are never 0, so zero-initialised
+// memory never validates.
+constexpr int LL_GPU = 0, LL_SYS = 1;
+
+__host__ __device__ __forceinline__ unsigned ll_tag(unsigned long long e) { return (unsigned)(e % 0xffffffffULL) + 1u; }
+
+struct LLVal {                       // one double as two LL words
+  unsigned long long w0, w1;
+};
+__device__ __forceinline__ LLVal ll_encode(double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  LLVal o;
+  o.w0 = ((unsigned long long)tag << 32) | (b & 0xffffffffULL);
+  o.w1 = ((unsigned long long)tag << 32) | (b >> 32);
+  return o;
+}
+__device__ __forceinline__ bool ll_ok(const LLVal& k, unsigned tag) {
+  return (unsigned)(k.w0 >> 32) == tag && (unsigned)(k.w1 >> 32) == tag;
+}
+__device__ __forceinline__ double ll_value(const LLVal& k) {
+  return __longlong_as_double((long long)((k.w1 << 32) | (k.w0 & 0xffffffffULL)));
+}
+
+#ifdef PF_HOST_EMULATION
+// Host emulation: every word is its own relaxed atomic access and the words of a packet are written in
+// DESCENDING address order with a yield in between -- a reader regularly sees torn packets, which is
+// exactly what the encoding has to survive (tests/test_kernels_on_host.py).
+template <int SCOPE>
+__device__ __forceinline__ void st_ll2(void* p, const LLVal& a) {
+  unsigned long long* q = (unsigned long long*)p;
+  __atomic_store_n(q + 1, a.w1, __ATOMIC_RELAXED);
+  emu_yield();
+  __atomic_store_n(q + 0, a.w0, __ATOMIC_RELAXED);
+}
+template <int SCOPE>
+__device__ __forceinline__ void st_ll4(void* p, const LLVal& a, const LLVal& b) {
+  st_ll2<SCOPE>((unsigned long long*)p + 2, b);
+  emu_yield();
+  st_ll2<SCOPE>(p, a);
+}
+template <int SCOPE>
+__device__ __forceinline__ LLVal ld_ll2(const void* p) {
+  const unsigned long long* q = (const unsigned long long*)p;
+  emu_yield();
+  LLVal k;
+  k.w0 = __atomic_load_n(q + 0, __ATOMIC_RELAXED);
+  k.w1 = __atomic_load_n(q + 1, __ATOMIC_RELAXED);
+  return k;
+}
+template <int SCOPE>
+__device__ __forceinline__ void ld_ll4(const void* p, LLVal& a, LLVal& b) {
+  a = ld_ll2<SCOPE>(p);
+  b = ld_ll2<SCOPE>((const unsigned long long*)p + 2);
+}
+#else
+template <int SCOPE>
+__device__ __forceinline__ void st_ll2(void* p, const LLVal& a) {
+  if (SCOPE == LL_SYS) asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a.w0), "l"(a.w1) : "memory");
+  else asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a.w0), "l"(a.w1) : "memory");
+}
+template <int SCOPE>
+__device__ __forceinline__ void st_ll4(void* p, const LLVal& a, const LLVal& b) {
+  if (SCOPE == LL_SYS)
+    asm volatile("st.relaxed.sys.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a.w0), "l"(a.w1), "l"(b.w0), "l"(b.w1) : "memory");
+  else
+    asm volatile("st.relaxed.gpu.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a.w0), "l"(a.w1), "l"(b.w0), "l"(b.w1) : "memory");
+}
+template <int SCOPE>
+__device__ __forceinline__ LLVal ld_ll2(const void* p) {
+  LLVal k;
+  if (SCOPE == LL_SYS) asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(k.w0), "=l"(k.w1) : "l"(p) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(k.w0), "=l"(k.w1) : "l"(p) : "memory");
+  return k;
+}
+template <int SCOPE>
+__device__ __forceinline__ void ld_ll4(const void* p, LLVal& a, LLVal& b) {
+  if (SCOPE == LL_SYS)
+    asm volatile("ld.relaxed.sys.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a.w0), "=l"(a.w1), "=l"(b.w0), "=l"(b.w1) : "l"(p) : "memory");
+  else
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a.w0), "=l"(a.w1), "=l"(b.w0), "=l"(b.w1) : "l"(p) : "memory");
+}
+#endif  // PF_HOST_EMULATION
+
+// A packet of three doubles = 6 LL words in a 64-byte slot (reduction partials across GPUs / CTAs).
+constexpr int LL_SLOT_BYTES = 64;
+template <int SCOPE>
+__device__ __forceinline__ void st_ll_triple(void* slot, unsigned long long e, double v0, double v1, double v2) {
+  const unsigned t = ll_tag(e);
+  st_ll4<SCOPE>(slot, ll_encode(v0, t), ll_encode(v1, t));
+  st_ll2<SCOPE>((char*)slot + 32, ll_encode(v2, t));
+}
+// One attempt: true (and the three values) iff every word carries the tag of epoch e.
+template <int SCOPE>
+__device__ __forceinline__ bool ld_ll_triple(const void* slot, unsigned long long e, double (&v)[3]) {
+  const unsigned t = ll_tag(e);
+  LLVal a, b;
+  ld_ll4<SCOPE>(slot, a, b);
+  const LLVal c = ld_ll2<SCOPE>((const char*)slot + 32);
+  v[0] = ll_value(a); v[1] = ll_value(b); v[2] = ll_value(c);
+  return ll_ok(a, t) && ll_ok(b, t) && ll_ok(c, t);
+}
 
 // ---- deterministic reductions ----------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -10,6 +10,7 @@
 #pragma once
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -119,6 +120,7 @@ static inline unsigned long long atomicMax(unsigned long long* p, unsigned long 
 static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) {
   return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST);
 }
+static inline void emu_yield() { sched_yield(); }     // pollers / half-written packets give way (pf_common.cuh LL words)
 long long clock64();                                 // SM clock stand-in: nanoseconds x 2 (emu_kernels.cpp)
 static inline double __longlong_as_double(long long v) { double d; __builtin_memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; __builtin_memcpy(&v, &d, 8); return v; }

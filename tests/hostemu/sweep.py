@@ -56,8 +56,8 @@ print("split sweep done",f"{time.time()-t:.0f}s","bad:",len(bad),flush=True)
 
 ppd=C.POINTER(dp)
 lib.emu_cg_small.argtypes=[i,i,i,dp,dp,dp,dp,dp,C.POINTER(C.c_ulonglong),d,d,d,d,i]
-lib.emu_cg_tmad.argtypes=[i,i,i,dp,dp,dp,dp,dp,d,d,d,d,i,dp,dp,C.POINTER(C.c_ulonglong)]
-lib.emu_cg_tmad_multi.argtypes=[i,i,i,i,ppd,ppd,ppd,ppd,ppd,d,d,d,d,i,ppd,ppd,C.POINTER(C.POINTER(C.c_ubyte))]
+lib.emu_cg_tmad.argtypes=[i,i,i,i,i,dp,dp,dp,dp,dp,d,d,d,d,i,dp,dp,C.POINTER(C.c_ulonglong)]
+lib.emu_cg_tmad_multi.argtypes=[i,i,i,i,i,i,ppd,ppd,ppd,ppd,ppd,d,d,d,d,i,ppd,ppd,C.POINTER(C.POINTER(C.c_ubyte))]
 lib.emu_cg_persistent_multi.argtypes=lib.emu_cg_tmad_multi.argtypes
 ptr=T.ptr
 bad=[]
@@ -91,11 +91,11 @@ for (ny,nx,rows) in [(2,2,1),(2,2,2),(3,2,1),(3,8,2),(4,16,3),(5,64,2),(3,66,1),
     small(ny,nx,rows,(ny+nx)%3!=0)
 print("small sweep done",f"{time.time()-t:.0f}s bad:",len(bad),flush=True)
 t=time.time()
-for (ny,nx,tr) in [(2,1024,4),(2,1024,2),(3,1024,2),(4,1024,4),(5,1024,4),(7,1024,2),(17,1024,16),(16,1024,16),(2,3072,4),(3,2048,2),(9,2048,8),(6,1024,8)]:
-    tmad(ny,nx,tr,(ny+tr)%2==0)
+for (ny,nx,tr) in [(2,1024,4),(2,1024,2),(3,1024,2),(4,1024,4),(5,1024,4),(7,1024,2),(17,1024,16),(16,1024,16),(2,3072,4),(3,2048,2),(9,2048,8),(6,1024,8),(13,1024,(4,1,2)),(20,2048,(4,2,2)),(40,1024,(8,2,3)),(9,1024,(4,1,1))]:
+    tmad(ny,nx,tr,(ny+(tr if isinstance(tr,int) else tr[0]))%2==0)
 print("tmad sweep done",f"{time.time()-t:.0f}s bad:",len(bad),flush=True)
 t=time.time()
-for (R,ny,nx,tr) in [(2,4,1024,4),(2,4,1024,2),(3,6,1024,4),(2,10,1024,4),(4,8,1024,2),(2,6,2048,2),(8,16,1024,2)]:
+for (R,ny,nx,tr) in [(2,4,1024,4),(2,4,1024,2),(3,6,1024,4),(2,10,1024,4),(4,8,1024,2),(2,6,2048,2),(8,16,1024,2),(2,28,1024,(4,1,2)),(3,36,1024,(4,1,1))]:
     multi("tmad",R,ny,nx,tr,(R+ny)%2==0)
 for (R,ny,nx) in [(2,4,2),(2,4,3),(3,6,64),(2,8,65),(4,8,129),(2,6,577),(8,16,33),(5,10,70)]:
     multi("register-window",R,ny,nx,4,(R+nx)%2==0)

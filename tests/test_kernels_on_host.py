@@ -39,42 +39,16 @@ LEGACY_TAGS = ["8x8", "16x12", "5x9", "2x2", "3x3", "2x7", "9x2", "33x17", "70x6
 UPWIND, QUICK, NONE = 0, 1, 2
 
 
-# Host stand-ins for the three PTX helpers k_cg_small uses beyond pf_common.cuh (32-byte packets, relaxed u64 load):
-# spliced into a GENERATED copy of pf_cg_small.cuh, together with per-block storage for its shared memory, so that
-# several of its CTAs can run at once in one process.  The product source is not touched; if one of the patterns
-# below no longer occurs exactly once the generation fails loudly.
-SMALL_HOST_PACKETS = '''
-#include <sched.h>
-#include <string.h>
-namespace pf {
-static pthread_mutex_t emu_packet_mutex = PTHREAD_MUTEX_INITIALIZER;     // a packet is complete or absent
-inline Packet emu_ld_packet(const void* p) {
-  sched_yield();                                   // pollers give way to the CTAs they wait for
-  Packet k;
-  pthread_mutex_lock(&emu_packet_mutex);
-  memcpy(&k, p, sizeof(k));
-  pthread_mutex_unlock(&emu_packet_mutex);
-  return k;
-}
-inline void emu_st_packet(void* p, unsigned long long e, double v0, double v1, double v2) {
-  Packet k;
-  k.epoch = e; k.v[0] = v0; k.v[1] = v1; k.v[2] = v2;
-  pthread_mutex_lock(&emu_packet_mutex);
-  memcpy(p, &k, sizeof(k));
-  pthread_mutex_unlock(&emu_packet_mutex);
-}
-inline unsigned long long emu_ld_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
-}  // namespace pf
-#define ld_packet_gpu emu_ld_packet
-#define st_packet_gpu emu_st_packet
-#define ld_relaxed_u64 emu_ld_u64
-'''
+# k_cg_small: a GENERATED copy of pf_cg_small.cuh gets per-block storage for its shared memory, so that several of its
+# CTAs can run at once in one process.  Its exchanges need no stand-ins: the LL-word helpers of pf_common.cuh have
+# host versions (PF_HOST_EMULATION) that store a packet word by word, highest address first, yielding in between --
+# so the pollers of the emulation regularly see TORN packets, which the encoding must (and does) reject.  The product
+# source is not touched; if one of the patterns below no longer occurs exactly once the generation fails loudly.
 
 
 def generate_small_kernel_copy(dest_dir):
     src = open(os.path.join(ROOT, "pyflow-solver_b200", "csrc", "pf_cg_small.cuh")).read()
     for old, new in (
-            ('#include "pf_cg.cuh"', '#include "pf_cg.cuh"\n' + SMALL_HOST_PACKETS),
             ("extern __shared__ __align__(16) double smem_d[];", "double* smem_d = emu::dyn_shared();"),
             ("__shared__ double sm[3 * 32];", "double* sm = emu::blk_shared(0);"),
             ("__shared__ double s_res[8];", "double* s_res = emu::blk_shared(1);")):
@@ -140,36 +114,14 @@ inline void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, 
 '''
 
 TMA_HOST_PACKETS = '''
-#include <sched.h>
-#include <string.h>
-// ---- host stand-ins for the packet / acquire / timer PTX of pf_cg.cuh (generated copy, tests only) ----
+// ---- host stand-ins for the acquire / timer PTX of pf_cg.cuh (generated copy, tests only); the LL packet words have
+// host versions of their own in pf_common.cuh ----
 namespace pf {
-static pthread_mutex_t emu_tma_packet_mutex = PTHREAD_MUTEX_INITIALIZER;
-inline Packet emu_tma_ld_packet(const void* p) {
-  sched_yield();
-  Packet k;
-  pthread_mutex_lock(&emu_tma_packet_mutex);
-  memcpy(&k, p, sizeof(k));
-  pthread_mutex_unlock(&emu_tma_packet_mutex);
-  return k;
-}
-inline void emu_tma_st_packet(void* p, unsigned long long e, double v0, double v1, double v2) {
-  Packet k;
-  k.epoch = e; k.v[0] = v0; k.v[1] = v1; k.v[2] = v2;
-  pthread_mutex_lock(&emu_tma_packet_mutex);
-  memcpy(p, &k, sizeof(k));
-  pthread_mutex_unlock(&emu_tma_packet_mutex);
-}
 inline unsigned long long emu_tma_ld_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
 inline unsigned long long emu_tma_gtime() { return (unsigned long long)clock64(); }
 }  // namespace pf
-#define ld_packet_sys emu_tma_ld_packet
-#define st_packet_sys emu_tma_st_packet
 #define ld_acquire_sys emu_tma_ld_u64
 #define gtime emu_tma_gtime
-#ifndef ld_relaxed_u64
-#define ld_relaxed_u64 emu_tma_ld_u64
-#endif
 '''
 
 
@@ -209,8 +161,7 @@ def generate_tma_kernel_copy(dest_dir):
 # `__shared__` declarations get per-block storage, and the two templates that argument-dependent lookup would otherwise
 # find twice are renamed.
 MULTI_PTX_HELPERS = ["ld_acquire_sys", "st_release_sys", "ld_acquire_gpu", "st_release_gpu", "st_sys_f64", "ld_sys_f64",
-                     "ld_relaxed_u64", "ld_relaxed_sys_u64", "gtime", "ld_packet_gpu", "ld_packet_sys", "st_packet_gpu",
-                     "st_packet_sys"]
+                     "ld_relaxed_sys_u64", "gtime"]
 MULTI_HEAD = '''// GENERATED (tests only) from the multi-GPU section of pf_cg.cuh.
 #pragma once
 #include "pf_cg.cuh"
@@ -224,32 +175,9 @@ inline unsigned long long ld_acquire_gpu(const unsigned long long* p) { return _
 inline void st_release_gpu(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
 inline void st_sys_f64(double* p, double v) { *(volatile double*)p = v; }
 inline double ld_sys_f64(const double* p) { return *(const volatile double*)p; }
-inline unsigned long long ld_relaxed_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
 inline unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
 inline unsigned long long gtime() { return (unsigned long long)clock64(); }
 '''
-MULTI_PACKETS = '''
-static pthread_mutex_t emu_packet_mutex = PTHREAD_MUTEX_INITIALIZER;     // a packet is complete or absent
-inline Packet ld_packet_sys(const void* p) {
-  sched_yield();
-  Packet k;
-  pthread_mutex_lock(&emu_packet_mutex);
-  memcpy(&k, p, sizeof(k));
-  pthread_mutex_unlock(&emu_packet_mutex);
-  return k;
-}
-inline Packet ld_packet_gpu(const void* p) { return ld_packet_sys(p); }
-inline void st_packet_sys(void* p, unsigned long long e, double v0, double v1, double v2) {
-  Packet k;
-  k.epoch = e; k.v[0] = v0; k.v[1] = v1; k.v[2] = v2;
-  pthread_mutex_lock(&emu_packet_mutex);
-  memcpy(p, &k, sizeof(k));
-  pthread_mutex_unlock(&emu_packet_mutex);
-}
-inline void st_packet_gpu(void* p, unsigned long long e, double v0, double v1, double v2) { st_packet_sys(p, e, v0, v1, v2); }
-'''
-
-
 def generate_multi_kernel_copy(dest_dir):
     import re
     src = open(os.path.join(ROOT, "pyflow-solver_b200", "csrc", "pf_cg.cuh")).read()
@@ -271,9 +199,6 @@ def generate_multi_kernel_copy(dest_dir):
     assert sec.count(smid) == 1
     sec = sec.replace(smid, "smid = 0;")
     assert "asm volatile" not in sec, "pf_cg.cuh changed: PTX left in the multi-GPU section"
-    m = re.search(r"struct Packet \{.*?\};\n", sec, flags=re.S)
-    assert m
-    sec = sec[:m.end()] + MULTI_PACKETS + sec[m.end():]
     counter = [19]                                       # ids 1.. are taken by the TMA copy
 
     def per_block(mm):
@@ -355,9 +280,9 @@ def emu(tmp_path_factory):
     lib.emu_krylov_grid.argtypes = [i] + lib.emu_krylov.argtypes
     lib.emu_cg_split.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp, dp]
     lib.emu_cg_small.argtypes = [i, i, i, dp, dp, dp, dp, dp, C.POINTER(C.c_ulonglong), d, d, d, d, i]
-    lib.emu_cg_tmad.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp, C.POINTER(C.c_ulonglong)]
+    lib.emu_cg_tmad.argtypes = [i, i, i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp, C.POINTER(C.c_ulonglong)]
     ppd = C.POINTER(dp)
-    lib.emu_cg_tmad_multi.argtypes = [i, i, i, i, ppd, ppd, ppd, ppd, ppd, d, d, d, d, i, ppd, ppd,
+    lib.emu_cg_tmad_multi.argtypes = [i, i, i, i, i, i, ppd, ppd, ppd, ppd, ppd, d, d, d, d, i, ppd, ppd,
                                       C.POINTER(C.POINTER(C.c_ubyte))]
     lib.emu_cg_persistent_multi.argtypes = lib.emu_cg_tmad_multi.argtypes
     return lib
@@ -873,7 +798,7 @@ class SmallSolver:
         self.emu, self.ny, self.nx, self.rows = emu, ny, nx, rows
         G = (ny + rows - 1) // rows
         self.rhalo = np.zeros(G * 2 * emu.emu_small_row_packets(nx) * 4)
-        self.part = np.zeros(2 * G * 4)
+        self.part = np.zeros(2 * 160 * 4)                     # [2][SM_MAX_GRID] slots, SM_SLOT_DOUBLES apart
         self.sync = np.zeros(2, dtype=np.uint64)             # epoch (persisted), error flag
 
     def solve(self, b_dev, x_dev, scal, dx, dy, invd, tol, maxiter):
@@ -947,12 +872,17 @@ def test_smallest_even_width_cavities_from_the_cuda_sources_vs_reference_golden(
 # ===================================================================================================================
 # the TMA-fed, dynamically scheduled CG kernel (k_cg_tmad): the production kernel of the 4096^2 ... 16384^2 configs
 # ===================================================================================================================
+def _tiles(tile_rows):
+    """tile_rows: an int (uniform tiles of that height) or (big height, small height, small bands at each end)."""
+    return (tile_rows, 0, 0) if isinstance(tile_rows, int) else tuple(tile_rows)
+
+
 def _tmad_solve(emu, dev, S, sync, b, dx, dy, invd, tol, maxiter, tile_rows):
     ny, nx = b.shape
     bb, x, r, p0, p1 = dev.put(b), dev.put(), dev.put(), dev.put(), dev.put()
     emu.emu_rhs2(nx, ny, ptr(bb), ptr(x), ptr(r), 0, 0, invd, ptr(S.scratch), ptr(S.scal))
     part = np.zeros(emu.emu_cg_part_doubles())
-    emu.emu_cg_tmad(nx, ny, tile_rows, ptr(bb), ptr(x), ptr(r), ptr(p0), ptr(p1), dx, dy, invd, tol, maxiter, ptr(part),
+    emu.emu_cg_tmad(nx, ny, *_tiles(tile_rows), ptr(bb), ptr(x), ptr(r), ptr(p0), ptr(p1), dx, dy, invd, tol, maxiter, ptr(part),
                     ptr(S.scal), sync.ctypes.data_as(C.POINTER(C.c_ulonglong)))
     assert sync[3] == 0, "a bounded wait inside k_cg_tmad timed out"
     return dev.get(x)
@@ -964,6 +894,10 @@ def _tmad_solve(emu, dev, S, sync, b, dx, dy, invd, tol, maxiter, tile_rows):
     (5, 2048, 4, True, False, 4),          # two column chunks x two bands = four tiles, no preconditioner
     (33, 1024, 16, True, True, 2),         # the library's default 16-row tiles: 16 + 16 + 1 rows
     (3, 1024, 4, True, True, 300),         # runs to convergence at a loose tolerance
+    (13, 1024, (4, 1, 2), True, True, 4),  # two 1-row tiles at each end, 4 + 4 + 1 rows between them (both sweeps end on short tiles)
+    (70, 2048, (16, 4, 3), False, True, 2),   # 2 chunks: 3 x 4-row bands, 16 + 16 + 14 rows, 3 x 4-row bands = 18 tiles < one fold group
+    (40, 4096, (4, 2, 4), True, True, 2),  # 4 chunks x (4 + 6 + 4) bands = 56 tiles ... and
+    (70, 4096, (4, 1, 3), True, True, 2),  # 4 chunks x (3 + 16 + 3) bands = 88 tiles: two fold groups (64 + 24)
 ])
 def test_tma_fed_cg_kernel_vs_oracle(emu, ny, nx, tile_rows, unit, jacobi, maxiter):
     """k_cg_tmad<unit, single GPU> on one CTA: producer thread, 8-stage ring, ticket-drawn tiles (ascending in phase
@@ -1014,7 +948,7 @@ def test_whole_projection_steps_with_the_tma_fed_kernel_vs_oracle(emu):
         u, uo, v, vo = uo, u, vo, v
         emu.emu_rhs1(nx, ny, ptr(u), ptr(v), ptr(b), max(dt, 1e-14), 1.0, 1.0, ptr(S.scratch), ptr(S.scal))
         emu.emu_rhs2(nx, ny, ptr(b), ptr(x), ptr(r), 1, 1, 0.25, ptr(S.scratch), ptr(S.scal))
-        emu.emu_cg_tmad(nx, ny, 4, ptr(b), ptr(x), ptr(r), ptr(p0), ptr(p1), 1.0, 1.0, 0.25, 1e-10, 6, ptr(part),
+        emu.emu_cg_tmad(nx, ny, 4, 0, 0, ptr(b), ptr(x), ptr(r), ptr(p0), ptr(p1), 1.0, 1.0, 0.25, 1e-10, 6, ptr(part),
                         ptr(S.scal), sync.ctypes.data_as(C.POINTER(C.c_ulonglong)))
         assert int(S["S_ITERS"]) == od["true_iterations"] and sync[3] == 0
         emu.emu_resid(nx, ny, ptr(b), ptr(x), 1.0, 1.0, ptr(S.scratch), ptr(S.scal))
@@ -1038,7 +972,7 @@ class Ranks:
         self.pitch, self.H = emu.emu_pitch(nx), emu.emu_halo()
         self.parts = [np.zeros(emu.emu_cg_part_doubles()) for _ in range(R)]
         self.scals = [np.zeros(emu.emu_scal_count()) for _ in range(R)]
-        self.syncs = [np.zeros(1024, dtype=np.uint8) for _ in range(R)]          # persist between solves (epochs, tickets)
+        self.syncs = [np.zeros(2048, dtype=np.uint8) for _ in range(R)]          # persist between solves (epochs, tickets)
 
     def slabs(self, full=None, halo=None):
         out = []
@@ -1075,7 +1009,7 @@ class Ranks:
         p0, p1 = self.slabs(zeros, halo=zeros), self.slabs(zeros, halo=zeros)
         sy = (C.POINTER(C.c_ubyte) * R)(*[s_.ctypes.data_as(C.POINTER(C.c_ubyte)) for s_ in self.syncs])
         launch = emu.emu_cg_tmad_multi if kernel == "tmad" else emu.emu_cg_persistent_multi
-        launch(R, self.nx, self.ny, tile_rows, self.arr(bs), self.arr(xs), self.arr(rs), self.arr(p0),
+        launch(R, self.nx, self.ny, *_tiles(tile_rows), self.arr(bs), self.arr(xs), self.arr(rs), self.arr(p0),
                self.arr(p1), dx, dy, invd, tol, maxiter, self.arr(self.parts), self.arr(self.scals), sy)
         assert all(int(s_.view(np.uint64)[3]) == 0 for s_ in self.syncs), "a bounded wait timed out"
         info = {int(sc[emu.emu_slot(b"S_INFO")]) for sc in self.scals}
@@ -1088,6 +1022,7 @@ class Ranks:
     (2, 8, 1024, 4, True, True, 4), (2, 12, 1024, 4, False, True, 5), (3, 9, 1024, 4, True, False, 4),
     (4, 8, 2048, 2, True, True, 3),          # four ranks, two column chunks, two-row slabs
     (2, 4, 1024, 4, True, True, 300),        # runs to convergence: every rank takes the same stop decision
+    (2, 28, 1024, (4, 1, 2), True, True, 3),   # per rank: two 1-row tiles at each end of the 14-row slab, 4 + 4 + 2 rows between
 ])
 def test_multi_gpu_tma_kernel_with_concurrent_ranks_vs_single_domain_oracle(emu, R, ny, nx, tile_rows, unit, jacobi,
                                                                             maxiter):
