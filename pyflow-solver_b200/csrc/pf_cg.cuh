@@ -64,13 +64,14 @@ constexpr int CG_UB = PF_CG_UB;   // ... in phase B (3 arrays)
 constexpr int CG_MAX_GRID = 2048;
 
 constexpr int CG_MAX_RANKS = 8;
-// Layout of the CG partial-sum scratch (doubles): [2][CG_MAX_TILES] per-tile partials of the TMA kernels (the
-// other kernels use [3][CG_MAX_GRID] per-CTA partials in the same space), 64 doubles of barrier timeline,
-// [2][CG_MAX_GROUPS] per-group partials and CG_MAX_GROUPS u32 group counters (hierarchical fold, pf_cg_tma.cuh).
+// Layout of the CG partial-sum scratch (doubles): [2][CG_MAX_TILES][2] per-tile partials of the TMA kernels as LL
+// words (the other kernels use [3][CG_MAX_GRID] per-CTA partials in the same space), 64 doubles of barrier
+// timeline, [2][CG_MAX_GROUPS] per-group partials and CG_MAX_GROUPS u32 group counters (hierarchical fold,
+// pf_cg_tma.cuh).
 constexpr int CG_MAX_TILES = 16384;         // per-tile partial sums of the dynamically scheduled kernel
 constexpr int CG_TILE_GROUP = 64;           // tiles per fold group
 constexpr int CG_MAX_GROUPS = CG_MAX_TILES / CG_TILE_GROUP;
-constexpr int PF_TRACE_OFFSET = 2 * CG_MAX_TILES;
+constexpr int PF_TRACE_OFFSET = 4 * CG_MAX_TILES;
 constexpr int PF_GPART_OFFSET = PF_TRACE_OFFSET + 64;
 constexpr int PF_GCOUNT_OFFSET = PF_GPART_OFFSET + 2 * CG_MAX_GROUPS;
 constexpr int PF_PART_DOUBLES = PF_GCOUNT_OFFSET + CG_MAX_GROUPS / 2;

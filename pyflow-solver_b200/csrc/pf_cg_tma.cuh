@@ -77,6 +77,46 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
+// Address-based variants for the hot loops.  The 32-bit shared address of the ring is pinned in a register once
+// per kernel (an opaque move): left to itself the compiler re-derives it from the CTA's shared window (S2R
+// SR_CgaCtaId + MOV + VIADD + LEA) at every mbarrier operation of every row visit.
+typedef uint32_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr_pin(const void* p) {
+  uint32_t o;
+  asm volatile("mov.u32 %0, %1;" : "=r"(o) : "r"(smem_u32(p)));
+  return o;
+}
+__device__ __forceinline__ bool mbar_try_wait_at(smem_addr_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_at(smem_addr_t bar, uint32_t parity) {
+  if (mbar_try_wait_at(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_at(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ void mbar_arrive_at(smem_addr_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ double2 lds2_at(smem_addr_t p) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(p));
+  return v;
+}
+__device__ __forceinline__ double lds1_at(smem_addr_t p) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(p));
+  return v;
+}
+
 struct TmaTile {
   int i0;            // first column of the tile
   int j0, j1;        // local rows [j0, j1)
@@ -100,6 +140,7 @@ struct Ring {
   unsigned char* base;
   uint64_t* full;
   uint64_t* empty;
+  smem_addr_t base_at, full_at, empty_at;      // the same three as pinned shared addresses (lean loops)
   __device__ __forceinline__ double* stage(int s) const { return (double*)(base + (size_t)s * TM_STAGE_BYTES); }
 };
 
@@ -496,7 +537,9 @@ inline void tmad_geometry(CgArgs& a, int G, int force_tile_rows = 0, int force_s
     while (hb > 4 && (long long)a.nchunks * ((nyl + hb - 1) / hb) < 6LL * G) hb /= 2;
   }
   int hs = force_small_rows >= 0 ? force_small_rows : (hb >= 8 ? hb / 4 : 0);
-  int ks = force_nb_small >= 0 ? force_nb_small : (hs > 0 ? (2 * G + a.nchunks - 1) / a.nchunks : 0);
+  // small end bands are OFF by default: measured at 4096^2 they cost more (two extra row visits per tile) than the
+  // shorter tail of a sweep saves -- 59.1 vs 55.5 ms per 300-iteration launch (profiles/r2_tile_geometry_sweep.txt)
+  int ks = force_nb_small >= 0 ? force_nb_small : 0;
   if (hs <= 0 || ks <= 0 || 2LL * ks * hs > nyl / 2) { hs = 0; ks = 0; }
   a.tile_rows = hb;
   a.small_rows = hs;
@@ -581,13 +624,20 @@ __device__ __forceinline__ bool tmad_produce(const CgArgs& a, const Ring& rg, Dy
 // CG_TILE_GROUP consecutive ids: the warp that completes the last tile of a group in this phase folds the
 // group's tile partials (fixed shape: lane i adds tiles i and i + 32 of the group, then the xor tree) into one
 // group partial -- during the sweep, off the critical path -- so that the phase-end fold reads ntiles / 64
-// values instead of ntiles: with every CTA folding 1024 x 2 partials after the grid barrier the reads of the
-// whole grid landed on the few L2 slices 16 KiB map to (~1.2 us), and the last-arriving CTA of the multi-GPU
-// exchange spent 2.3 us (4096^2) to 10 us (16384^2) folding alone.  The result does not depend on which SM
-// processed which tile, nor on which warp folds a group.
+// values instead of ntiles (the last-arriving CTA of the multi-GPU exchange spent 2.3 us at 4096^2 and 10 us at
+// 16384^2 folding alone, profiles/r2_barrier_timeline_2gpu_v1.txt).  NO FENCE inside the sweep: a fence makes the
+// warp wait for its outstanding field stores and the ring couples all warps of the CTA to the slowest one
+// (measured: +3.7 us per phase).  Instead the tile partials travel as LL words tagged with the phase (pf_common.cuh):
+// the group counter only ELECTS the folding warp (relaxed atomic, orders nothing), which then polls the group's
+// words until each carries the tag.  The result does not depend on which SM processed which tile, nor on which warp
+// folds a group; the group partials are plain stores published by the barrier that ends the phase.
+__device__ __forceinline__ unsigned long long* tmad_ll_partial(const CgArgs& a, int k, int tile) {
+  return (unsigned long long*)a.part + 2 * ((size_t)k * CG_MAX_TILES + (size_t)tile);
+}
+
 template <int NV>
 __device__ __forceinline__ void tmad_tile_partial(const CgArgs& a, DynShared* ds, int slot, int tile, int warp,
-                                                  double (&v)[NV], bool negate, unsigned phase_seq) {
+                                                  double (&v)[NV], bool negate, unsigned phase_seq, unsigned tag) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
@@ -610,21 +660,33 @@ __device__ __forceinline__ void tmad_tile_partial(const CgArgs& a, DynShared* ds
       for (int k = 0; k < NV; ++k) {
         double t = 0.0;
         for (int q = 0; q < TM_WARPS; ++q) t += ds->wpart[slot][k][q];
-        a.part[k * CG_MAX_TILES + tile] = negate ? -t : t;
+        st_ll2<LL_GPU>(tmad_ll_partial(a, k, tile), ll_encode(negate ? -t : t, tag));
       }
       ds->count[slot] = 0u;
-      __threadfence();                                // release: the tile partial goes before the group count
       done = atomicAdd((unsigned*)(a.part + PF_GCOUNT_OFFSET) + g, 1u);
-      __threadfence();                                // acquire (when this was the group's last tile)
     }
     done = __shfl_sync(0xffffffffu, done, 0);
-    if (done == phase_seq * (unsigned)gsize + (unsigned)gsize - 1u) {
-      __syncwarp();
+    if (done == phase_seq * (unsigned)gsize + (unsigned)gsize - 1u) {      // this warp folds the group
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         double t = 0.0;
-        if (lane < gsize) t += ld_cg(a.part + k * CG_MAX_TILES + gfirst + lane);
-        if (lane + 32 < gsize) t += ld_cg(a.part + k * CG_MAX_TILES + gfirst + lane + 32);
+#pragma unroll
+        for (int h = 0; h < CG_TILE_GROUP / 32; ++h) {
+          const int q = lane + 32 * h;
+          if (q < gsize) {
+            const unsigned long long* src = tmad_ll_partial(a, k, gfirst + q);
+            LLVal w = ld_ll2<LL_GPU>(src);
+            const long long t0 = clock64();
+            while (!ll_ok(w, tag)) {
+              if (clock64() - t0 > CG_SPIN_LIMIT) {
+                atomicExch(a.y.err, 1ULL);
+                break;
+              }
+              w = ld_ll2<LL_GPU>(src);
+            }
+            t += ll_value(w);
+          }
+        }
         t = warp_sum(t);
         if (lane == 0) a.part[PF_GPART_OFFSET + k * CG_MAX_GROUPS + g] = t;
       }
@@ -653,14 +715,144 @@ __device__ __forceinline__ void tmad_fold_groups(const CgArgs& a, double (&out)[
   for (int k = 0; k < NV; ++k) out[k] = sm[k];
 }
 
+// ---- lean row loops ---------------------------------------------------------------------------------------
+// Tiles whose visited rows and centre rows are all strictly inside the global domain (every tile except those of
+// the first and last band) need none of the per-row predicates of the generic loops below: every row exists, no
+// Neumann / ring / pin treatment in y, the Jacobi factors are per-lane constants.  The visits are peeled (t = 0: load
+// only; t = 1: first store; t = 2 .. TH: store + stencil; t = TH + 1: stencil only) so that the steady loop carries no
+// conditions on t either, addresses advance by pointer increments, the ring is addressed through pinned 32-bit
+// shared addresses.  Same arithmetic, same operation order as the generic loops: results are bit-identical.
+// ncu on the round-1 kernel: 181 warp instructions per 64-column row visit, 48 % issue utilisation, time
+// proportional to row VISITS (halo visits that hit L2 cost as much as streamed ones) -- the SM side, not DRAM, set
+// the pace at 4096^2.
+struct LeanCtx {
+  smem_addr_t ring_at, full_at, empty_at;
+  uint32_t koff, khoff, kcoff;     // byte offsets of this lane's pair / halo column in a haloed row, pair in an un-haloed row
+  bool vh;
+  int lane;
+};
+
+template <bool UNIT, int XE>
+__device__ __forceinline__ bool tmad_lean_A(const CgArgs& a, const LeanCtx& L, const Cols& c, int TH, double* pdst,
+                                            double beta, uint64_t keep, unsigned long long& n, double& acc) {
+  const size_t pitch = (size_t)a.s.pitch;
+  const double da = (XE != X_IN && c.ring_a) ? 1.0 : a.invd;
+  const double db = (XE != X_IN && c.ring_b) ? 1.0 : a.invd;
+  const double dh = (XE != X_IN && c.ring_h) ? 1.0 : a.invd;
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  auto visit = [&](Row& nw) -> bool {
+    const uint32_t st = (uint32_t)n & (TM_STAGES - 1);
+    if (!mbar_wait_at(L.full_at + 8u * st, (uint32_t)(n / TM_STAGES) & 1u)) return false;
+    const smem_addr_t sa = L.ring_at + st * (uint32_t)TM_STAGE_BYTES;
+    const double2 rr = lds2_at(sa + L.koff);
+    const double2 pp = lds2_at(sa + (uint32_t)(TM_ROW * 8) + L.koff);
+    double rh = 0.0, ph = 0.0;
+    if (L.vh) {
+      rh = lds1_at(sa + L.khoff);
+      ph = lds1_at(sa + (uint32_t)(TM_ROW * 8) + L.khoff);
+    }
+    __syncwarp();
+    if (L.lane == 0) mbar_arrive_at(L.empty_at + 8u * st);
+    ++n;
+    nw.a = (pp.x * beta) + da * rr.x;
+    nw.b = (pp.y * beta) + db * rr.y;
+    nw.h = (ph * beta) + dh * rh;
+    return true;
+  };
+  auto stencil = [&](const Row& south, const Row& centre, const Row& north) {
+    double la, lb;
+    lap_pair<UNIT, XE, false>(a, c, south, centre, north, true, true, la, lb);
+    acc += centre.a * la;
+    acc += centre.b * lb;
+  };
+  Row nw;
+  if (!visit(nw)) return false;                       // t = 0: the row below the tile
+  cur = nw;
+  if (!visit(nw)) return false;                       // t = 1: first tile row
+  st2_hint(pdst, nw.a, nw.b, keep);
+  pdst += pitch;
+  prev = cur; cur = nw;
+#pragma unroll 2
+  for (int t = 2; t <= TH; ++t) {
+    if (!visit(nw)) return false;
+    st2_hint(pdst, nw.a, nw.b, keep);
+    pdst += pitch;
+    stencil(prev, cur, nw);
+    prev = cur; cur = nw;
+  }
+  if (!visit(nw)) return false;                       // t = TH + 1: the row above the tile
+  stencil(prev, cur, nw);
+  return true;
+}
+
+template <bool UNIT, int XE>
+__device__ __forceinline__ bool tmad_lean_B(const CgArgs& a, const LeanCtx& L, const Cols& c, int TH, double* xdst,
+                                            double* rdst, double alpha, uint64_t pol, uint64_t keep,
+                                            unsigned long long& n, double& acc_rr, double& acc_rz) {
+  const size_t pitch = (size_t)a.s.pitch;
+  const double da = (XE != X_IN && c.ring_a) ? 1.0 : a.invd;
+  const double db = (XE != X_IN && c.ring_b) ? 1.0 : a.invd;
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  // rows are visited top -> bottom: prev is the row ABOVE cur
+  auto visit_p = [&](Row& nw, double2& xx, double2& rr, bool centre) -> bool {
+    const uint32_t st = (uint32_t)n & (TM_STAGES - 1);
+    if (!mbar_wait_at(L.full_at + 8u * st, (uint32_t)(n / TM_STAGES) & 1u)) return false;
+    const smem_addr_t sa = L.ring_at + st * (uint32_t)TM_STAGE_BYTES;
+    const double2 pv = lds2_at(sa + L.koff);
+    nw.a = pv.x; nw.b = pv.y; nw.h = 0.0;
+    if (L.vh) nw.h = lds1_at(sa + L.khoff);
+    if (centre) {
+      xx = lds2_at(sa + (uint32_t)(TM_ROW * 8) + L.kcoff);
+      rr = lds2_at(sa + (uint32_t)((TM_ROW + TM_CW) * 8) + L.kcoff);
+    }
+    __syncwarp();
+    if (L.lane == 0) mbar_arrive_at(L.empty_at + 8u * st);
+    ++n;
+    return true;
+  };
+  Row nw;
+  double2 xx = make_double2(0.0, 0.0), rr = make_double2(0.0, 0.0);
+  if (!visit_p(nw, xx, rr, false)) return false;      // t = 0: the row above the tile
+  cur = nw;
+  if (!visit_p(nw, xx, rr, false)) return false;      // t = 1: top tile row
+  prev = cur; cur = nw;
+#pragma unroll 2
+  for (int t = 2; t <= TH + 1; ++t) {                 // centre row = cur, visited row = the one below it
+    if (!visit_p(nw, xx, rr, true)) return false;
+    double la, lb;
+    lap_pair<UNIT, XE, false>(a, c, nw, cur, prev, true, true, la, lb);
+    const double xa = xx.x + alpha * cur.a;
+    const double xb = xx.y + alpha * cur.b;
+    const double ra = rr.x + alpha * la;
+    const double rb = rr.y + alpha * lb;
+    st2_hint(xdst, xa, xb, pol);
+    st2_hint(rdst, ra, rb, keep);
+    xdst -= pitch;
+    rdst -= pitch;
+    acc_rr += ra * ra;
+    acc_rz += ra * (da * ra);
+    acc_rr += rb * rb;
+    acc_rz += rb * (db * rb);
+    prev = cur; cur = nw;
+  }
+  return true;
+}
+
 template <bool UNIT, int XE, bool MULTI>
 __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* pnew,
                                                double* peer_lo, double* peer_hi, bool first, double beta,
-                                               unsigned long long& n, unsigned long long& seq, unsigned phase_seq) {
+                                               unsigned long long& n, unsigned long long& seq, unsigned phase_seq,
+                                               unsigned ptag) {
   const Slab& s = a.s;
   constexpr int DIR = +1;
   const int lane = threadIdx.x & 31;
   const uint64_t keep = (a.y.opt & 8) ? policy_evict_last() : policy_evict_normal();
+  const int k = TM_HALO + warp * STRIP + 2 * lane;                // my first column inside the haloed smem row
+  const int kh = (lane == 0) ? k - 1 : k + 2;                    // strip halo column (lanes 0 / 31)
+  LeanCtx L;
+  L.ring_at = rg.base_at; L.full_at = rg.full_at; L.empty_at = rg.empty_at;
+  L.koff = (uint32_t)k * 8u; L.khoff = (uint32_t)kh * 8u; L.kcoff = (uint32_t)(warp * STRIP + 2 * lane) * 8u;
+  L.lane = lane;
   for (;;) {
     int st = (int)(n % TM_STAGES);
     if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
@@ -678,69 +870,75 @@ __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, 
     const Cols c = strip_cols<XE>(s, i0);
     const int TH = w.j1 - w.j0, nrows = TH + 2;
     const int jl0 = w.j0 - 1;
-    const int k = TM_HALO + warp * STRIP + 2 * lane;
-    const int kh = (lane == 0) ? k - 1 : k + 2;
-    Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
     double acc = 0.0;
-    for (int t = 0; t < nrows; ++t, ++n) {
-      st = (int)(n % TM_STAGES);
-      if (t > 0 && !mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
-      const double* sr = rg.stage(st);
-      const double* sp = sr + TM_ROW;
-      const int jl = jl0 + DIR * t;
-      const int jg = s.row0 + jl;
-      const bool exists = jg >= 0 && jg < s.nyg;
-      double2 rr = make_double2(0.0, 0.0), pp = make_double2(0.0, 0.0);
-      double rh = 0.0, ph = 0.0;
-      if (exists) {
-        rr = *reinterpret_cast<const double2*>(sr + k);
-        if (c.vh) rh = sr[kh];
-        if (!first) {
-          pp = *reinterpret_cast<const double2*>(sp + k);
-          if (c.vh) ph = sp[kh];
+    // lean: no visited or centre row is a global boundary row; with several GPUs also none that is mirrored to a peer
+    const bool lean = !first && !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) && (s.row0 + w.j1 < s.nyg - 1) &&
+                      !(MULTI && (w.j0 == 0 || w.j1 == s.nyl));
+    if (lean) {
+      L.vh = c.vh;
+      if (!tmad_lean_A<UNIT, XE>(a, L, c, TH, pnew + cell(s, w.j0, c.ia), beta, keep, n, acc)) return false;
+    } else {
+      Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+      for (int t = 0; t < nrows; ++t, ++n) {
+        st = (int)(n % TM_STAGES);
+        if (t > 0 && !mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+        const double* sr = rg.stage(st);
+        const double* sp = sr + TM_ROW;
+        const int jl = jl0 + DIR * t;
+        const int jg = s.row0 + jl;
+        const bool exists = jg >= 0 && jg < s.nyg;
+        double2 rr = make_double2(0.0, 0.0), pp = make_double2(0.0, 0.0);
+        double rh = 0.0, ph = 0.0;
+        if (exists) {
+          rr = *reinterpret_cast<const double2*>(sr + k);
+          if (c.vh) rh = sr[kh];
+          if (!first) {
+            pp = *reinterpret_cast<const double2*>(sp + k);
+            if (c.vh) ph = sp[kh];
+          }
         }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(rg.empty + st);
-      const int jgc = jg - DIR;
-      const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
-      const bool ring_row = (jg == 0) || (jg == s.nyg - 1);
-      double da = a.invd, db = a.invd, dh = a.invd;
-      if (XE != X_IN || gen) {
-        da = (ring_row || c.ring_a) ? 1.0 : a.invd;
-        db = (ring_row || c.ring_b) ? 1.0 : a.invd;
-        dh = (ring_row || c.ring_h) ? 1.0 : a.invd;
-      }
-      const double za = da * rr.x, zb = db * rr.y, zh = dh * rh;
-      Row nw;
-      if (first) {
-        nw.a = za; nw.b = zb; nw.h = zh;
-      } else {
-        nw.a = (pp.x * beta) + za;
-        nw.b = (pp.y * beta) + zb;
-        nw.h = (ph * beta) + zh;
-      }
-      if (t >= 1 && t <= TH) {
-        st2_hint(pnew + cell(s, jl, c.ia), nw.a, nw.b, keep);
-        if (MULTI && (jl == 0 || jl == s.nyl - 1)) peer_row_store(s, c, jl, peer_lo, peer_hi, nw.a, nw.b);
-      }
-      if (t >= 2) {
-        const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
-        double la, lb;
-        if (gen) {
-          lap_pair<UNIT, XE, true>(a, c, prev, cur, nw, hs, hn, la, lb);
-          if (jgc == 0 && c.ia == 0) la = -cur.a;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rg.empty + st);
+        const int jgc = jg - DIR;
+        const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
+        const bool ring_row = (jg == 0) || (jg == s.nyg - 1);
+        double da = a.invd, db = a.invd, dh = a.invd;
+        if (XE != X_IN || gen) {
+          da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+          db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+          dh = (ring_row || c.ring_h) ? 1.0 : a.invd;
+        }
+        const double za = da * rr.x, zb = db * rr.y, zh = dh * rh;
+        Row nw;
+        if (first) {
+          nw.a = za; nw.b = zb; nw.h = zh;
         } else {
-          lap_pair<UNIT, XE, false>(a, c, prev, cur, nw, hs, hn, la, lb);
+          nw.a = (pp.x * beta) + za;
+          nw.b = (pp.y * beta) + zb;
+          nw.h = (ph * beta) + zh;
         }
-        acc += cur.a * la;
-        acc += cur.b * lb;
+        if (t >= 1 && t <= TH) {
+          st2_hint(pnew + cell(s, jl, c.ia), nw.a, nw.b, keep);
+          if (MULTI && (jl == 0 || jl == s.nyl - 1)) peer_row_store(s, c, jl, peer_lo, peer_hi, nw.a, nw.b);
+        }
+        if (t >= 2) {
+          const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+          double la, lb;
+          if (gen) {
+            lap_pair<UNIT, XE, true>(a, c, prev, cur, nw, hs, hn, la, lb);
+            if (jgc == 0 && c.ia == 0) la = -cur.a;
+          } else {
+            lap_pair<UNIT, XE, false>(a, c, prev, cur, nw, hs, hn, la, lb);
+          }
+          acc += cur.a * la;
+          acc += cur.b * lb;
+        }
+        prev = cur;
+        cur = nw;
       }
-      prev = cur;
-      cur = nw;
     }
     double v[1] = {acc};
-    tmad_tile_partial<1>(a, ds, slot, tile, warp, v, /*negate=*/true, phase_seq);     // p.q = -(sum p*lap)
+    tmad_tile_partial<1>(a, ds, slot, tile, warp, v, /*negate=*/true, phase_seq, ptag);     // p.q = -(sum p*lap)
     ++seq;
   }
 }
@@ -748,11 +946,19 @@ __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, 
 template <bool UNIT, int XE, bool MULTI>
 __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* x,
                                                double* r, double* peer_lo, double* peer_hi, double alpha, uint64_t pol,
-                                               unsigned long long& n, unsigned long long& seq, unsigned phase_seq) {
+                                               unsigned long long& n, unsigned long long& seq, unsigned phase_seq,
+                                               unsigned ptag) {
   const Slab& s = a.s;
   constexpr int DIR = -1;
   const int lane = threadIdx.x & 31;
   const uint64_t keep = (a.y.opt & 8) ? policy_evict_last() : policy_evict_normal();
+  const int k = TM_HALO + warp * STRIP + 2 * lane;
+  const int kh = (lane == 0) ? k - 1 : k + 2;
+  const int kc = warp * STRIP + 2 * lane;                         // column inside the un-haloed x / r rows
+  LeanCtx L;
+  L.ring_at = rg.base_at; L.full_at = rg.full_at; L.empty_at = rg.empty_at;
+  L.koff = (uint32_t)k * 8u; L.khoff = (uint32_t)kh * 8u; L.kcoff = (uint32_t)kc * 8u;
+  L.lane = lane;
   for (;;) {
     int st = (int)(n % TM_STAGES);
     if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
@@ -770,68 +976,73 @@ __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, 
     const Cols c = strip_cols<XE>(s, i0);
     const int TH = w.j1 - w.j0, nrows = TH + 2;
     const int jl0 = w.j1;
-    const int k = TM_HALO + warp * STRIP + 2 * lane;
-    const int kh = (lane == 0) ? k - 1 : k + 2;
-    const int kc = warp * STRIP + 2 * lane;
-    Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
     double v[2] = {0.0, 0.0};
-    for (int t = 0; t < nrows; ++t, ++n) {
-      st = (int)(n % TM_STAGES);
-      if (t > 0 && !mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
-      const double* sp = rg.stage(st);
-      const double* sx = sp + TM_ROW;
-      const double* sr = sx + TM_CW;
-      const int jl = jl0 + DIR * t;
-      const int jg = s.row0 + jl;
-      const bool exists = jg >= 0 && jg < s.nyg;
-      Row nw = {0.0, 0.0, 0.0};
-      if (exists) {
-        const double2 pv = *reinterpret_cast<const double2*>(sp + k);
-        nw.a = pv.x; nw.b = pv.y;
-        if (c.vh) nw.h = sp[kh];
-      }
-      double2 xx = make_double2(0.0, 0.0), rr = make_double2(0.0, 0.0);
-      if (t >= 2) {
-        xx = *reinterpret_cast<const double2*>(sx + kc);
-        rr = *reinterpret_cast<const double2*>(sr + kc);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(rg.empty + st);
-      if (t >= 2) {
-        const int jc = jl - DIR;
-        const int jgc = jg - DIR;
-        const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
-        const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
-        double la, lb;
-        if (gen) {
-          lap_pair<UNIT, XE, true>(a, c, nw, cur, prev, hs, hn, la, lb);
-          if (jgc == 0 && c.ia == 0) la = -cur.a;
-        } else {
-          lap_pair<UNIT, XE, false>(a, c, nw, cur, prev, hs, hn, la, lb);
+    const bool lean = !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) && (s.row0 + w.j1 < s.nyg - 1) &&
+                      !(MULTI && (w.j0 == 0 || w.j1 == s.nyl));
+    if (lean) {
+      L.vh = c.vh;
+      const size_t o = cell(s, w.j1 - 1, c.ia);
+      if (!tmad_lean_B<UNIT, XE>(a, L, c, TH, x + o, r + o, alpha, pol, keep, n, v[0], v[1])) return false;
+    } else {
+      Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+      for (int t = 0; t < nrows; ++t, ++n) {
+        st = (int)(n % TM_STAGES);
+        if (t > 0 && !mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+        const double* sp = rg.stage(st);
+        const double* sx = sp + TM_ROW;
+        const double* sr = sx + TM_CW;
+        const int jl = jl0 + DIR * t;
+        const int jg = s.row0 + jl;
+        const bool exists = jg >= 0 && jg < s.nyg;
+        Row nw = {0.0, 0.0, 0.0};
+        if (exists) {
+          const double2 pv = *reinterpret_cast<const double2*>(sp + k);
+          nw.a = pv.x; nw.b = pv.y;
+          if (c.vh) nw.h = sp[kh];
         }
-        const double xa = xx.x + alpha * cur.a;
-        const double xb = xx.y + alpha * cur.b;
-        const double ra = rr.x + alpha * la;
-        const double rb = rr.y + alpha * lb;
-        const size_t o = cell(s, jc, c.ia);
-        st2_hint(x + o, xa, xb, pol);
-        st2_hint(r + o, ra, rb, keep);
-        if (MULTI && (jc == 0 || jc == s.nyl - 1)) peer_row_store(s, c, jc, peer_lo, peer_hi, ra, rb);
-        const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
-        double da = a.invd, db = a.invd;
-        if (XE != X_IN || gen) {
-          da = (ring_row || c.ring_a) ? 1.0 : a.invd;
-          db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+        double2 xx = make_double2(0.0, 0.0), rr = make_double2(0.0, 0.0);
+        if (t >= 2) {
+          xx = *reinterpret_cast<const double2*>(sx + kc);
+          rr = *reinterpret_cast<const double2*>(sr + kc);
         }
-        v[0] += ra * ra;
-        v[1] += ra * (da * ra);
-        v[0] += rb * rb;
-        v[1] += rb * (db * rb);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rg.empty + st);
+        if (t >= 2) {
+          const int jc = jl - DIR;
+          const int jgc = jg - DIR;
+          const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
+          const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+          double la, lb;
+          if (gen) {
+            lap_pair<UNIT, XE, true>(a, c, nw, cur, prev, hs, hn, la, lb);
+            if (jgc == 0 && c.ia == 0) la = -cur.a;
+          } else {
+            lap_pair<UNIT, XE, false>(a, c, nw, cur, prev, hs, hn, la, lb);
+          }
+          const double xa = xx.x + alpha * cur.a;
+          const double xb = xx.y + alpha * cur.b;
+          const double ra = rr.x + alpha * la;
+          const double rb = rr.y + alpha * lb;
+          const size_t o = cell(s, jc, c.ia);
+          st2_hint(x + o, xa, xb, pol);
+          st2_hint(r + o, ra, rb, keep);
+          if (MULTI && (jc == 0 || jc == s.nyl - 1)) peer_row_store(s, c, jc, peer_lo, peer_hi, ra, rb);
+          const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
+          double da = a.invd, db = a.invd;
+          if (XE != X_IN || gen) {
+            da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+            db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+          }
+          v[0] += ra * ra;
+          v[1] += ra * (da * ra);
+          v[0] += rb * rb;
+          v[1] += rb * (db * rb);
+        }
+        prev = cur;
+        cur = nw;
       }
-      prev = cur;
-      cur = nw;
     }
-    tmad_tile_partial<2>(a, ds, slot, tile, warp, v, /*negate=*/false, phase_seq);
+    tmad_tile_partial<2>(a, ds, slot, tile, warp, v, /*negate=*/false, phase_seq, ptag);
     ++seq;
   }
 }
@@ -933,6 +1144,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
   rg.base = smem_raw;
   rg.full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TM_STAGES * TM_STAGE_BYTES);
   rg.empty = rg.full + TM_STAGES;
+  rg.base_at = smem_addr_pin(rg.base);
+  rg.full_at = smem_addr_pin(rg.full);
+  rg.empty_at = smem_addr_pin(rg.empty);
   if (tid == 0) {
     for (int q = 0; q < TM_STAGES; ++q) {
       mbar_init(rg.full + q, 1u);
@@ -993,9 +1207,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
           double* plo = (pnext == a.p0) ? a.y.below_p0 : a.y.below_p1;
           double* phi = (pnext == a.p0) ? a.y.above_p0 : a.y.above_p1;
           if (warp == 0 || warp == TM_WARPS - 1)
-            good = tmad_consume_A<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase);
+            good = tmad_consume_A<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
           else
-            good = tmad_consume_A<UNIT, X_IN, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase);
+            good = tmad_consume_A<UNIT, X_IN, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
         }
         if (!good) atomicExch(a.y.err, 1ULL);
         ++phase;
@@ -1027,9 +1241,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
           }
         } else {
           if (warp == 0 || warp == TM_WARPS - 1)
-            good = tmad_consume_B<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase);
+            good = tmad_consume_B<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
           else
-            good = tmad_consume_B<UNIT, X_IN, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase);
+            good = tmad_consume_B<UNIT, X_IN, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
         }
         if (!good) atomicExch(a.y.err, 1ULL);
         ++phase;

@@ -110,6 +110,13 @@ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint6
 inline void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t) {
   bulk_g2s(dst_smem, src_gmem, bytes, bar);
 }
+// address-based variants of the lean loops: on the host an "address" is the pointer itself
+typedef uintptr_t smem_addr_t;
+inline smem_addr_t smem_addr_pin(const void* p) { return (smem_addr_t)p; }
+inline bool mbar_wait_at(smem_addr_t bar, uint32_t parity) { return mbar_wait((uint64_t*)bar, parity); }
+inline void mbar_arrive_at(smem_addr_t bar) { mbar_arrive((uint64_t*)bar); }
+inline double2 lds2_at(smem_addr_t p) { return *(const double2*)p; }
+inline double lds1_at(smem_addr_t p) { return *(const double*)p; }
 
 '''
 
