@@ -103,15 +103,31 @@ def compare(name, got, want, rel_bar=REL_BAR, iter_bar=ITER_BAR):
             "iters": git, "oracle_iters": wit, "max_iter_diff": int(dit), "peer_kernel": peer, "ok": ok}
 
 
+_GLOO = None
+
+
+def _host_barrier():
+    """Barrier over a gloo group: the ranks that wait for rank 0's oracle SLEEP in a socket poll.  (Waiting in the next
+    NCCL collective instead spins one host core per rank, and the OpenMP barriers of the oracle collapse when its
+    threads have to share cores with spinning processes: measured 16 s instead of 0.5 s for a 4096 x 512 case.)"""
+    global _GLOO
+    import torch.distributed as dist
+    if _GLOO is None:
+        _GLOO = dist.new_group(backend="gloo")
+    dist.barrier(group=_GLOO)
+
+
 def check_case(name, cfg, steps, rank=0, world=1, options=None):
-    """One case on `world` GPUs; the comparison happens on rank 0 (other ranks return None)."""
+    """One case on `world` GPUs; the comparison happens on rank 0 (other ranks return None).  Collective."""
     got = gpu_run(cfg, steps, rank, world, options)
-    if rank != 0:
-        return None
-    t0 = time.perf_counter()
-    want = oracle_run(cfg, steps)
-    out = compare(name, got, want)
-    out["oracle_s"] = round(time.perf_counter() - t0, 2)
+    out = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        want = oracle_run(cfg, steps)
+        out = compare(name, got, want)
+        out["oracle_s"] = round(time.perf_counter() - t0, 2)
+    if world > 1:
+        _host_barrier()
     return out
 
 

@@ -12,7 +12,7 @@ cfg = SimpleNamespace(nx=n, ny=n, Re=1000.0, lid_velocity=1.0, cfl_target=0.5, c
 st = allocate_state(n, n); tr = ResidualManager()
 for it in range(5): step(cfg, st, tr, it)
 slab = st.fields._slab
-buf = np.zeros(64); slab._lib.pf_debug_read_partials(slab.ctx, buf.ctypes.data_as(C.POINTER(C.c_double)), 2 * 16384, 64)
+buf = np.zeros(64); slab._lib.pf_debug_read_partials(slab.ctx, buf.ctypes.data_as(C.POINTER(C.c_double)), 4 * 16384, 64)
 t = buf.view(np.uint64).reshape(8, 8).astype(np.int64)
 print(f"n={n} cg_ms {st.meta['cg_ms']:.2f}")
 prev_exit = None

@@ -17,7 +17,7 @@ cfg = SimpleNamespace(nx=NX, ny=ROWS*world, Re=1000.0, lid_velocity=1.0, cfl_tar
 st = allocate_slab_state(NX, ROWS*world, rank, world); tr = ResidualManager()
 for it in range(4): step(cfg, st, tr, it)
 slab = st.fields._slab
-buf = np.zeros(64); slab._lib.pf_debug_read_partials(slab.ctx, buf.ctypes.data_as(C.POINTER(C.c_double)), 2 * 16384, 64)
+buf = np.zeros(64); slab._lib.pf_debug_read_partials(slab.ctx, buf.ctypes.data_as(C.POINTER(C.c_double)), 4 * 16384, 64)
 t = buf.view(np.uint64).reshape(8, 8).astype(np.int64)
 for r in range(world):
     dist.barrier()

@@ -533,8 +533,11 @@ inline void tmad_geometry(CgArgs& a, int G, int force_tile_rows = 0, int force_s
   int hb = force_tile_rows > 0 ? force_tile_rows : 16;
   if (force_tile_rows <= 0) {
     while ((long long)a.nchunks * ((nyl + hb - 1) / hb) > CG_MAX_TILES / 2) hb *= 2;
-    // short slabs (strong scaling): keep >= ~6 tiles per CTA so the dynamic schedule can balance
-    while (hb > 4 && (long long)a.nchunks * ((nyl + hb - 1) / hb) < 6LL * G) hb /= 2;
+    // keep >= ~8 tiles per CTA so that the dynamic schedule can balance (4096^2: 12-row tiles, 9 per CTA; short
+    // slabs of a strong-scaling run: down to 4 rows).  With the lean row loops a tile's two extra row visits are
+    // cheap enough that 12-row tiles beat 16-row ones at 4096^2 (profiles/r2_tile_rows_sweep_v3.txt).
+    const int cand[] = {12, 8, 6, 4};
+    for (int q = 0; q < 4 && hb <= 16 && (long long)a.nchunks * ((nyl + hb - 1) / hb) < 8LL * G; ++q) hb = cand[q];
   }
   int hs = force_small_rows >= 0 ? force_small_rows : (hb >= 8 ? hb / 4 : 0);
   // small end bands are OFF by default: measured at 4096^2 they cost more (two extra row visits per tile) than the
@@ -561,19 +564,130 @@ __device__ __forceinline__ TmaTile tmad_tile(const CgArgs& a, int t) {
   return w;
 }
 
-// Producer side of one phase.  PHASE_B selects the stage layout / tile order.
+// Producer side.  PHASE_B selects the stage layout / tile order.
+//
+// Every CTA's FIRST tile of a phase is static (tile b in phase A, ntiles-1-b in phase B for CTA b; the ticket
+// counter hands out the rest), so it is known before the phase starts -- and the operands of its first visits that
+// the CURRENT phase does not write can be fetched BEFORE the barrier that separates the phases:
+//   next phase B: x and r of the centre rows (phase A writes neither);   not p (phase A writes it)
+//   next phase A: p_old = this iteration's new p (phase B only reads it); not r (phase B writes it)
+// The producer reserves up to TM_STAGES stages for those visits (arrive.expect_tx with the visit's FULL byte count),
+// issues the safe copies, and after the barrier only adds the missing ones -- which were written moments ago and
+// come from L2.  While the CTAs sit in the barrier (1.5-2 us on one GPU, 4-6 us across GPUs) the memory system keeps
+// streaming ~100 KB per SM that the sweep needs anyway, and the compute warps start the phase on a full ring
+// instead of waiting for a ticket and a DRAM round trip.
+struct Prefetch {
+  int tile;      // first tile of the coming phase whose leading visits are reserved (-1: nothing pending)
+  int npref;     // number of reserved visits (the first npref row-sequence numbers of the coming phase)
+  bool phase_b;  // the coming phase is a phase B
+};
+
+constexpr int TM_ISSUE_ALL = 0, TM_ISSUE_SAFE = 1, TM_ISSUE_REST = 2;
+
+// One row visit of tile w.  MODE ALL: expect_tx + every copy; SAFE: expect_tx for the full visit, only the copies the
+// running phase does not write; REST: the copies SAFE left out (the stage is already reserved).
+template <bool PHASE_B, int MODE>
+__device__ __forceinline__ void tmad_issue_visit(const CgArgs& a, const Ring& rg, const TmaTile& w, int t, int st,
+                                                 const double* f0, const double* f1, const double* f2, bool first,
+                                                 uint64_t pol, uint64_t keep) {
+  const Slab& s = a.s;
+  constexpr int DIR = PHASE_B ? -1 : +1;
+  const int jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
+  const uint32_t hbytes = (uint32_t)(w.ce - w.cs) * 8u;
+  const uint32_t cbytes = (uint32_t)TM_CW * 8u;
+  const int soff = w.cs - (w.i0 - TM_HALO);
+  const int jl = jl0 + DIR * t;
+  const int jg = s.row0 + jl;
+  const bool exists = jg >= 0 && jg < s.nyg;
+  double* dst = rg.stage(st);
+  if (!PHASE_B) {                                     // {r (written by phase B), p_old (stable)} of the visited row, haloed
+    if (MODE != TM_ISSUE_REST) mbar_expect_tx(rg.full + st, exists ? (first ? hbytes : 2u * hbytes) : 0u);
+    if (exists) {
+      if (MODE != TM_ISSUE_SAFE) bulk_g2s_hint(dst + soff, f0 + cell(s, jl, w.cs), hbytes, rg.full + st, keep);
+      if (MODE != TM_ISSUE_REST && !first)
+        bulk_g2s_hint(dst + TM_ROW + soff, f1 + cell(s, jl, w.cs), hbytes, rg.full + st, pol);
+    }
+  } else {                                            // p of the visited row (haloed; written by phase A) + x, r of the centre row (stable)
+    const bool centre = t >= 2;
+    if (MODE != TM_ISSUE_REST) mbar_expect_tx(rg.full + st, (exists ? hbytes : 0u) + (centre ? 2u * cbytes : 0u));
+    if (MODE != TM_ISSUE_SAFE && exists) bulk_g2s_hint(dst + soff, f0 + cell(s, jl, w.cs), hbytes, rg.full + st, keep);
+    if (MODE != TM_ISSUE_REST && centre) {
+      bulk_g2s_hint(dst + TM_ROW, f1 + cell(s, jl - DIR, w.i0), cbytes, rg.full + st, pol);
+      bulk_g2s_hint(dst + TM_ROW + TM_CW, f2 + cell(s, jl - DIR, w.i0), cbytes, rg.full + st, keep);
+    }
+  }
+}
+
+__device__ __forceinline__ int tmad_first_tile(const CgArgs& a, bool phase_b) {
+  const int b = (int)blockIdx.x;
+  if (b >= a.ntiles) return -1;
+  return phase_b ? a.ntiles - 1 - b : b;
+}
+// tickets of one phase: the tiles beyond the static first ones + one failing draw per CTA
+__host__ __device__ __forceinline__ unsigned long long tmad_tickets_per_phase(int ntiles, int G) {
+  return (unsigned long long)(ntiles > G ? ntiles - G : 0) + (unsigned long long)G;
+}
+
+// Before the barrier that precedes a phase: reserve the leading visits of this CTA's first tile of that phase and
+// start the copies the running phase cannot invalidate.  n is the row sequence number the phase will start with.
+template <bool PHASE_B>
+__device__ __forceinline__ bool tmad_prefetch(const CgArgs& a, const Ring& rg, DynShared* ds, const double* f0,
+                                              const double* f1, const double* f2, uint64_t pol, unsigned long long n,
+                                              unsigned long long seq, Prefetch& pf) {
+  pf.tile = -1;
+  pf.npref = 0;
+  if (a.y.opt & 32) return true;                      // experiment switch: no prefetch across the barrier
+  const int tile = tmad_first_tile(a, PHASE_B);
+  if (tile < 0) return true;
+  const uint64_t keep = (a.y.opt & 8) ? policy_evict_last() : policy_evict_normal();
+  const TmaTile w = tmad_tile(a, tile);
+  const int nrows = w.j1 - w.j0 + 2;
+  const int np = nrows < TM_STAGES ? nrows : TM_STAGES;
+  for (int t = 0; t < np; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.empty + st, (uint32_t)(((n / TM_STAGES) & 1ULL) ^ 1ULL))) return false;
+    if (t == 0) ds->tile[(int)(seq % TD_SLOTS)] = tile;
+    tmad_issue_visit<PHASE_B, TM_ISSUE_SAFE>(a, rg, w, t, st, f0, f1, f2, false, pol, keep);
+  }
+  pf.tile = tile;
+  pf.npref = np;
+  pf.phase_b = PHASE_B;
+  return true;
+}
+
+// A phase that will not run after all (the solve stopped): complete the reserved visits and wait for the copies,
+// so that no bulk copy is in flight into this CTA's shared memory when it exits.
+template <bool PHASE_B>
+__device__ __forceinline__ void tmad_drain(const CgArgs& a, const Ring& rg, const double* f0, const double* f1,
+                                           const double* f2, uint64_t pol, unsigned long long n, Prefetch& pf) {
+  if (pf.tile < 0) return;
+  const uint64_t keep = policy_evict_normal();
+  const TmaTile w = tmad_tile(a, pf.tile);
+  for (int t = 0; t < pf.npref; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    tmad_issue_visit<PHASE_B, TM_ISSUE_REST>(a, rg, w, t, st, f0, f1, f2, false, pol, keep);
+    (void)mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL));
+  }
+  pf.tile = -1;
+}
+
 template <bool PHASE_B>
 __device__ __forceinline__ bool tmad_produce(const CgArgs& a, const Ring& rg, DynShared* ds, unsigned long long tbase,
                                              const double* f0, const double* f1, const double* f2, bool first,
-                                             uint64_t pol, unsigned long long& n, unsigned long long& seq) {
-  const Slab& s = a.s;
-  constexpr int DIR = PHASE_B ? -1 : +1;
+                                             uint64_t pol, unsigned long long& n, unsigned long long& seq,
+                                             Prefetch& pf) {
   // r and p are re-read by the next (reversed) sweep.  Marking them evict_last (opt bit 8) was measured:
   // DRAM reads 173.0 GB vs 168.7 GB with the default priority, no gain -- default stays evict_normal.
   const uint64_t keep = (a.y.opt & 8) ? policy_evict_last() : policy_evict_normal();
+  const int G = (int)gridDim.x;
+  int tile = tmad_first_tile(a, PHASE_B);             // static first tile, then tickets
+  int npref = (pf.tile == tile) ? pf.npref : 0;       // its leading visits may already be reserved (tmad_prefetch)
+  pf.tile = -1;
   for (;;) {
-    const unsigned long long tk = atomicAdd(a.y.tickets, 1ULL) - tbase;
-    const int tile = tk < (unsigned long long)a.ntiles ? (PHASE_B ? a.ntiles - 1 - (int)tk : (int)tk) : -1;
+    if (tile < 0) {
+      const unsigned long long tk = (unsigned long long)G + atomicAdd(a.y.tickets, 1ULL) - tbase;
+      tile = tk < (unsigned long long)a.ntiles ? (PHASE_B ? a.ntiles - 1 - (int)tk : (int)tk) : -1;
+    }
     const int slot = (int)(seq % TD_SLOTS);
     if (tile < 0) {                                   // end marker: an empty visit carrying tile = -1
       const int st = (int)(n % TM_STAGES);
@@ -585,38 +699,20 @@ __device__ __forceinline__ bool tmad_produce(const CgArgs& a, const Ring& rg, Dy
       return true;
     }
     const TmaTile w = tmad_tile(a, tile);
-    const int TH = w.j1 - w.j0, nrows = TH + 2;
-    const int jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
-    const uint32_t hbytes = (uint32_t)(w.ce - w.cs) * 8u;
-    const uint32_t cbytes = (uint32_t)TM_CW * 8u;
-    const int soff = w.cs - (w.i0 - TM_HALO);
+    const int nrows = w.j1 - w.j0 + 2;
     for (int t = 0; t < nrows; ++t, ++n) {
       const int st = (int)(n % TM_STAGES);
+      if (t < npref) {                                // reserved before the barrier: add what was left out
+        tmad_issue_visit<PHASE_B, TM_ISSUE_REST>(a, rg, w, t, st, f0, f1, f2, first, pol, keep);
+        continue;
+      }
       if (!mbar_wait(rg.empty + st, (uint32_t)(((n / TM_STAGES) & 1ULL) ^ 1ULL))) return false;
       if (t == 0) ds->tile[slot] = tile;             // published by the release of the arrive below
-      const int jl = jl0 + DIR * t;
-      const int jg = s.row0 + jl;
-      const bool exists = jg >= 0 && jg < s.nyg;
-      double* dst = rg.stage(st);
-      if (!PHASE_B) {                                 // {r, p_old} of the visited row, with halo columns
-        if (exists) {
-          mbar_expect_tx(rg.full + st, first ? hbytes : 2u * hbytes);
-          bulk_g2s_hint(dst + soff, f0 + cell(s, jl, w.cs), hbytes, rg.full + st, keep);
-          if (!first) bulk_g2s_hint(dst + TM_ROW + soff, f1 + cell(s, jl, w.cs), hbytes, rg.full + st, pol);
-        } else {
-          mbar_expect_tx(rg.full + st, 0u);
-        }
-      } else {                                        // p of the visited row (haloed) + x, r of the centre row
-        const bool centre = t >= 2;
-        mbar_expect_tx(rg.full + st, (exists ? hbytes : 0u) + (centre ? 2u * cbytes : 0u));
-        if (exists) bulk_g2s_hint(dst + soff, f0 + cell(s, jl, w.cs), hbytes, rg.full + st, keep);
-        if (centre) {
-          bulk_g2s_hint(dst + TM_ROW, f1 + cell(s, jl - DIR, w.i0), cbytes, rg.full + st, pol);
-          bulk_g2s_hint(dst + TM_ROW + TM_CW, f2 + cell(s, jl - DIR, w.i0), cbytes, rg.full + st, keep);
-        }
-      }
+      tmad_issue_visit<PHASE_B, TM_ISSUE_ALL>(a, rg, w, t, st, f0, f1, f2, first, pol, keep);
     }
     ++seq;
+    npref = 0;
+    tile = -1;
   }
 }
 
@@ -1161,7 +1257,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
   const uint64_t pol = policy_evict_first();
   unsigned long long n = 0, seq = 0;                  // row / tile sequence numbers of this CTA
   const unsigned long long tbase0 = *((volatile unsigned long long*)a.y.ticket_base);
-  const unsigned long long per_phase = (unsigned long long)a.ntiles + (unsigned long long)G;
+  const unsigned long long per_phase = tmad_tickets_per_phase(a.ntiles, G);
+  Prefetch pf;                                        // producer lane only
+  pf.tile = -1; pf.npref = 0; pf.phase_b = false;
   unsigned long long phase = 0;
   unsigned long long e = *((volatile unsigned long long*)a.y.epoch);   // cross-GPU barrier epochs (MULTI)
   const unsigned long long e0 = e;
@@ -1198,8 +1296,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
         const unsigned long long tbase = tbase0 + phase * per_phase;
         if (producer) {
           if (lane == 0) {
-            good = tmad_produce<false>(a, rg, &ds, tbase, a.r, pcur, nullptr, first, pol, n, seq);
+            good = tmad_produce<false>(a, rg, &ds, tbase, a.r, pcur, nullptr, first, pol, n, seq, pf);
             ds.n_end = n; ds.seq_end = seq;
+            // phase B follows unconditionally: fetch x and r of its first visits while the barrier runs
+            if (good) good = tmad_prefetch<true>(a, rg, &ds, pnext, a.x, a.r, pol, n, seq, pf);
           }
         } else {
           // wall strips exist only in the first / last column chunk: the generic WALL instantiation is
@@ -1236,8 +1336,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
         const unsigned long long tbase = tbase0 + phase * per_phase;
         if (producer) {
           if (lane == 0) {
-            good = tmad_produce<true>(a, rg, &ds, tbase, pnext, a.x, a.r, false, pol, n, seq);
+            good = tmad_produce<true>(a, rg, &ds, tbase, pnext, a.x, a.r, false, pol, n, seq, pf);
             ds.n_end = n; ds.seq_end = seq;
+            // phase A of the next iteration (if the solve goes on): its p_old is this iteration's new p
+            if (good && it + 1 < a.maxiter) good = tmad_prefetch<false>(a, rg, &ds, a.r, pnext, nullptr, pol, n, seq, pf);
           }
         } else {
           if (warp == 0 || warp == TM_WARPS - 1)
@@ -1276,6 +1378,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
       double* tmp = pcur; pcur = pnext; pnext = tmp;
       ++iters;
     }
+  }
+  // the solve stopped with a phase A reserved (converged, or an error): complete and retire those copies.  After the
+  // swap at the end of the iteration pcur is the buffer the prefetch was reading from.
+  // (An error exit in the middle of an iteration can leave a phase B reserved instead: p is pnext then.)
+  if (producer && lane == 0) {
+    if (pf.phase_b) tmad_drain<true>(a, rg, pnext, a.x, a.r, pol, n, pf);
+    else tmad_drain<false>(a, rg, a.r, pcur, nullptr, pol, n, pf);
   }
   if (blockIdx.x == 0 && tid == 0) {
     a.scal[S_INFO] = ok ? (double)info : -2.0;
