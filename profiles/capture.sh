@@ -31,12 +31,11 @@ for what in "$@"; do
       ncu -i gpurun_out/cg_small_full.ncu-rep --page raw --csv | grep -E \
           'dram__bytes_(read|write)\.sum|lts__t_bytes|gpu__time_duration|launch__registers_per_thread|smsp__issue_active|smsp__average_warp.*stall|l1tex__data_bank_conflicts' \
           > gpurun_out/cg_small_full_summary.txt ;;
-    sanitize)     # memcheck + racecheck + synccheck of every CG kernel variant on small grids
-      for tool in memcheck racecheck synccheck; do
-        timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 \
-          python -m pytest tests/test_gpu_parity.py -x -q -k "pcg_matches or forced_cg_kernel or strip_and_chunk" \
+    sanitize)     # memcheck + racecheck + synccheck + initcheck of every CG kernel variant on small grids
+      for tool in memcheck racecheck synccheck initcheck; do
+        timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python tests/sanitize_cases.py \
           > gpurun_out/sanitizer_$tool.log 2>&1
-        echo "$tool rc=$?" | tee -a gpurun_out/sanitizer_summary.txt
+        echo "$tool rc=$? $(grep -c SANITIZE gpurun_out/sanitizer_$tool.log) lines, $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_$tool.log | tail -1)" | tee -a gpurun_out/sanitizer_summary.txt
       done ;;
     scaling)      # configs 4 and 5 at every GPU count the box has (`gpurun --gpus 8 -- 'bash profiles/capture.sh scaling'`)
       ngpu=$(nvidia-smi -L | wc -l)

@@ -6,8 +6,10 @@ flags: every CTA stores one self-validating 32-byte packet ``{epoch, partials}``
 (slots double-buffered by epoch parity), warp 0 polls every slot until it carries the current
 epoch, and -- on the second exchange of an iteration -- the other warps publish the CTA's two
 boundary rows of ``r`` as packets tagged with the same epoch and fetch the neighbours' rows the
-same way.  A packet is written with ONE 256-bit store, so a reader sees it complete or not at
-all; what has to be proved is that nobody can ever miss an epoch:
+same way.  A packet consists of self-validating LL words (every 64-bit word carries the epoch tag,
+pf_common.cuh), so a reader accepts it complete or not at all -- proved against a torn-packet
+adversary at the end of this file, where the round-1 design (one 256-bit store, epoch in word 0)
+is shown to fail; what has to be proved here is that nobody can ever miss an epoch:
 
   SAFETY    whenever a CTA still waits for epoch ``e`` at some location, that location does
             not already hold a LATER epoch (the wait could never end: epochs only grow);
@@ -276,3 +278,105 @@ def test_checker_finds_the_bug_in_a_single_buffered_mailbox():
     one of barrier e that a slow GPU's last CTA has not read yet."""
     _states, violation, _deadlock = explore_multi(R=2, G=1, T=3, single_buffered_mailbox=True)
     assert violation is not None and violation[2][0] == "mbox"
+
+
+# =====================================================================================================
+# Packet INTEGRITY under a torn-packet adversary (round 2).
+#
+# The models above treat a packet as one location: "a reader sees it complete or not at all".  Round 1 obtained that
+# from writing {epoch, v0, v1, v2} with ONE 256-bit store -- an implementation property (STG.256 / LDG.256), not a
+# guarantee: the PTX memory model makes only scalar accesses of up to 64 bits single-copy atomic and treats a vector
+# access as independent scalar accesses in unspecified order.  Here every 64-bit word of a packet becomes visible on
+# its own, arbitrarily late (per word in store order), and the reader's words are read at different times, in any
+# order.  Two designs:
+#   header  : word 0 = epoch, words 1.. = payload; the reader accepts when word 0 carries the awaited epoch (round 1)
+#   ll      : EVERY word = {32-bit tag, 32 payload bits}; the reader accepts when every word carries the tag
+#             (pf_common.cuh: ll_encode / ll_ok, the encoding of NCCL's LL protocol)
+# Property: a packet accepted for epoch e consists of the words stored for epoch e.  The writer reuses the slot for
+# epoch e+1 only after the reader accepted e (what parity double-buffering plus the data dependency between
+# consecutive exchanges provide in the kernels; proved on the packet level by the models above).
+# =====================================================================================================
+def explore_torn(words=3, epochs=3, design="ll", max_states=2_000_000):
+    """Returns (states, integrity violation or None, deadlock or None)."""
+    W = words
+    # state: (writer epoch being stored, mask of its words still to be issued, accepted epochs so far,
+    #         visible epoch per word, in-flight epochs per word (oldest first), reader's words read in this attempt)
+    start = (1, (1 << W) - 1, 0, tuple(0 for _ in range(W)), tuple(() for _ in range(W)), tuple(-1 for _ in range(W)))
+    seen = {start}
+    todo = deque([start])
+    while todo:
+        st = todo.popleft()
+        wep, wmask, accepted, visible, inflight, got = st
+        succ = []
+        if accepted >= epochs:
+            continue
+        # writer: stores of the words of one packet in any order; the next packet only after the reader took this one
+        if wep <= epochs and wep == accepted + 1:
+            for k in range(W):
+                if wmask >> k & 1:
+                    inf = list(inflight)
+                    inf[k] = inflight[k] + (wep,)
+                    nm = wmask & ~(1 << k)
+                    succ.append((wep, nm, accepted, visible, tuple(inf), got))
+        # a word in flight becomes visible (per word in store order)
+        for k in range(W):
+            if inflight[k]:
+                vis, inf = list(visible), list(inflight)
+                vis[k], inf[k] = inflight[k][0], inflight[k][1:]
+                succ.append((wep, wmask, accepted, tuple(vis), tuple(inf), got))
+        # reader: one poll attempt = one read of every word, any order, each at its own time
+        want = accepted + 1
+        unread = [k for k in range(W) if got[k] < 0]
+        if unread:
+            for k in unread:
+                g = list(got)
+                g[k] = visible[k]
+                succ.append((wep, wmask, accepted, visible, inflight, tuple(g)))
+        else:
+            ok = got[0] == want if design == "header" else all(v == want for v in got)
+            if ok:
+                if any(v != want for v in got):           # INTEGRITY: accepted words of another epoch
+                    return len(seen), (want, got), None
+                nwep, nmask = (wep + 1, (1 << W) - 1) if wmask == 0 and wep == want else (wep, wmask)
+                succ.append((nwep, nmask, want, visible, inflight, tuple(-1 for _ in range(W))))
+            else:
+                succ.append((wep, wmask, accepted, visible, inflight, tuple(-1 for _ in range(W))))      # poll again
+        if not succ:
+            return len(seen), None, st
+        for s2 in succ:
+            if s2 not in seen:
+                seen.add(s2)
+                todo.append(s2)
+                if len(seen) > max_states:
+                    raise RuntimeError("state space larger than expected")
+    return len(seen), None, None
+
+
+@pytest.mark.parametrize("words", [2, 4])
+def test_torn_packets_break_the_round_one_header_tag_design(words):
+    """With words that become visible independently, `epoch in word 0` can be seen next to payload words of an
+    earlier packet: the 256-bit-store design is only as good as the hardware's (unguaranteed) 32-byte atomicity."""
+    _states, violation, _deadlock = explore_torn(words=words, epochs=2, design="header")
+    assert violation is not None
+    want, got = violation
+    assert got[0] == want and any(v != want for v in got[1:])
+
+
+@pytest.mark.parametrize("words,epochs", [(2, 3), (4, 3), (6, 2)])
+def test_ll_words_survive_the_torn_packet_adversary(words, epochs):
+    """Every word self-validates: whatever the visibility order of the words and of the reader's loads, an accepted
+    packet is the packet of the awaited epoch, and the reader always gets there (6 words = the three-double packets
+    of the cross-GPU exchanges, 4 = the reduction / row packets of k_cg_small, 2 = the tile partials of k_cg_tmad)."""
+    states, violation, deadlock = explore_torn(words=words, epochs=epochs, design="ll")
+    assert violation is None, f"accepted a mixed packet: {violation}"
+    assert deadlock is None, f"reader can be stuck: {deadlock}"
+    assert states > 100
+
+
+def test_ll_tag_is_never_zero_and_distinguishes_neighbouring_epochs():
+    """Mirror of pf_common.cuh ll_tag(): zero-initialised memory never validates, and the epochs that share a slot
+    (e and e + 2 with parity double-buffering; e and e + 1 without) carry different tags, also across the wrap."""
+    tag = lambda e: (e % 0xffffffff) + 1                  # noqa: E731
+    for e in (0, 1, 2, 0xfffffffd, 0xfffffffe, 0xffffffff, 0x100000000, 0x1fffffffd, 2 ** 40 + 7):
+        assert 1 <= tag(e) <= 0xffffffff
+        assert tag(e) != tag(e + 1) and tag(e) != tag(e + 2)
