@@ -685,7 +685,7 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
 #pragma unroll
     for (int k = 0; k < NV; ++k) a.part[k * CG_MAX_GRID + blockIdx.x] = vals[k];
     // cumulative release: publishes the CTA's field / partial / peer-halo stores
-    if (R > 1) __threadfence_system(); else __threadfence();
+    if (R > 1) fence_acq_rel_sys(); else fence_acq_rel_gpu();
     if (tr) {
       const unsigned long long t = gtime();
       atomicMin(tr + 0, t);
@@ -701,7 +701,7 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
   }
   __syncthreads();
   if (s_last) {
-    if (tid == 0) __threadfence();   // acquire the other CTAs' partials (read below with ld.cg)
+    if (tid == 0) fence_acq_rel_gpu();   // acquire the other CTAs' partials (read below with ld.cg)
     __syncthreads();
     double loc[3] = {0.0, 0.0, 0.0};
     for (int q = tid; q < G; q += CG_THREADS) {
@@ -713,7 +713,7 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
     if (R > 1) {
       const size_t slot_of_me = (size_t)(par * CG_MAX_RANKS + y.rank) * LL_SLOT_BYTES;
       if (tid == 0) {
-        __threadfence_system();      // the halo rows pushed by the other CTAs of this GPU go out before the packet
+        fence_acq_rel_sys();         // the halo rows pushed by the other CTAs of this GPU go out before the packet
         for (int q = 0; q < R; ++q) st_ll_triple<LL_SYS>((char*)y.peer_mbox[q] + slot_of_me, e, loc[0], loc[1], loc[2]);
         if (tr) tr[3] = gtime();
       }
@@ -742,7 +742,7 @@ __device__ __forceinline__ bool grid_exchange(const CgArgs& a, unsigned long lon
     }
     if (tid == 0) {
       if (tr) tr[4] = gtime();
-      __threadfence();               // (R > 1) peers' halo rows, made visible to this thread, go before the release
+      fence_acq_rel_gpu();           // (R > 1) peers' halo rows, made visible to this thread, go before the release
       st_ll_triple<LL_GPU>(y.gsum, e, loc[0], loc[1], loc[2]);
       if (tr) tr[5] = gtime();
     }

@@ -1143,36 +1143,41 @@ __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, 
   }
 }
 
-// Phase end for several GPUs.  Every CTA arrives (gpu-scope release: its stores, peer halo rows
-// included, become visible to the CTA that arrives last); the last CTA folds the per-TILE partials,
-// issues ONE system fence (cumulative: it also publishes the halo rows pushed by the other CTAs) and
-// writes one LL packet (three doubles as six self-validating words) into the mailbox of EVERY rank, its own included.
-// All CTAs of all ranks then poll their local mailbox directly -- no separate local release hop --
-// and add the packets in rank order, so every CTA of every GPU holds bit-identical sums.
-template <int NV>
-__device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long long e, double (&out)[NV], double* sm,
+// Phase end: barrier + all-reduce in one, on one GPU (SYS = false) or across the GPUs of a box (SYS = true).
+// Every CTA arrives (release fence + atomic on the GPU's counter: its stores, peer halo rows included, happen
+// before the CTA that arrives last); the last CTA folds the group partials (<= CG_MAX_GROUPS values) while the
+// thread that will publish runs the one fence that makes everything visible at the scope of the exchange
+// (cumulative: it also covers the halo rows pushed to the peers by the other CTAs), then writes one LL packet
+// (three doubles as six self-validating words) into the mailbox of EVERY rank, its own included.  All CTAs of all
+// ranks poll their local mailbox directly -- no separate local release hop -- and add the packets in rank order, so
+// every CTA of every GPU holds bit-identical sums.  On one GPU this replaces cooperative-groups grid.sync() followed
+// by a fold in every CTA: one atomic, one 1-2 sector fold, one packet, instead of two sequentially consistent fences
+// per CTA, a polled barrier word and 148 folds.
+template <int NV, bool SYS>
+__device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long long e, double (&out)[NV],
                                               unsigned long long e0 = 0) {
+  constexpr int SCOPE = SYS ? LL_SYS : LL_GPU;
   unsigned long long* tr = trace_slot(a, e0, e);
   __shared__ int s_last;
   __shared__ double s_out[4];
   __shared__ double s_peer[CG_MAX_RANKS][3];
   const CgSync& y = a.y;
-  const int G = gridDim.x, tid = threadIdx.x, R = y.nranks;
+  const int G = gridDim.x, tid = threadIdx.x, R = SYS ? y.nranks : 1;
   const int par = (int)(e & 1ULL);
-  __syncthreads();                   // every thread's stores (fields, tile partials, peer halos) before thread 0's fence
+  __syncthreads();                   // every thread's stores (fields, group partials, peer halos) before thread 0's fence
   if (tid == 0) {
-    __threadfence();
+    fence_acq_rel_gpu();             // release
     if (tr) { const unsigned long long t = gtime(); atomicMin(tr + 0, t); atomicMax(tr + 1, t); }
     s_last = (atomicAdd(y.arrive, 1ULL) == e * (unsigned long long)G - 1ULL) ? 1 : 0;
+    if (s_last) fence_acq_rel_gpu(); // acquire: every CTA's group partials and peer halo stores happen-before what follows
   }
   __syncthreads();
   if (s_last) {
-    if (tid == 0) __threadfence();   // acquire: every CTA's group partials and peer halo stores happen-before what follows
-    __syncthreads();
-    // ONE system fence (cumulative: it also publishes the halo rows pushed by the other CTAs), issued by the
-    // thread that will write the packets, WHILE warp 0 folds the group partials: the two ~2 us steps overlap
+    // the fence of the publishing thread runs WHILE warp 0 folds the group partials
     const bool publisher = (tid == TM_WARPS * 32);
-    if (publisher) __threadfence_system();
+    if (publisher) {
+      if (SYS) fence_acq_rel_sys(); else fence_acq_rel_gpu();
+    }
     if (tid < 32) {
       const int ng = (a.ntiles + CG_TILE_GROUP - 1) / CG_TILE_GROUP;
 #pragma unroll
@@ -1188,8 +1193,12 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
     }
     __syncthreads();
     if (publisher) {
-      const size_t slot = (size_t)(par * CG_MAX_RANKS + y.rank) * LL_SLOT_BYTES;
-      for (int q = 0; q < R; ++q) st_ll_triple<LL_SYS>((char*)y.peer_mbox[q] + slot, e, s_out[0], s_out[1], s_out[2]);
+      const size_t slot = (size_t)(par * CG_MAX_RANKS + (SYS ? y.rank : 0)) * LL_SLOT_BYTES;
+      if (SYS) {
+        for (int q = 0; q < R; ++q) st_ll_triple<LL_SYS>((char*)y.peer_mbox[q] + slot, e, s_out[0], s_out[1], s_out[2]);
+      } else {
+        st_ll_triple<LL_GPU>((char*)y.mbox + slot, e, s_out[0], s_out[1], s_out[2]);
+      }
       if (tr) tr[3] = gtime();
     }
     __syncthreads();                 // s_out is reused for the totals below
@@ -1198,16 +1207,17 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
     const long long t0 = clock64();
     double k[3];
     const char* src = (const char*)y.mbox + (size_t)(par * CG_MAX_RANKS + tid) * LL_SLOT_BYTES;
-    while (!ld_ll_triple<LL_SYS>(src, e, k)) {
+    while (!ld_ll_triple<SCOPE>(src, e, k)) {
       if (clock64() - t0 > CG_SPIN_LIMIT) {
         atomicExch(y.err, 1ULL);
         break;
       }
     }
     if (tr && blockIdx.x == 0) tr[4 + (tid & 1)] = gtime();      // when block 0 saw rank tid's packet
-    // acquire (LDG.STRONG.SYS + L1 invalidate; a full fence.sys = MEMBAR.ALL.SYS cost ~4 us here): the
-    // field data of this GPU's other CTAs and the peers' halo rows are visible to what follows
-    (void)ld_acquire_sys((const unsigned long long*)src);
+    // acquire (an acquire load: LDG.STRONG + L1 invalidate; a full fence on the wait side cost ~4 us across GPUs):
+    // the field data of this GPU's other CTAs and the peers' halo rows are visible to what follows
+    if (SYS) (void)ld_acquire_sys((const unsigned long long*)src);
+    else (void)ld_acquire_gpu((const unsigned long long*)src);
     s_peer[tid][0] = k[0]; s_peer[tid][1] = k[1]; s_peer[tid][2] = k[2];
   }
   __syncthreads();
@@ -1228,8 +1238,6 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
 
 template <bool UNIT, bool MULTI>
 __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
-  namespace cgr = cooperative_groups;
-  cgr::grid_group grid = cgr::this_grid();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double sm[3 * 32];
   __shared__ DynShared ds;
@@ -1317,16 +1325,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
       __syncthreads();
       n = ds.n_end; seq = ds.seq_end;
       double pq;
-      if (MULTI) {
+      {
         double o1[1];
-        ok = tile_exchange<1>(a, ++e, o1, sm, e0);
+        ok = tile_exchange<1, MULTI>(a, ++e, o1, e0);
         if (!ok) break;
-        pq = o1[0];
-      } else {
-        __threadfence();
-        grid.sync();
-        double o1[1];
-        tmad_fold_groups<1>(a, o1, sm);
         pq = o1[0];
       }
       const double alpha = rho / pq;
@@ -1353,25 +1355,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
       __syncthreads();
       n = ds.n_end; seq = ds.seq_end;
       double rz;
-      if (MULTI) {
+      {
         double o2[2];
-        ok = tile_exchange<2>(a, ++e, o2, sm, e0);
+        ok = tile_exchange<2, MULTI>(a, ++e, o2, e0);
         if (!ok) break;
         rr = o2[0];
         rz = o2[1];
-      } else {
-        __threadfence();
-        grid.sync();
-        {
-          double f[2];
-          tmad_fold_groups<2>(a, f, sm);
-          rr = f[0];
-          rz = f[1];
-        }
-        if (ld_cg((const double*)a.y.err) != 0.0) {   // a pipeline wait timed out somewhere (non-zero bit pattern)
-          ok = false;
-          break;
-        }
       }
       rho_prev = rho;
       rho = rz;
@@ -1391,7 +1380,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
     a.scal[S_ITERS] = (double)iters;
     a.scal[S_RR] = rr;
     *a.y.ticket_base = tbase0 + phase * per_phase;
-    if (MULTI) *a.y.epoch = e;
+    *a.y.epoch = e;
   }
 }
 

@@ -246,6 +246,17 @@ __device__ __forceinline__ void ld_ll4(const void* p, LLVal& a, LLVal& b) {
 }
 #endif  // PF_HOST_EMULATION
 
+// Acquire / release fences.  __threadfence() and __threadfence_system() compile to SEQUENTIALLY CONSISTENT fences
+// (MEMBAR.SC.GPU / MEMBAR.SC.SYS); every pattern in this library is a release (fence, then relaxed store / atomic)
+// or an acquire (relaxed load / atomic, then fence), for which fence.acq_rel is what the PTX model asks for.
+#ifdef PF_HOST_EMULATION
+__device__ __forceinline__ void fence_acq_rel_gpu() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+__device__ __forceinline__ void fence_acq_rel_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+#else
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+#endif
+
 // A packet of three doubles = 6 LL words in a 64-byte slot (reduction partials across GPUs / CTAs).
 constexpr int LL_SLOT_BYTES = 64;
 template <int SCOPE>

@@ -76,7 +76,7 @@ def small(ny,nx,rows,unit,maxiter=3):
     if not err<1e-10: bad.append(("small",ny,nx,rows,err)); print("BAD small",ny,nx,rows,err,flush=True)
 def tmad(ny,nx,tr,unit,maxiter=3):
     dx,dy=(1.0,1.0) if unit else (0.5,0.25); invd=1.0/(2.0/dx**2+2.0/dy**2); b=mk(ny,nx)
-    dev=T.Dev(lib,ny,nx); S=T.Scalars(lib); sync=np.zeros(16,dtype=np.uint64)
+    dev=T.Dev(lib,ny,nx); S=T.Scalars(lib); sync=np.zeros(256,dtype=np.uint64)
     x=T._tmad_solve(lib,dev,S,sync,b,dx,dy,invd,1e-10,maxiter,tr)
     xo,io,to=ref(b,dx,dy,maxiter); err=np.linalg.norm(x.ravel()-xo)/np.linalg.norm(xo)
     if not err<1e-10: bad.append(("tmad",ny,nx,tr,err)); print("BAD tmad",ny,nx,tr,err,flush=True)

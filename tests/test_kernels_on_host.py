@@ -128,6 +128,7 @@ inline unsigned long long emu_tma_ld_u64(const unsigned long long* p) { return _
 inline unsigned long long emu_tma_gtime() { return (unsigned long long)clock64(); }
 }  // namespace pf
 #define ld_acquire_sys emu_tma_ld_u64
+#define ld_acquire_gpu emu_tma_ld_u64
 #define gtime emu_tma_gtime
 '''
 
@@ -917,7 +918,7 @@ def test_tma_fed_cg_kernel_vs_oracle(emu, ny, nx, tile_rows, unit, jacobi, maxit
     invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2) if jacobi else 1.0
     tol = 1e-10 if maxiter < 100 else 0.9
     dev, S = Dev(emu, ny, nx), Scalars(emu)
-    sync = np.zeros(16, dtype=np.uint64)
+    sync = np.zeros(256, dtype=np.uint64)          # 2 KiB sync block (fill_sync layout)
     A = lambda z: orc.neg_laplacian_pinned(z, nx, ny, dx, dy)        # noqa: E731
     inv = orc.jacobi_inverse_diagonal(nx, ny, dx, dy) if jacobi else None
     for _repeat in range(2):
@@ -943,7 +944,7 @@ def test_whole_projection_steps_with_the_tma_fed_kernel_vs_oracle(emu):
                           lin_maxiter=6, advection_scheme="quick", disable_advection=False, diagnostics=False)
     ost = orc.allocate_state(nx, ny)
     dev, S = Dev(emu, ny, nx), Scalars(emu)
-    sync = np.zeros(16, dtype=np.uint64)
+    sync = np.zeros(256, dtype=np.uint64)          # 2 KiB sync block (fill_sync layout)
     u, v, uo, vo = dev.put(), dev.put(), dev.put(), dev.put()
     b, x, r, p0, p1 = dev.put(), dev.put(), dev.put(), dev.put(), dev.put()
     part = np.zeros(emu.emu_cg_part_doubles())
