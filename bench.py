@@ -58,6 +58,9 @@ WORKLOADS = {
     "strong8192": dict(nx=8192, ny=8192, Re=5000.0, scaling="strong", per_gpu=False),
     "weak16384": dict(nx=16384, ny=16384, Re=1000.0, scaling="weak", per_gpu=True),
     "weak16384_tight": dict(nx=16384, ny=16384, Re=1000.0, scaling="weak", per_gpu=True, lin_maxiter=10000),
+    # widths that are not a multiple of the TMA kernel's 1024-column chunk (clipped last chunk)
+    "cavity4000": dict(nx=4000, ny=4000, Re=1000.0, scaling="weak", per_gpu=True),
+    "cavity5000x3000": dict(nx=5000, ny=3000, Re=1000.0, scaling="weak", per_gpu=True),
 }
 CG_BYTES_PER_CELL_ITER = 64.0     # SURVEY.md 8d contract figure
 STEP_BYTES_PER_CELL = 200.0
@@ -282,7 +285,7 @@ def cg_kernel_name(nx, ny_local, world, sm_count=148):
     if (world == 1 and nx % 2 == 0 and nx <= 2048 and rows * (nx // 2) <= 8 * 512
             and 8 * nx * ((rows + 2) * 2 + rows) <= 200 * 1024):
         return "k_cg_small<unit> (shared-memory-resident CG; L2/latency-bound workload, HBM roofline informational)"
-    if nx % 1024 == 0 and ny_local >= 2:
+    if nx >= 1024 and ny_local >= 2:
         return "k_cg_tmad<unit> (TMA-fed persistent CG)"
     return "k_cg_persistent<unit> (register-window persistent CG)"
 
@@ -446,7 +449,7 @@ def run_gpu_arm(args, wl, rank, world):
     other = None
     if not getattr(args, 'no_extra', False) and args.workload == "cavity4096":
         other = {}
-        extra = [("cavity512", 3, 50)] if world == 1 else []
+        extra = [("cavity512", 3, 50), ("cavity4000", 2, 6), ("cavity5000x3000", 2, 6)] if world == 1 else []
         extra += [("strong8192", 2, 4), ("weak16384", 2, 2), ("weak16384_tight", 1, 1)]
         for name, w2, n2 in extra:
             wl2 = WORKLOADS[name]

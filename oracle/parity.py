@@ -149,6 +149,7 @@ def bench_cases(workload, nx, ny_local, Re, world):
             (f"1024x{36 * world} TMA kernel", make_cfg(1024, 36 * world, 1000.0), 3),
             (f"2048x{20 * world} TMA kernel, 2 chunks, upwind", make_cfg(2048, 20 * world, 1000.0, "upwind", 200), 3),
             (f"1024x{64 * world} converged (lin_maxiter 10000)", make_cfg(1024, 64 * world, 100.0, lin_maxiter=10000), 3),
+            (f"1100x{24 * world} TMA kernel, clipped last chunk", make_cfg(1100, 24 * world, 1000.0), 3),
         ]
     return cases
 

@@ -247,9 +247,10 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     const void* fn = small_kernel(unit, np);
     PF_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SM_THREADS), args, small_smem, st));
     c->launches++;
-  } else if (c->opt_kernel == 3 && (!c->comm || c->peers) && c->tma_grid > 0 && s.nx % TM_CW == 0 && s.nyl >= 2) {
-    // TMA-fed sweeps, dynamically scheduled 1024-column tiles (16 rows, more for huge slabs), one CTA per SM;
-    // with several ranks: halo rows + dot-product partials over NVLink peer memory inside the same kernel
+  } else if (c->opt_kernel == 3 && (!c->comm || c->peers) && c->tma_grid > 0 && s.nx >= TM_CW && s.nyl >= 2) {
+    // TMA-fed sweeps, dynamically scheduled 1024-column tiles (the last column chunk narrower when nx is not a
+    // multiple of 1024; any nx >= 1024, odd ones too), one CTA per SM; with several ranks: halo rows + dot-product
+    // partials over NVLink peer memory inside the same kernel
     // tile geometry: 16-row tiles (taller on huge slabs, shorter on short ones) with a few bands of quarter-height
     // tiles at both ends of the slab, so that both sweeps end on short tiles (pf_cg_tma.cuh)
     tmad_geometry(a, c->tma_grid, c->opt_tile_rows, c->opt_small_rows, c->opt_nb_small);

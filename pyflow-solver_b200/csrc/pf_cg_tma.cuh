@@ -529,7 +529,7 @@ __host__ __device__ __forceinline__ void tmad_band_rows(const CgArgs& a, int bd,
 // tile_rows_min > 0 forces the big-tile height (tests); small tiles only when the slab is tall enough.
 inline void tmad_geometry(CgArgs& a, int G, int force_tile_rows = 0, int force_small_rows = -1, int force_nb_small = -1) {
   const int nyl = a.s.nyl;
-  a.nchunks = a.s.nx / TM_CW;
+  a.nchunks = (a.s.nx + TM_CW - 1) / TM_CW;        // the last chunk may be narrower (any nx >= TM_CW)
   int hb = force_tile_rows > 0 ? force_tile_rows : 16;
   if (force_tile_rows <= 0) {
     while ((long long)a.nchunks * ((nyl + hb - 1) / hb) > CG_MAX_TILES / 2) hb *= 2;
@@ -561,7 +561,8 @@ __device__ __forceinline__ TmaTile tmad_tile(const CgArgs& a, int t) {
   tmad_band_rows(a, bd, w.j0, w.j1);
   w.cs = w.i0 - TM_HALO < 0 ? 0 : w.i0 - TM_HALO;
   w.ce = w.i0 + TM_CW + TM_HALO > a.s.nx ? a.s.nx : w.i0 + TM_CW + TM_HALO;
-  return w;
+  w.ce += w.ce & 1;                 // bulk copies move multiples of 16 bytes: an odd width takes the padding column along
+  return w;                         // (pitch is a multiple of 16 doubles; padding is never stored to, never used)
 }
 
 // Producer side.  PHASE_B selects the stage layout / tile order.
@@ -594,7 +595,9 @@ __device__ __forceinline__ void tmad_issue_visit(const CgArgs& a, const Ring& rg
   constexpr int DIR = PHASE_B ? -1 : +1;
   const int jl0 = DIR > 0 ? w.j0 - 1 : w.j1;
   const uint32_t hbytes = (uint32_t)(w.ce - w.cs) * 8u;
-  const uint32_t cbytes = (uint32_t)TM_CW * 8u;
+  int cw = a.s.nx - w.i0 < TM_CW ? a.s.nx - w.i0 : TM_CW;       // centre-row segment, clipped in the last chunk
+  cw += cw & 1;
+  const uint32_t cbytes = (uint32_t)cw * 8u;
   const int soff = w.cs - (w.i0 - TM_HALO);
   const int jl = jl0 + DIR * t;
   const int jg = s.row0 + jl;
@@ -934,23 +937,124 @@ __device__ __forceinline__ bool tmad_lean_B(const CgArgs& a, const LeanCtx& L, c
   return true;
 }
 
+// A warp whose 64-column strip lies entirely beyond the last column (tiles of a clipped last chunk): it only keeps
+// the ring protocol going.
+__device__ __forceinline__ bool tmad_tile_idle(const Ring& rg, int nrows, int lane, unsigned long long& n) {
+  for (int t = 0; t < nrows; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(rg.empty + st);
+  }
+  return true;
+}
+
+// One tile of phase A for one warp.  XE: strip kind (X_IN / X_WALL: all 64 columns exist; X_PART: the strip is cut by
+// the last column -- per-lane validity, generic loop only).
 template <bool UNIT, int XE, bool MULTI>
+__device__ __forceinline__ bool tmad_tile_A(const CgArgs& a, const Ring& rg, LeanCtx& L, const TmaTile& w, int warp,
+                                            double* pnew, double* peer_lo, double* peer_hi, bool first, double beta,
+                                            uint64_t keep, unsigned long long& n, double& acc) {
+  const Slab& s = a.s;
+  constexpr int DIR = +1;
+  const int lane = L.lane;
+  const int k = TM_HALO + warp * STRIP + 2 * lane;                // my first column inside the haloed smem row
+  const int kh = (lane == 0) ? k - 1 : k + 2;                    // strip halo column (lanes 0 / 31)
+  const int i0 = w.i0 + warp * STRIP;
+  const Cols c = strip_cols<XE>(s, i0);
+  const int TH = w.j1 - w.j0, nrows = TH + 2;
+  const int jl0 = w.j0 - 1;
+  // lean: no visited or centre row is a global boundary row; with several GPUs also none that is mirrored to a peer
+  const bool lean = XE != X_PART && !first && !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) &&
+                    (s.row0 + w.j1 < s.nyg - 1) && !(MULTI && (w.j0 == 0 || w.j1 == s.nyl));
+  if (lean) {
+    L.vh = c.vh;
+    return tmad_lean_A<UNIT, (XE == X_PART ? X_WALL : XE)>(a, L, c, TH, pnew + cell(s, w.j0, c.ia), beta, keep, n, acc);
+  }
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  for (int t = 0; t < nrows; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+    const double* sr = rg.stage(st);
+    const double* sp = sr + TM_ROW;
+    const int jl = jl0 + DIR * t;
+    const int jg = s.row0 + jl;
+    const bool exists = jg >= 0 && jg < s.nyg;
+    double2 rr = make_double2(0.0, 0.0), pp = make_double2(0.0, 0.0);
+    double rh = 0.0, ph = 0.0;
+    if (exists) {
+      rr = *reinterpret_cast<const double2*>(sr + k);
+      if (c.vh) rh = sr[kh];
+      if (!first) {
+        pp = *reinterpret_cast<const double2*>(sp + k);
+        if (c.vh) ph = sp[kh];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(rg.empty + st);
+    const int jgc = jg - DIR;
+    const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
+    const bool ring_row = (jg == 0) || (jg == s.nyg - 1);
+    double da = a.invd, db = a.invd, dh = a.invd;
+    if (XE != X_IN || gen) {
+      da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+      db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+      dh = (ring_row || c.ring_h) ? 1.0 : a.invd;
+    }
+    const double za = da * rr.x, zb = db * rr.y, zh = dh * rh;
+    Row nw;
+    if (first) {
+      nw.a = za; nw.b = zb; nw.h = zh;
+    } else {
+      nw.a = (pp.x * beta) + za;
+      nw.b = (pp.y * beta) + zb;
+      nw.h = (ph * beta) + zh;
+    }
+    if (t >= 1 && t <= TH) {
+      double* dst = pnew + cell(s, jl, c.ia);
+      if (XE != X_PART || c.vb) st2_hint(dst, nw.a, nw.b, keep);
+      else if (c.va) st1(dst, nw.a);
+      if (MULTI && (jl == 0 || jl == s.nyl - 1)) peer_row_store(s, c, jl, peer_lo, peer_hi, nw.a, nw.b);
+    }
+    if (t >= 2) {
+      const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+      double la, lb;
+      if (gen) {
+        lap_pair<UNIT, XE, true>(a, c, prev, cur, nw, hs, hn, la, lb);
+        if (jgc == 0 && c.ia == 0) la = -cur.a;
+      } else {
+        lap_pair<UNIT, XE, false>(a, c, prev, cur, nw, hs, hn, la, lb);
+      }
+      if (XE == X_PART) {
+        if (c.va) acc += cur.a * la;
+        if (c.vb) acc += cur.b * lb;
+      } else {
+        acc += cur.a * la;
+        acc += cur.b * lb;
+      }
+    }
+    prev = cur;
+    cur = nw;
+  }
+  return true;
+}
+
+template <bool UNIT, bool MULTI>
 __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* pnew,
                                                double* peer_lo, double* peer_hi, bool first, double beta,
                                                unsigned long long& n, unsigned long long& seq, unsigned phase_seq,
                                                unsigned ptag) {
   const Slab& s = a.s;
-  constexpr int DIR = +1;
   const int lane = threadIdx.x & 31;
   const uint64_t keep = (a.y.opt & 8) ? policy_evict_last() : policy_evict_normal();
-  const int k = TM_HALO + warp * STRIP + 2 * lane;                // my first column inside the haloed smem row
-  const int kh = (lane == 0) ? k - 1 : k + 2;                    // strip halo column (lanes 0 / 31)
+  const int k = TM_HALO + warp * STRIP + 2 * lane;
+  const int kh = (lane == 0) ? k - 1 : k + 2;
   LeanCtx L;
   L.ring_at = rg.base_at; L.full_at = rg.full_at; L.empty_at = rg.empty_at;
   L.koff = (uint32_t)k * 8u; L.khoff = (uint32_t)kh * 8u; L.kcoff = (uint32_t)(warp * STRIP + 2 * lane) * 8u;
-  L.lane = lane;
+  L.lane = lane; L.vh = false;
   for (;;) {
-    int st = (int)(n % TM_STAGES);
+    const int st = (int)(n % TM_STAGES);
     if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
     const int slot = (int)(seq % TD_SLOTS);
     const int tile = ds->tile[slot];
@@ -963,76 +1067,17 @@ __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, 
     }
     const TmaTile w = tmad_tile(a, tile);
     const int i0 = w.i0 + warp * STRIP;
-    const Cols c = strip_cols<XE>(s, i0);
-    const int TH = w.j1 - w.j0, nrows = TH + 2;
-    const int jl0 = w.j0 - 1;
     double acc = 0.0;
-    // lean: no visited or centre row is a global boundary row; with several GPUs also none that is mirrored to a peer
-    const bool lean = !first && !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) && (s.row0 + w.j1 < s.nyg - 1) &&
-                      !(MULTI && (w.j0 == 0 || w.j1 == s.nyl));
-    if (lean) {
-      L.vh = c.vh;
-      if (!tmad_lean_A<UNIT, XE>(a, L, c, TH, pnew + cell(s, w.j0, c.ia), beta, keep, n, acc)) return false;
+    bool good;
+    if (i0 >= s.nx) {
+      good = tmad_tile_idle(rg, w.j1 - w.j0 + 2, lane, n);
     } else {
-      Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
-      for (int t = 0; t < nrows; ++t, ++n) {
-        st = (int)(n % TM_STAGES);
-        if (t > 0 && !mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
-        const double* sr = rg.stage(st);
-        const double* sp = sr + TM_ROW;
-        const int jl = jl0 + DIR * t;
-        const int jg = s.row0 + jl;
-        const bool exists = jg >= 0 && jg < s.nyg;
-        double2 rr = make_double2(0.0, 0.0), pp = make_double2(0.0, 0.0);
-        double rh = 0.0, ph = 0.0;
-        if (exists) {
-          rr = *reinterpret_cast<const double2*>(sr + k);
-          if (c.vh) rh = sr[kh];
-          if (!first) {
-            pp = *reinterpret_cast<const double2*>(sp + k);
-            if (c.vh) ph = sp[kh];
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(rg.empty + st);
-        const int jgc = jg - DIR;
-        const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
-        const bool ring_row = (jg == 0) || (jg == s.nyg - 1);
-        double da = a.invd, db = a.invd, dh = a.invd;
-        if (XE != X_IN || gen) {
-          da = (ring_row || c.ring_a) ? 1.0 : a.invd;
-          db = (ring_row || c.ring_b) ? 1.0 : a.invd;
-          dh = (ring_row || c.ring_h) ? 1.0 : a.invd;
-        }
-        const double za = da * rr.x, zb = db * rr.y, zh = dh * rh;
-        Row nw;
-        if (first) {
-          nw.a = za; nw.b = zb; nw.h = zh;
-        } else {
-          nw.a = (pp.x * beta) + za;
-          nw.b = (pp.y * beta) + zb;
-          nw.h = (ph * beta) + zh;
-        }
-        if (t >= 1 && t <= TH) {
-          st2_hint(pnew + cell(s, jl, c.ia), nw.a, nw.b, keep);
-          if (MULTI && (jl == 0 || jl == s.nyl - 1)) peer_row_store(s, c, jl, peer_lo, peer_hi, nw.a, nw.b);
-        }
-        if (t >= 2) {
-          const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
-          double la, lb;
-          if (gen) {
-            lap_pair<UNIT, XE, true>(a, c, prev, cur, nw, hs, hn, la, lb);
-            if (jgc == 0 && c.ia == 0) la = -cur.a;
-          } else {
-            lap_pair<UNIT, XE, false>(a, c, prev, cur, nw, hs, hn, la, lb);
-          }
-          acc += cur.a * la;
-          acc += cur.b * lb;
-        }
-        prev = cur;
-        cur = nw;
-      }
+      const int kind = strip_kind(s, i0);
+      if (kind == X_IN) good = tmad_tile_A<UNIT, X_IN, MULTI>(a, rg, L, w, warp, pnew, peer_lo, peer_hi, first, beta, keep, n, acc);
+      else if (kind == X_WALL) good = tmad_tile_A<UNIT, X_WALL, MULTI>(a, rg, L, w, warp, pnew, peer_lo, peer_hi, first, beta, keep, n, acc);
+      else good = tmad_tile_A<UNIT, X_PART, MULTI>(a, rg, L, w, warp, pnew, peer_lo, peer_hi, first, beta, keep, n, acc);
     }
+    if (!good) return false;
     double v[1] = {acc};
     tmad_tile_partial<1>(a, ds, slot, tile, warp, v, /*negate=*/true, phase_seq, ptag);     // p.q = -(sum p*lap)
     ++seq;
@@ -1040,23 +1085,112 @@ __device__ __forceinline__ bool tmad_consume_A(const CgArgs& a, const Ring& rg, 
 }
 
 template <bool UNIT, int XE, bool MULTI>
+__device__ __forceinline__ bool tmad_tile_B(const CgArgs& a, const Ring& rg, LeanCtx& L, const TmaTile& w, int warp,
+                                            double* x, double* r, double* peer_lo, double* peer_hi, double alpha,
+                                            uint64_t pol, uint64_t keep, unsigned long long& n, double& acc_rr,
+                                            double& acc_rz) {
+  const Slab& s = a.s;
+  constexpr int DIR = -1;
+  const int lane = L.lane;
+  const int k = TM_HALO + warp * STRIP + 2 * lane;
+  const int kh = (lane == 0) ? k - 1 : k + 2;
+  const int kc = warp * STRIP + 2 * lane;                         // column inside the un-haloed x / r rows
+  const int i0 = w.i0 + warp * STRIP;
+  const Cols c = strip_cols<XE>(s, i0);
+  const int TH = w.j1 - w.j0, nrows = TH + 2;
+  const int jl0 = w.j1;
+  const bool lean = XE != X_PART && !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) && (s.row0 + w.j1 < s.nyg - 1) &&
+                    !(MULTI && (w.j0 == 0 || w.j1 == s.nyl));
+  if (lean) {
+    L.vh = c.vh;
+    const size_t o = cell(s, w.j1 - 1, c.ia);
+    return tmad_lean_B<UNIT, (XE == X_PART ? X_WALL : XE)>(a, L, c, TH, x + o, r + o, alpha, pol, keep, n, acc_rr, acc_rz);
+  }
+  Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
+  for (int t = 0; t < nrows; ++t, ++n) {
+    const int st = (int)(n % TM_STAGES);
+    if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
+    const double* sp = rg.stage(st);
+    const double* sx = sp + TM_ROW;
+    const double* sr = sx + TM_CW;
+    const int jl = jl0 + DIR * t;
+    const int jg = s.row0 + jl;
+    const bool exists = jg >= 0 && jg < s.nyg;
+    Row nw = {0.0, 0.0, 0.0};
+    if (exists) {
+      const double2 pv = *reinterpret_cast<const double2*>(sp + k);
+      nw.a = pv.x; nw.b = pv.y;
+      if (c.vh) nw.h = sp[kh];
+    }
+    double2 xx = make_double2(0.0, 0.0), rr = make_double2(0.0, 0.0);
+    if (t >= 2) {
+      xx = *reinterpret_cast<const double2*>(sx + kc);
+      rr = *reinterpret_cast<const double2*>(sr + kc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(rg.empty + st);
+    if (t >= 2) {
+      const int jc = jl - DIR;
+      const int jgc = jg - DIR;
+      const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
+      const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
+      double la, lb;
+      if (gen) {
+        lap_pair<UNIT, XE, true>(a, c, nw, cur, prev, hs, hn, la, lb);
+        if (jgc == 0 && c.ia == 0) la = -cur.a;
+      } else {
+        lap_pair<UNIT, XE, false>(a, c, nw, cur, prev, hs, hn, la, lb);
+      }
+      const double xa = xx.x + alpha * cur.a;
+      const double xb = xx.y + alpha * cur.b;
+      const double ra = rr.x + alpha * la;
+      const double rb = rr.y + alpha * lb;
+      const size_t o = cell(s, jc, c.ia);
+      if (XE != X_PART || c.vb) {
+        st2_hint(x + o, xa, xb, pol);
+        st2_hint(r + o, ra, rb, keep);
+      } else if (c.va) {
+        st1(x + o, xa);
+        st1(r + o, ra);
+      }
+      if (MULTI && (jc == 0 || jc == s.nyl - 1)) peer_row_store(s, c, jc, peer_lo, peer_hi, ra, rb);
+      const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
+      double da = a.invd, db = a.invd;
+      if (XE != X_IN || gen) {
+        da = (ring_row || c.ring_a) ? 1.0 : a.invd;
+        db = (ring_row || c.ring_b) ? 1.0 : a.invd;
+      }
+      if (XE != X_PART || c.va) {
+        acc_rr += ra * ra;
+        acc_rz += ra * (da * ra);
+      }
+      if (XE != X_PART || c.vb) {
+        acc_rr += rb * rb;
+        acc_rz += rb * (db * rb);
+      }
+    }
+    prev = cur;
+    cur = nw;
+  }
+  return true;
+}
+
+template <bool UNIT, bool MULTI>
 __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, DynShared* ds, int warp, double* x,
                                                double* r, double* peer_lo, double* peer_hi, double alpha, uint64_t pol,
                                                unsigned long long& n, unsigned long long& seq, unsigned phase_seq,
                                                unsigned ptag) {
   const Slab& s = a.s;
-  constexpr int DIR = -1;
   const int lane = threadIdx.x & 31;
   const uint64_t keep = (a.y.opt & 8) ? policy_evict_last() : policy_evict_normal();
   const int k = TM_HALO + warp * STRIP + 2 * lane;
   const int kh = (lane == 0) ? k - 1 : k + 2;
-  const int kc = warp * STRIP + 2 * lane;                         // column inside the un-haloed x / r rows
   LeanCtx L;
   L.ring_at = rg.base_at; L.full_at = rg.full_at; L.empty_at = rg.empty_at;
-  L.koff = (uint32_t)k * 8u; L.khoff = (uint32_t)kh * 8u; L.kcoff = (uint32_t)kc * 8u;
-  L.lane = lane;
+  L.koff = (uint32_t)k * 8u; L.khoff = (uint32_t)kh * 8u; L.kcoff = (uint32_t)(warp * STRIP + 2 * lane) * 8u;
+  L.lane = lane; L.vh = false;
   for (;;) {
-    int st = (int)(n % TM_STAGES);
+    const int st = (int)(n % TM_STAGES);
     if (!mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
     const int slot = (int)(seq % TD_SLOTS);
     const int tile = ds->tile[slot];
@@ -1069,75 +1203,17 @@ __device__ __forceinline__ bool tmad_consume_B(const CgArgs& a, const Ring& rg, 
     }
     const TmaTile w = tmad_tile(a, tile);
     const int i0 = w.i0 + warp * STRIP;
-    const Cols c = strip_cols<XE>(s, i0);
-    const int TH = w.j1 - w.j0, nrows = TH + 2;
-    const int jl0 = w.j1;
     double v[2] = {0.0, 0.0};
-    const bool lean = !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) && (s.row0 + w.j1 < s.nyg - 1) &&
-                      !(MULTI && (w.j0 == 0 || w.j1 == s.nyl));
-    if (lean) {
-      L.vh = c.vh;
-      const size_t o = cell(s, w.j1 - 1, c.ia);
-      if (!tmad_lean_B<UNIT, XE>(a, L, c, TH, x + o, r + o, alpha, pol, keep, n, v[0], v[1])) return false;
+    bool good;
+    if (i0 >= s.nx) {
+      good = tmad_tile_idle(rg, w.j1 - w.j0 + 2, lane, n);
     } else {
-      Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
-      for (int t = 0; t < nrows; ++t, ++n) {
-        st = (int)(n % TM_STAGES);
-        if (t > 0 && !mbar_wait(rg.full + st, (uint32_t)((n / TM_STAGES) & 1ULL))) return false;
-        const double* sp = rg.stage(st);
-        const double* sx = sp + TM_ROW;
-        const double* sr = sx + TM_CW;
-        const int jl = jl0 + DIR * t;
-        const int jg = s.row0 + jl;
-        const bool exists = jg >= 0 && jg < s.nyg;
-        Row nw = {0.0, 0.0, 0.0};
-        if (exists) {
-          const double2 pv = *reinterpret_cast<const double2*>(sp + k);
-          nw.a = pv.x; nw.b = pv.y;
-          if (c.vh) nw.h = sp[kh];
-        }
-        double2 xx = make_double2(0.0, 0.0), rr = make_double2(0.0, 0.0);
-        if (t >= 2) {
-          xx = *reinterpret_cast<const double2*>(sx + kc);
-          rr = *reinterpret_cast<const double2*>(sr + kc);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(rg.empty + st);
-        if (t >= 2) {
-          const int jc = jl - DIR;
-          const int jgc = jg - DIR;
-          const bool gen = (jg <= 0) || (jg >= s.nyg - 1) || (jgc <= 0) || (jgc >= s.nyg - 1);
-          const bool hs = jgc > 0, hn = jgc < s.nyg - 1;
-          double la, lb;
-          if (gen) {
-            lap_pair<UNIT, XE, true>(a, c, nw, cur, prev, hs, hn, la, lb);
-            if (jgc == 0 && c.ia == 0) la = -cur.a;
-          } else {
-            lap_pair<UNIT, XE, false>(a, c, nw, cur, prev, hs, hn, la, lb);
-          }
-          const double xa = xx.x + alpha * cur.a;
-          const double xb = xx.y + alpha * cur.b;
-          const double ra = rr.x + alpha * la;
-          const double rb = rr.y + alpha * lb;
-          const size_t o = cell(s, jc, c.ia);
-          st2_hint(x + o, xa, xb, pol);
-          st2_hint(r + o, ra, rb, keep);
-          if (MULTI && (jc == 0 || jc == s.nyl - 1)) peer_row_store(s, c, jc, peer_lo, peer_hi, ra, rb);
-          const bool ring_row = (jgc == 0) || (jgc == s.nyg - 1);
-          double da = a.invd, db = a.invd;
-          if (XE != X_IN || gen) {
-            da = (ring_row || c.ring_a) ? 1.0 : a.invd;
-            db = (ring_row || c.ring_b) ? 1.0 : a.invd;
-          }
-          v[0] += ra * ra;
-          v[1] += ra * (da * ra);
-          v[0] += rb * rb;
-          v[1] += rb * (db * rb);
-        }
-        prev = cur;
-        cur = nw;
-      }
+      const int kind = strip_kind(s, i0);
+      if (kind == X_IN) good = tmad_tile_B<UNIT, X_IN, MULTI>(a, rg, L, w, warp, x, r, peer_lo, peer_hi, alpha, pol, keep, n, v[0], v[1]);
+      else if (kind == X_WALL) good = tmad_tile_B<UNIT, X_WALL, MULTI>(a, rg, L, w, warp, x, r, peer_lo, peer_hi, alpha, pol, keep, n, v[0], v[1]);
+      else good = tmad_tile_B<UNIT, X_PART, MULTI>(a, rg, L, w, warp, x, r, peer_lo, peer_hi, alpha, pol, keep, n, v[0], v[1]);
     }
+    if (!good) return false;
     tmad_tile_partial<2>(a, ds, slot, tile, warp, v, /*negate=*/false, phase_seq, ptag);
     ++seq;
   }
@@ -1237,7 +1313,7 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
 }
 
 template <bool UNIT, bool MULTI>
-__global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
+__global__ void __maxnreg__(112) k_cg_tmad(CgArgs a) {   // 544 threads x 112 registers: one CTA per SM; __launch_bounds__(544, 1) makes ptxas stop at 96 and spill
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double sm[3 * 32];
   __shared__ DynShared ds;
@@ -1310,14 +1386,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
             if (good) good = tmad_prefetch<true>(a, rg, &ds, pnext, a.x, a.r, pol, n, seq, pf);
           }
         } else {
-          // wall strips exist only in the first / last column chunk: the generic WALL instantiation is
-          // exact for interior strips too (its predicates are all true there), so edge warps use it always
+          // the strip kind (interior / wall / cut by the last column / beyond it) is resolved per tile
           double* plo = (pnext == a.p0) ? a.y.below_p0 : a.y.below_p1;
           double* phi = (pnext == a.p0) ? a.y.above_p0 : a.y.above_p1;
-          if (warp == 0 || warp == TM_WARPS - 1)
-            good = tmad_consume_A<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
-          else
-            good = tmad_consume_A<UNIT, X_IN, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
+          good = tmad_consume_A<UNIT, MULTI>(a, rg, &ds, warp, pnext, plo, phi, first, beta, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
         }
         if (!good) atomicExch(a.y.err, 1ULL);
         ++phase;
@@ -1344,10 +1416,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
             if (good && it + 1 < a.maxiter) good = tmad_prefetch<false>(a, rg, &ds, a.r, pnext, nullptr, pol, n, seq, pf);
           }
         } else {
-          if (warp == 0 || warp == TM_WARPS - 1)
-            good = tmad_consume_B<UNIT, X_WALL, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
-          else
-            good = tmad_consume_B<UNIT, X_IN, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
+          good = tmad_consume_B<UNIT, MULTI>(a, rg, &ds, warp, a.x, a.r, a.y.below_r, a.y.above_r, alpha, pol, n, seq, (unsigned)phase, ll_tag(tbase + 1ULL));
         }
         if (!good) atomicExch(a.y.err, 1ULL);
         ++phase;

@@ -111,7 +111,8 @@ def test_pcg_matches_scipy_recurrence(ny, nx, unit, jac):
     assert bits_equal(A.matvec(xo), orc.neg_laplacian_pinned(xo, nx, ny, dx, dy))
 
 
-@pytest.mark.parametrize("ny,nx", [(70, 65), (257, 513), (40, 1100), (33, 4096), (48, 577), (21, 129)])
+@pytest.mark.parametrize("ny,nx", [(70, 65), (257, 513), (40, 1100), (33, 4096), (48, 577), (21, 129),
+                                   (36, 2049), (50, 1030), (24, 1089), (200, 3000), (19, 1025)])
 def test_pcg_strip_and_chunk_layouts_vs_oracle(ny, nx):
     """Column layouts of the tuned kernel: one column beyond a strip (nx % 64 == 1, the
     neighbour strip's halo column is then the wall), several column chunks, partial chunks."""

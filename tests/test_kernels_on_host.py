@@ -906,6 +906,10 @@ def _tmad_solve(emu, dev, S, sync, b, dx, dy, invd, tol, maxiter, tile_rows):
     (70, 2048, (16, 4, 3), False, True, 2),   # 2 chunks: 3 x 4-row bands, 16 + 16 + 14 rows, 3 x 4-row bands = 18 tiles < one fold group
     (40, 4096, (4, 2, 4), True, True, 2),  # 4 chunks x (4 + 6 + 4) bands = 56 tiles ... and
     (70, 4096, (4, 1, 3), True, True, 2),  # 4 chunks x (3 + 16 + 3) bands = 88 tiles: two fold groups (64 + 24)
+    (9, 1100, 4, True, True, 3),           # clipped last chunk: 76 columns = one full strip + a strip cut at 12 columns, 14 idle warps
+    (11, 1030, 4, False, True, 3),         # last chunk of 6 columns (one cut strip), non-unit spacing
+    (22, 2049, 4, True, True, 2),          # ODD width: the last chunk is ONE column (copied together with the padding column)
+    (10, 1089, 4, True, True, 3),          # 1024 + 65: the strip whose east halo column is the wall, then a one-column strip
 ])
 def test_tma_fed_cg_kernel_vs_oracle(emu, ny, nx, tile_rows, unit, jacobi, maxiter):
     """k_cg_tmad<unit, single GPU> on one CTA: producer thread, 8-stage ring, ticket-drawn tiles (ascending in phase
@@ -1031,6 +1035,8 @@ class Ranks:
     (4, 8, 2048, 2, True, True, 3),          # four ranks, two column chunks, two-row slabs
     (2, 4, 1024, 4, True, True, 300),        # runs to convergence: every rank takes the same stop decision
     (2, 28, 1024, (4, 1, 2), True, True, 3),   # per rank: two 1-row tiles at each end of the 14-row slab, 4 + 4 + 2 rows between
+    (2, 12, 1100, 4, True, True, 3),           # clipped last chunk across two ranks (peer rows of a cut strip)
+    (3, 12, 1025, 2, False, True, 3),          # odd width, three ranks
 ])
 def test_multi_gpu_tma_kernel_with_concurrent_ranks_vs_single_domain_oracle(emu, R, ny, nx, tile_rows, unit, jacobi,
                                                                             maxiter):

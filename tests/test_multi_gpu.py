@@ -37,7 +37,7 @@ def test_slab_parity(mode):
     if os.path.isdir(keep):
         with open(os.path.join(keep, f"multi_gpu_parity_{mode}_world{world}.log"), "w") as fh:
             fh.write("\n".join(lines) + "\n")
-    want = 9 if mode == "peer" else 8               # slab cases + the driver case
+    want = 10 if mode == "peer" else 9              # slab cases + the driver case
     assert r.returncode == 0 and "FAIL" not in r.stdout and len(lines) == want, r.stdout[-3000:] + r.stderr[-3000:]
     if mode == "peer":
-        assert sum("peer_kernel=True" in ln for ln in lines) >= 6   # the equal-slab cases really ran the NVLink kernels
+        assert sum("peer_kernel=True" in ln for ln in lines) >= 7   # the equal-slab cases really ran the NVLink kernels

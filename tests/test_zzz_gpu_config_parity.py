@@ -61,3 +61,10 @@ def test_config5_16384_full_slab_vs_c_oracle():
     if _host_gib() < 80:
         pytest.skip("needs ~60 GiB of host memory for the oracle and both states")
     _check("config5 16384x16384 (lin_maxiter 30)", parity.make_cfg(16384, 16384, 1000.0, lin_maxiter=30), 2)
+
+
+@pytest.mark.parametrize("nx,ny", [(4000, 4000), (5000, 3000), (4097, 1500)])
+def test_general_widths_take_the_tma_kernel_and_match_the_c_oracle(nx, ny):
+    """Widths that are not a multiple of 1024 (clipped last column chunk, strips cut by the east wall, an odd width
+    whose last chunk is a single column): the TMA-fed kernel, whole steps against the C oracle."""
+    _check(f"{nx}x{ny}", parity.make_cfg(nx, ny, 1000.0), 3)
