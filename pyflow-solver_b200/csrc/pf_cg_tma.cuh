@@ -1313,7 +1313,11 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
 }
 
 template <bool UNIT, bool MULTI>
+#ifdef PF_TMAD_LAUNCH_BOUNDS
+__global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
+#else
 __global__ void __maxnreg__(112) k_cg_tmad(CgArgs a) {   // 544 threads x 112 registers: one CTA per SM; __launch_bounds__(544, 1) makes ptxas stop at 96 and spill
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double sm[3 * 32];
   __shared__ DynShared ds;
