@@ -1313,10 +1313,13 @@ __device__ __forceinline__ bool tile_exchange(const CgArgs& a, unsigned long lon
 }
 
 template <bool UNIT, bool MULTI>
-#ifdef PF_TMAD_LAUNCH_BOUNDS
-__global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
+// __launch_bounds__(544, 1) makes ptxas stop at 96 registers (a few bytes of spills in the general-spacing and multi-GPU
+// instantiations).  Measured alternative, -DPF_TMAD_MAXNREG: __maxnreg__(112) removes the spills and is 7 % (4096^2) to
+// 19 % (16384^2) SLOWER (profiles/r2_ab_maxnreg.txt).
+#ifdef PF_TMAD_MAXNREG
+__global__ void __maxnreg__(112) k_cg_tmad(CgArgs a) {
 #else
-__global__ void __maxnreg__(112) k_cg_tmad(CgArgs a) {   // 544 threads x 112 registers: one CTA per SM; __launch_bounds__(544, 1) makes ptxas stop at 96 and spill
+__global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tmad(CgArgs a) {
 #endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double sm[3 * 32];
