@@ -240,6 +240,7 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     sa.epoch = (unsigned long long*)(c->ws_base + c->sync_off) + 7;
     sa.err = (unsigned long long*)(c->ws_base + c->sync_off) + 3;
     sa.dx = dx; sa.dy = dy; sa.invd = invd; sa.tol = tol; sa.maxiter = maxiter; sa.rows = small_rows;
+    sa.trace = (c->opt_sync & 4) ? (unsigned long long*)c->cg_part : nullptr;      // [G][8] stamps of iteration 100
     PF_CUDA(c, cudaMemsetAsync(sa.err, 0, sizeof(unsigned long long), st));
     const int grid = (s.nyl + small_rows - 1) / small_rows;
     void* args[] = {&sa};

@@ -41,6 +41,7 @@ struct SmallArgs {
   double dx, dy, invd, tol;
   int maxiter;
   int rows;                 // rows per CTA (last CTA may own fewer)
+  unsigned long long* trace;    // timeline of iteration 100 (pf_set_option cg_sync_opt bit 4), else null: [G][8] globaltimer stamps
 };
 
 // shared memory: p with halo rows [(rows+2)][nx] + the neighbours' boundary rows of r [2][nx]
@@ -76,7 +77,7 @@ constexpr unsigned SMF_VALID = 1u, SMF_HS = 2u, SMF_HN = 4u, SMF_HW = 8u, SMF_HE
 // reduction, which needs this CTA's packet, which is posted after these reads.
 template <int NV, bool HALO>
 __device__ __forceinline__ void small_allreduce(const SmallArgs& a, unsigned long long e, double (&v)[NV], double* sm,
-                                                double* s_res2, double* rh_s) {
+                                                double* s_res2, double* rh_s, unsigned long long* tr = nullptr) {
   const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bid = blockIdx.x;
   const int nx = a.s.nx;
   const unsigned tag = ll_tag(e);
@@ -96,6 +97,7 @@ __device__ __forceinline__ void small_allreduce(const SmallArgs& a, unsigned lon
       for (int k = 0; k < NV; ++k)
         for (int q = 0; q < SM_THREADS / 32; ++q) t[k] += sm[k * 32 + q];
       st_ll4<LL_GPU>(slots + (size_t)bid * SM_SLOT_DOUBLES, ll_encode(t[0], tag), ll_encode(t[1], tag));
+      if (tr) tr[0] = gtime();                           // posted
     }
     double g0[SM_POLL], g1[SM_POLL];                   // decoded partials of this lane's slots
     unsigned pending = 0u;
@@ -122,6 +124,7 @@ __device__ __forceinline__ void small_allreduce(const SmallArgs& a, unsigned lon
         break;
       }
     }
+    if (tr && lane == 0) tr[1] = gtime();                // every packet seen
     double acc[2] = {0.0, 0.0};
 #pragma unroll
     for (int j = 0; j < SM_POLL; ++j) {                  // CTA order within a lane, fixed xor tree across lanes
@@ -233,6 +236,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_cg_small(SmallArgs a) {
       if (sqrt(rr) < atol) { info = 0; break; }
       const bool first = (it == 0);
       const double beta = first ? 0.0 : rho / rho_prev;
+      unsigned long long* tr = (a.trace && it == 100) ? a.trace + (size_t)bid * 8 : nullptr;
+      if (tr && tid == 0) tr[0] = gtime();                // iteration start
       // ---- phase A.1: p = (p*beta) + M r on own cells (registers -> shared) AND on the two halo rows
 #pragma unroll
       for (int k = 0; k < NP; ++k) {
@@ -283,7 +288,9 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_cg_small(SmallArgs a) {
           v1[0] += pb[k] * q1;
         }
       }
-      small_allreduce<1, false>(a, ++e, v1, sm, s_res, rh_s);
+      if (tr && tid == 0) tr[1] = gtime();                // A.1 + A.2 done
+      small_allreduce<1, false>(a, ++e, v1, sm, s_res, rh_s, tr ? tr + 2 : nullptr);      // tr[2] posted, tr[3] all seen
+      if (tr && tid == 0) tr[4] = gtime();                // exchange 1 done
       const double alpha = rho / v1[0];
       // ---- phase B: x += alpha p ; r -= alpha q (registers) ; the owners of the band's first / last row
       //      post them for the neighbours, tagged with the epoch of the exchange that follows
@@ -310,7 +317,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_cg_small(SmallArgs a) {
           v2[1] += rb[k] * (((f & SMF_RING_B) ? 1.0 : a.invd) * rb[k]);
         }
       }
-      small_allreduce<2, true>(a, e, v2, sm, s_res, rh_s);   // also fetches the neighbours' boundary rows of r
+      if (tr && tid == 0) tr[5] = gtime();                // phase B done
+      small_allreduce<2, true>(a, e, v2, sm, s_res, rh_s, tr ? tr + 6 : nullptr);   // also fetches the neighbours' boundary rows of r; tr[6] posted, tr[7] all seen
       rr = v2[0];
       rho_prev = rho;
       rho = v2[1];

@@ -861,20 +861,29 @@ __device__ __forceinline__ bool tmad_lean_A(const CgArgs& a, const LeanCtx& L, c
   auto stencil = [&](const Row& south, const Row& centre, const Row& north) {
     double la, lb;
     lap_pair<UNIT, XE, false>(a, c, south, centre, north, true, true, la, lb);
-    acc += centre.a * la;
-    acc += centre.b * lb;
+    if (XE == X_PART) {                               // strip cut by the last column: per-lane validity
+      if (c.va) acc += centre.a * la;
+      if (c.vb) acc += centre.b * lb;
+    } else {
+      acc += centre.a * la;
+      acc += centre.b * lb;
+    }
+  };
+  auto store = [&](double* dst, const Row& v) {
+    if (XE != X_PART || c.vb) st2_hint(dst, v.a, v.b, keep);
+    else if (c.va) st1(dst, v.a);
   };
   Row nw;
   if (!visit(nw)) return false;                       // t = 0: the row below the tile
   cur = nw;
   if (!visit(nw)) return false;                       // t = 1: first tile row
-  st2_hint(pdst, nw.a, nw.b, keep);
+  store(pdst, nw);
   pdst += pitch;
   prev = cur; cur = nw;
 #pragma unroll 2
   for (int t = 2; t <= TH; ++t) {
     if (!visit(nw)) return false;
-    st2_hint(pdst, nw.a, nw.b, keep);
+    store(pdst, nw);
     pdst += pitch;
     stencil(prev, cur, nw);
     prev = cur; cur = nw;
@@ -924,14 +933,23 @@ __device__ __forceinline__ bool tmad_lean_B(const CgArgs& a, const LeanCtx& L, c
     const double xb = xx.y + alpha * cur.b;
     const double ra = rr.x + alpha * la;
     const double rb = rr.y + alpha * lb;
-    st2_hint(xdst, xa, xb, pol);
-    st2_hint(rdst, ra, rb, keep);
+    if (XE != X_PART || c.vb) {
+      st2_hint(xdst, xa, xb, pol);
+      st2_hint(rdst, ra, rb, keep);
+    } else if (c.va) {
+      st1(xdst, xa);
+      st1(rdst, ra);
+    }
     xdst -= pitch;
     rdst -= pitch;
-    acc_rr += ra * ra;
-    acc_rz += ra * (da * ra);
-    acc_rr += rb * rb;
-    acc_rz += rb * (db * rb);
+    if (XE != X_PART || c.va) {
+      acc_rr += ra * ra;
+      acc_rz += ra * (da * ra);
+    }
+    if (XE != X_PART || c.vb) {
+      acc_rr += rb * rb;
+      acc_rz += rb * (db * rb);
+    }
     prev = cur; cur = nw;
   }
   return true;
@@ -950,7 +968,7 @@ __device__ __forceinline__ bool tmad_tile_idle(const Ring& rg, int nrows, int la
 }
 
 // One tile of phase A for one warp.  XE: strip kind (X_IN / X_WALL: all 64 columns exist; X_PART: the strip is cut by
-// the last column -- per-lane validity, generic loop only).
+// the last column -- per-lane validity in the stores and the sums).
 template <bool UNIT, int XE, bool MULTI>
 __device__ __forceinline__ bool tmad_tile_A(const CgArgs& a, const Ring& rg, LeanCtx& L, const TmaTile& w, int warp,
                                             double* pnew, double* peer_lo, double* peer_hi, bool first, double beta,
@@ -965,11 +983,11 @@ __device__ __forceinline__ bool tmad_tile_A(const CgArgs& a, const Ring& rg, Lea
   const int TH = w.j1 - w.j0, nrows = TH + 2;
   const int jl0 = w.j0 - 1;
   // lean: no visited or centre row is a global boundary row; with several GPUs also none that is mirrored to a peer
-  const bool lean = XE != X_PART && !first && !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) &&
+  const bool lean = !first && !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) &&
                     (s.row0 + w.j1 < s.nyg - 1) && !(MULTI && (w.j0 == 0 || w.j1 == s.nyl));
   if (lean) {
     L.vh = c.vh;
-    return tmad_lean_A<UNIT, (XE == X_PART ? X_WALL : XE)>(a, L, c, TH, pnew + cell(s, w.j0, c.ia), beta, keep, n, acc);
+    return tmad_lean_A<UNIT, XE>(a, L, c, TH, pnew + cell(s, w.j0, c.ia), beta, keep, n, acc);
   }
   Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
   for (int t = 0; t < nrows; ++t, ++n) {
@@ -1099,12 +1117,12 @@ __device__ __forceinline__ bool tmad_tile_B(const CgArgs& a, const Ring& rg, Lea
   const Cols c = strip_cols<XE>(s, i0);
   const int TH = w.j1 - w.j0, nrows = TH + 2;
   const int jl0 = w.j1;
-  const bool lean = XE != X_PART && !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) && (s.row0 + w.j1 < s.nyg - 1) &&
+  const bool lean = !(a.y.opt & 16) && (s.row0 + w.j0 - 1 > 0) && (s.row0 + w.j1 < s.nyg - 1) &&
                     !(MULTI && (w.j0 == 0 || w.j1 == s.nyl));
   if (lean) {
     L.vh = c.vh;
     const size_t o = cell(s, w.j1 - 1, c.ia);
-    return tmad_lean_B<UNIT, (XE == X_PART ? X_WALL : XE)>(a, L, c, TH, x + o, r + o, alpha, pol, keep, n, acc_rr, acc_rz);
+    return tmad_lean_B<UNIT, XE>(a, L, c, TH, x + o, r + o, alpha, pol, keep, n, acc_rr, acc_rz);
   }
   Row prev = {0.0, 0.0, 0.0}, cur = {0.0, 0.0, 0.0};
   for (int t = 0; t < nrows; ++t, ++n) {

@@ -49,6 +49,8 @@ UPWIND, QUICK, NONE = 0, 1, 2
 def generate_small_kernel_copy(dest_dir):
     src = open(os.path.join(ROOT, "pyflow-solver_b200", "csrc", "pf_cg_small.cuh")).read()
     for old, new in (
+            ('#include "pf_cg.cuh"', '#include "pf_cg.cuh"\nnamespace pf { inline unsigned long long emu_small_gtime() '
+                                     '{ return (unsigned long long)clock64(); } }\n#define gtime emu_small_gtime'),
             ("extern __shared__ __align__(16) double smem_d[];", "double* smem_d = emu::dyn_shared();"),
             ("__shared__ double sm[3 * 32];", "double* sm = emu::blk_shared(0);"),
             ("__shared__ double s_res[8];", "double* s_res = emu::blk_shared(1);")):
