@@ -178,6 +178,16 @@ int pf_op_krylov_diag(pf_ctx* ctx, int method, const double* b, const double* in
                       double dx, double dy, double tol, int maxiter,
                       int* info, int* true_iters, double* rnorm, void* stream);
 
+/* The same two recurrences on the matrix the reference ASSEMBLES (assemble_negative_laplacian,
+ * src/pyflow/solvers/pressure_solver.py:15-40): identity rows on the boundary ring, the plain 5-point stencil
+ * coef = {south, west, centre, east, north} on interior rows, products summed in CSR column order like scipy's
+ * csr_matvec.  This is what linear_solvers/interface.py:23-53 `solve(A, b)` runs when a caller hands it that sparse
+ * matrix (recognised on the host from its CSR arrays) instead of the matrix-free operator.  method 0: cg, 1: bicgstab;
+ * jacobi != 0: M = diag(1 on the ring, inv_diag_interior inside).  Outputs as pf_op_bicgstab.                      */
+int pf_op_krylov_stencil5(pf_ctx* ctx, int method, const double* b, double* x, const double coef[5], int jacobi,
+                          double inv_diag_interior, double tol, int maxiter,
+                          int* info, int* true_iters, double* rnorm, void* stream);
+
 /* Multi-GPU slabs (no reference counterpart: SURVEY.md section 8e).  One
  * process per GPU; rank 0 makes the id, the host side broadcasts the 128
  * bytes (torch.distributed), every rank calls pf_comm_init.                  */

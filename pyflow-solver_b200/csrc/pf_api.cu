@@ -895,7 +895,7 @@ int pf_op_cg_generic(pf_ctx* c, int mode, const double* b, double* x, double dx,
 // buffers, which hold nothing between time steps (k_predict rewrites them before anything reads them).
 static int krylov_generic(pf_ctx* c, int method, const double* b, const double* inv_diag, double* x, double dx,
                           double dy, int jacobi, double inv_diag_interior, double tol, int maxiter, int* info,
-                          int* true_iters, double* rnorm, void* stream) {
+                          int* true_iters, double* rnorm, void* stream, const double* ring5_coef = nullptr) {
   PF_OP_PROLOGUE();
   if (!b || !x || maxiter < 0 || (method != 0 && method != 1) || (method == 0 && !inv_diag)) return PF_ERR_ARG;
   PF_TRY(h2d_field(c, c->b, b, nxs, st));
@@ -905,6 +905,8 @@ static int krylov_generic(pf_ctx* c, int method, const double* b, const double* 
   a.part = c->cg_part; a.scal = c->scal;
   a.minv = inv_diag ? c->vo : nullptr;
   a.dx = dx; a.dy = dy; a.invd = jacobi ? inv_diag_interior : 1.0; a.tol = tol; a.maxiter = maxiter;
+  a.ring5 = ring5_coef ? 1 : 0;
+  for (int k = 0; k < 5; ++k) a.coef[k] = ring5_coef ? ring5_coef[k] : 0.0;
   void* args[] = {&a};
   const bool unit = is_unit(dx, dy);
   const void* fn = method == 1 ? (unit ? (const void*)k_bicgstab<true> : (const void*)k_bicgstab<false>)
@@ -936,6 +938,36 @@ int pf_op_krylov_diag(pf_ctx* c, int method, const double* b, const double* inv_
                       double tol, int maxiter, int* info, int* true_iters, double* rnorm, void* stream) {
   if (!inv_diag) return PF_ERR_ARG;
   return krylov_generic(c, method, b, inv_diag, x, dx, dy, 0, 1.0, tol, maxiter, info, true_iters, rnorm, stream);
+}
+
+// Krylov solve on the matrix the reference assembles (identity ring, 5-point interior; see MODE_RING5).
+int pf_op_krylov_stencil5(pf_ctx* c, int method, const double* b, double* x, const double coef[5], int jacobi,
+                          double inv_diag_interior, double tol, int maxiter, int* info, int* true_iters,
+                          double* rnorm, void* stream) {
+  if (!c || !coef) return PF_ERR_ARG;
+  if (method == 1)
+    return krylov_generic(c, 1, b, nullptr, x, 1.0, 1.0, jacobi, inv_diag_interior, tol, maxiter, info, true_iters,
+                          rnorm, stream, coef);
+  PF_OP_PROLOGUE();
+  if (!b || !x || maxiter < 0 || method != 0) return PF_ERR_ARG;
+  PF_TRY(h2d_field(c, c->b, b, nxs, st));
+  GenArgs a{};
+  a.s = s; a.b = c->b; a.x = c->x; a.r = c->r; a.p = c->p0; a.q = c->p1;
+  a.part = c->cg_part; a.scal = c->scal;
+  a.dx = 1.0; a.dy = 1.0; a.invd = jacobi ? inv_diag_interior : 1.0; a.tol = tol; a.maxiter = maxiter; a.mode = MODE_RING5;
+  for (int k = 0; k < 5; ++k) a.coef[k] = coef[k];
+  void* args[] = {&a};
+  const long long ncell = (long long)s.nx * s.nyl;
+  const int grid = (int)std::max(1LL, std::min((long long)c->gen_grid, (ncell + CG_THREADS - 1) / CG_THREADS));
+  PF_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_cg_generic<true>, dim3(grid), dim3(CG_THREADS), args, 0, st));
+  c->launches++;
+  c->center_valid = false;
+  PF_TRY(d2h_field(c, x, c->x, nxs, st));
+  PF_TRY(read_scalars(c, st, false));
+  if (info) *info = (int)c->h_scal[S_INFO];
+  if (true_iters) *true_iters = (int)c->h_scal[S_ITERS];
+  if (rnorm) *rnorm = sqrt(c->h_scal[S_RES_SUMSQ]);
+  return PF_OK;
 }
 
 int pf_comm_unique_id(void* out128) { return comm_unique_id(out128); }

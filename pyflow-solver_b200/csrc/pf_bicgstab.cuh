@@ -45,6 +45,8 @@ struct BiArgs {
   const double* minv; // general inverse diagonal (device field layout) or nullptr = ring identity / invd
   double dx, dy, invd, tol;
   int maxiter;
+  int ring5;          // != 0: the assembled ring-identity 5-point matrix (MODE_RING5 of pf_cg_generic.cuh) instead of the pinned operator
+  double coef[5];
 };
 
 // M[cell]: the caller's diagonal if there is one, else 1 on the boundary ring and invd inside
@@ -80,6 +82,7 @@ __device__ __forceinline__ double bi_apply_scaled(const BiArgs& a, const double*
     if (hs) so = bi_scale(a, ring_s, cell(s, jl - 1, i)) * so;
     if (hn) n = bi_scale(a, ring_n, cell(s, jl + 1, i)) * n;
   }
+  if (a.ring5) return ring5_row(c, ww, e, so, n, !hw || !he || !hs || !hn, a.coef);
   const double nl = neg_lap<UNIT>(c, ww, e, so, n, hw, he, hs, hn, a.dx, a.dy);
   return (jg == 0 && i == 0) ? c : nl;
 }

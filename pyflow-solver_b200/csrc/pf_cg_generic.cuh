@@ -5,6 +5,11 @@
 //                  of the tuned kernels)
 //   MODE_DIRICHLET x -> +laplacian_coherent(x), identity rows on the boundary ring
 //                  (manufactured / verification mode, pressure_solver.py:61-93)
+//   MODE_RING5     the matrix the reference ASSEMBLES (assemble_negative_laplacian,
+//                  pressure_solver.py:15-40): identity rows on the boundary ring, the plain
+//                  5-point -Laplacian inside, evaluated in CSR column order like scipy's
+//                  csr_matvec -- what linear_solvers.solve(A, b) gets when a caller hands it
+//                  that sparse matrix instead of the matrix-free operator
 // Same scipy recurrence and stopping rule as pf_cg.cuh; no preconditioner other
 // than the ring Jacobi of the pinned operator (the reference skips the automatic
 // Jacobi in manufactured mode).  Single-GPU contexts only.
@@ -16,7 +21,7 @@
 
 namespace pf {
 
-enum { MODE_PINNED = 0, MODE_DIRICHLET = 1 };
+enum { MODE_PINNED = 0, MODE_DIRICHLET = 1, MODE_RING5 = 2 };
 
 struct GenArgs {
   Slab s;
@@ -30,6 +35,7 @@ struct GenArgs {
   double dx, dy, invd, tol;
   int maxiter;
   int mode;
+  double coef[5];     // MODE_RING5: interior row {south, west, centre, east, north} = {-1/dy^2, -1/dx^2, 2/dx^2+2/dy^2, -1/dx^2, -1/dy^2}
 };
 
 template <bool UNIT>
@@ -42,9 +48,10 @@ __device__ __forceinline__ double gen_apply(const GenArgs& a, const double* v, i
   const double e = he ? v[cell(s, jl, i + 1)] : 0.0;
   const double so = hs ? v[cell(s, jl - 1, i)] : 0.0;
   const double n = hn ? v[cell(s, jl + 1, i)] : 0.0;
+  const bool ring = !hw || !he || !hs || !hn;
+  if (a.mode == MODE_RING5) return ring5_row(c, w, e, so, n, ring, a.coef);
   const double nl = neg_lap<UNIT>(c, w, e, so, n, hw, he, hs, hn, a.dx, a.dy);
   if (a.mode == MODE_PINNED) return (jg == 0 && i == 0) ? c : nl;
-  const bool ring = !hw || !he || !hs || !hn;
   return ring ? c : -nl;
 }
 

@@ -76,6 +76,20 @@ __device__ __forceinline__ double neg_lap(double c, double w, double e, double s
   return -lap;
 }
 
+// One row of the matrix the reference assembles (pressure_solver.py:15-40) applied to a vector: identity on the
+// boundary ring, else the five products summed left to right in CSR column order (south, west, centre, east, north),
+// which is how scipy's csr_matvec evaluates it.
+__device__ __forceinline__ double ring5_row(double c, double w, double e, double s, double n, bool ring, const double* coef) {
+  if (ring) return c;
+  double sum = 0.0;
+  sum += coef[0] * s;
+  sum += coef[1] * w;
+  sum += coef[2] * c;
+  sum += coef[3] * e;
+  sum += coef[4] * n;
+  return sum;
+}
+
 // ---- raw global memory access (never the non-coherent path: buffers are
 // rewritten between phases of the persistent kernel) -------------------------
 #ifdef PF_HOST_EMULATION

@@ -269,6 +269,20 @@ class DeviceSlab:
                    self.ctx, "pf_op_krylov_diag")
         return x, info.value, iters.value, rnorm.value
 
+    def krylov_stencil5(self, method: str, b, coef, tol, maxiter, jacobi=False, inv_diag_interior=1.0):
+        """CG ('cg') or BiCGSTAB (anything else, as in the reference) on the ASSEMBLED ring-identity 5-point matrix
+        (reference pressure_solver.py:15-40); coef = (south, west, centre, east, north) of an interior row.
+        Returns like ``pcg``."""
+        b = self._dense(b)
+        x = np.empty_like(b)
+        cf = (C.c_double * 5)(*[float(v) for v in coef])
+        info, iters, rnorm = C.c_int(), C.c_int(), C.c_double()
+        _lib.check(self._lib.pf_op_krylov_stencil5(self.ctx, 0 if method == "cg" else 1, _ptr(b), _ptr(x), cf,
+                                                   int(bool(jacobi)), float(inv_diag_interior), float(tol), int(maxiter),
+                                                   C.byref(info), C.byref(iters), C.byref(rnorm), self._stream()),
+                   self.ctx, "pf_op_krylov_stencil5")
+        return x, info.value, iters.value, rnorm.value
+
     def cg_generic(self, mode: str, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=1.0, want_x=True):
         """Reference-order CG with the plain (q stored) kernel.  mode 'pinned' | 'dirichlet'.
         The solution stays in the context's p field.  Returns (x|None, info, iters, ||b-Ax||, ||b||)."""

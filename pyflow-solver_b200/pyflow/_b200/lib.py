@@ -21,7 +21,7 @@ EXPORTS = (
     "pf_upload", "pf_download", "pf_prestep_reduce", "pf_step", "pf_centerline", "pf_divergence_stats",
     "pf_op_gradient_coherent", "pf_op_divergence_coherent", "pf_op_laplacian_coherent",
     "pf_op_divergence_central", "pf_op_gradient_central", "pf_op_laplacian_central",
-    "pf_op_pressure_correction_central", "pf_op_advect", "pf_op_pcg", "pf_op_cg_generic", "pf_op_bicgstab", "pf_op_krylov_diag",
+    "pf_op_pressure_correction_central", "pf_op_advect", "pf_op_pcg", "pf_op_cg_generic", "pf_op_bicgstab", "pf_op_krylov_diag", "pf_op_krylov_stencil5",
     "pf_comm_unique_id", "pf_comm_init", "pf_comm_set_peers", "pf_device_info", "pf_launch_count", "pf_set_option", "pf_debug_read_partials",
 )
 
@@ -84,6 +84,8 @@ def _declare(lib):
     lib.pf_op_bicgstab.argtypes = lib.pf_op_pcg.argtypes
     lib.pf_op_krylov_diag.argtypes = [vp, C.c_int, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_int,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), dp, vp]
+    lib.pf_op_krylov_stencil5.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double,
+                                          C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), dp, vp]
     lib.pf_op_cg_generic.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                      C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, vp]
     lib.pf_comm_unique_id.argtypes = [vp]

@@ -217,6 +217,28 @@ class CpuSlab:
         self.p[:] = x.reshape(ny, nx)
         return x.reshape(ny, nx), int(info), int(iters), float(np.sqrt(_norm2(rhs - A(x))))
 
+    def krylov_stencil5(self, method, b, coef, tol, maxiter, jacobi=False, inv_diag_interior=1.0):
+        """The assembled ring-identity 5-point matrix (reference pressure_solver.py:15-40) through scipy's own CSR
+        matvec, so the stand-in has the arithmetic of the reference's `solve(A, b)` on that matrix."""
+        import scipy.sparse as sp
+        b = self._dense(b)
+        ny, nx = b.shape
+        n = nx * ny
+        jj, ii = np.divmod(np.arange(n), nx)
+        ring = (ii == 0) | (ii == nx - 1) | (jj == 0) | (jj == ny - 1)
+        inner = np.flatnonzero(~ring)
+        rows = np.concatenate([np.flatnonzero(ring), np.repeat(inner, 5)])
+        cols = np.concatenate([np.flatnonzero(ring), (inner[:, None] + np.array([-nx, -1, 0, 1, nx])[None, :]).reshape(-1)])
+        vals = np.concatenate([np.ones(int(ring.sum())), np.tile(np.asarray(coef, dtype=np.float64), inner.size)])
+        Amat = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+        Amat.sort_indices()
+        inv_diag = np.where(ring, 1.0, inv_diag_interior) if jacobi else None
+        rhs = b.reshape(-1).copy()
+        x, info, iters = (orc.pcg if method == "cg" else orc.bicgstab)(lambda v: Amat @ v, rhs, tol, maxiter, inv_diag)
+        x = np.array(x, dtype=np.float64)
+        self.p[:] = x.reshape(ny, nx)
+        return x.reshape(ny, nx), int(info), int(iters), float(np.sqrt(_norm2(rhs - Amat @ x)))
+
     def bicgstab(self, b, dx, dy, tol, maxiter, jacobi=False, inv_diag_interior=None):
         return self.pcg(b, dx, dy, tol, maxiter, jacobi, inv_diag_interior, _krylov=orc.bicgstab)
 

@@ -706,3 +706,35 @@ def test_reference_recipe_for_the_jacobi_preconditioner_is_recognised(slab_cls):
         with pytest.raises(NotImplementedError):
             solve_pressure_poisson(allocate_state(nx, ny), 0.01, dx, dy, cfg, preconditioner=bad)
     assert jacobi_preconditioner(sp.identity(4, format="csr")).as_ring(2, 2).inv_diag_interior == 0.25
+
+
+# ------------------------------------------------------------------ linear_solvers.solve on the assembled matrix
+def test_solve_recognises_the_assembled_matrix_of_the_reference(slab_cls):
+    """``solve(A, b)`` with the sparse matrix ``assemble_negative_laplacian`` returns (reference
+    pressure_solver.py:15-40): recognised from its CSR arrays (identity ring rows + one 5-point interior row), routed
+    to the device entry point with the stencil coefficients; anything else is refused -- no CPU fallback."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from pyflow.linear_solvers.interface import Ring5Matrix, recognise_ring5, solve
+    from pyflow.linear_solvers.preconditioners import jacobi_preconditioner
+    from pyflow.solvers.pressure_solver import assemble_negative_laplacian
+    nx, ny, dx, dy = 12, 9, 0.5, 0.25
+    A = assemble_negative_laplacian(nx, ny, dx, dy)
+    found = recognise_ring5(A)
+    assert found == Ring5Matrix(nx, ny, (-1.0 / dy ** 2, -1.0 / dx ** 2, 2.0 / dx ** 2 + 2.0 / dy ** 2, -1.0 / dx ** 2, -1.0 / dy ** 2))
+    assert recognise_ring5(A.tolil()) == found and recognise_ring5(sp.csc_matrix(A)) == found      # any sparse format
+    b = np.random.default_rng(5).standard_normal(nx * ny)
+    # the matrix is NOT symmetric (interior rows couple to ring cells, ring rows are identity rows): CG on it is what
+    # the reference does when asked, so it is compared truncated; BiCGSTAB converges
+    for method, ref, maxiter in (("cg", spla.cg, 25), ("bicgstab", spla.bicgstab, 400)):
+        got = solve(A, b, method=method, tol=1e-10, maxiter=maxiter, M=jacobi_preconditioner(A))
+        D = A.diagonal()
+        x_ref, info = ref(A, b, rtol=1e-10, maxiter=maxiter, M=spla.LinearOperator(A.shape, matvec=lambda v: v / D))
+        assert got.iterations == (info if info > 0 else 0) and (method == "cg" or (info == 0 and got.converged))
+        assert np.linalg.norm(got.x - x_ref) <= 1e-9 * np.linalg.norm(x_ref)
+    bad = A.tolil()
+    bad[nx + 1, nx + 2] = -3.0
+    for M in (bad.tocsr(), sp.identity(nx * ny).tocsr(), sp.random(nx * ny, nx * ny, 0.05, random_state=1).tocsr()):
+        assert recognise_ring5(M) is None
+        with pytest.raises(NotImplementedError):
+            solve(M, b, method="cg")

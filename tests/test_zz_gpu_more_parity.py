@@ -169,6 +169,49 @@ def test_assembled_matrix_jacobi_runs_on_the_device():
     assert bits_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
 
 
+@pytest.mark.parametrize("method,nx,ny,dx,dy,maxiter,pc", [
+    ("cg", 24, 20, 1.0, 1.0, 40, True), ("cg", 70, 33, 0.5, 0.25, 25, False), ("cg", 300, 200, 1.0, 1.0, 30, True),
+    ("bicgstab", 24, 20, 1.0, 1.0, 400, True), ("bicgstab", 70, 33, 0.5, 0.25, 12, False),
+    ("bicgstab", 40, 48, 1.0, 1.0, 2000, True)])
+def test_solve_accepts_the_assembled_matrix_of_the_reference(method, nx, ny, dx, dy, maxiter, pc):
+    """linear_solvers.solve(A, b) with A = assemble_negative_laplacian(...) as a scipy CSR matrix -- the one matrix the
+    reference itself builds (pressure_solver.py:15-40) -- is recognised from its CSR arrays and solved on the device
+    (k_cg_generic MODE_RING5 / k_bicgstab, products summed in CSR column order).  Checker: scipy itself on the same
+    matrix, called the way the reference's interface.py:17-45 calls it.  The matrix is not symmetric (identity ring
+    rows), so CG -- which the reference runs on it when asked -- is compared truncated, BiCGSTAB also converged."""
+    import scipy.sparse.linalg as spla
+    from pyflow.linear_solvers.interface import recognise_ring5, solve
+    from pyflow.linear_solvers.preconditioners import jacobi_preconditioner
+    from pyflow.solvers.pressure_solver import assemble_negative_laplacian
+    A = assemble_negative_laplacian(nx, ny, dx, dy)
+    assert recognise_ring5(A) is not None
+    rng = np.random.default_rng(nx * 131 + ny)
+    b = rng.standard_normal(nx * ny)
+    tol = 1e-10
+    M_dev = jacobi_preconditioner(A) if pc else None
+    got = solve(A, b, method=method, tol=tol, maxiter=maxiter, **({"M": M_dev} if pc else {}))
+    D = A.diagonal()
+    M_ref = spla.LinearOperator(A.shape, matvec=lambda v: v / D) if pc else None
+    x_ref, info = (spla.cg if method == "cg" else spla.bicgstab)(A, b, rtol=tol, maxiter=maxiter, M=M_ref)
+    rn = float(np.linalg.norm(b - A @ x_ref))
+    assert got.iterations == (info if info > 0 else 0)
+    assert got.converged == ((info == 0) and rn <= tol * np.linalg.norm(b))
+    err = float(np.linalg.norm(got.x - x_ref) / np.linalg.norm(x_ref))
+    assert err < (1e-9 if method == "cg" or info == 0 else 1e-7), (method, err, info)
+
+
+def test_solve_refuses_matrices_it_cannot_map_onto_the_device():
+    import scipy.sparse as sp
+    from pyflow.linear_solvers.interface import solve
+    from pyflow.solvers.pressure_solver import assemble_negative_laplacian
+    A = assemble_negative_laplacian(9, 7, 1.0, 1.0).tolil()
+    A[10, 11] = -0.75                                   # one interior row differs: not the reference's matrix any more
+    with pytest.raises(NotImplementedError):
+        solve(A.tocsr(), np.ones(63), method="cg")
+    with pytest.raises(NotImplementedError):
+        solve(sp.identity(63).tocsr(), np.ones(63), method="cg")
+
+
 def test_exact_restart_on_the_device_path(tmp_path):
     """SURVEY 8f item 3 (optional part): checkpoint after 5 steps, load, restore the saved dt-controller memory
     (``step_state``), run 4 more: the same dt sequence as the uninterrupted 9 steps (through the safeguard halving)
