@@ -478,21 +478,26 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cg_tma(CgArgs a) {
 
 
 // =====================================================================================
-// Dynamically scheduled variant (production for nx % 1024 == 0 on one GPU).
+// Dynamically scheduled variant: the production kernel for every grid at least 1024 columns wide, on one GPU and
+// (MULTI) on the row slabs of several.
 //
 // The globaltimer timeline of k_cg_tma (static: one 1024 x ~110-row tile per SM)
 // showed the first CTA finishing phase B after 62 us and the last after 106 us: SMs
 // do not get equal shares of the memory system (neighbouring SM ids are slow
 // together: GPC / TPC level sharing), so equal static tiles leave a third of the
-// chip idle at the end of every sweep.  Here tiles are 1024 columns x TD_ROWS rows
-// and every CTA DRAWS its next tile from an atomic ticket counter -- ascending in
-// phase A, descending in phase B (grid-wide LIFO: what A wrote last B reads first,
-// from L2).  The producer keeps the shared-memory ring full ACROSS tile boundaries
-// (it draws the next ticket and starts streaming its rows while the compute warps
-// still work on the current tile), so a small tile costs two extra row visits, not a
-// pipeline drain.  Partial sums are kept per tile (the last compute warp to finish a
-// tile adds the 16 warp partials in warp order) and folded in tile order: the result
-// does not depend on which SM processed which tile.
+// chip idle at the end of every sweep.  Here tiles are 1024 columns (the last column
+// chunk narrower when nx is not a multiple of 1024) x 12-16 rows; a CTA's FIRST tile
+// of a phase is static, the others are DRAWN from an atomic ticket counter --
+// ascending in phase A, descending in phase B (grid-wide LIFO: what A wrote last B
+// reads first, from L2).  The producer keeps the shared-memory ring full ACROSS tile
+// boundaries and across the phase barrier (tmad_prefetch), so a small tile costs two
+// extra row visits, not a pipeline drain.  Interior tiles run the lean row loops
+// (no per-row predicates, pinned shared addresses, ~85 instructions per row visit
+// instead of ~180).  Partial sums are kept per tile (the last compute warp to finish
+// a tile adds the 16 warp partials in warp order), folded per group of 64 tiles by
+// whichever warp completes the group (fence-free: LL-tagged words) and the <= 256
+// group partials in fixed order at the phase end (tile_exchange): the result does not
+// depend on which SM processed which tile.
 constexpr int TD_ROWS = 16;            // default rows per tile (CgArgs::tile_rows; larger for huge slabs)
 constexpr int TD_SLOTS = 4;            // tile descriptors in flight (ring depth 8 visits < 1 tile)
 
@@ -791,27 +796,6 @@ __device__ __forceinline__ void tmad_tile_partial(const CgArgs& a, DynShared* ds
       }
     }
   }
-}
-
-// Phase-end fold of the group partials (<= CG_MAX_GROUPS values per sum) by warp 0; every thread of the CTA gets
-// the totals.  Same fixed order in every CTA of every GPU.  Call with all threads of the CTA.
-template <int NV>
-__device__ __forceinline__ void tmad_fold_groups(const CgArgs& a, double (&out)[NV], double* sm) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ng = (a.ntiles + CG_TILE_GROUP - 1) / CG_TILE_GROUP;
-  __syncthreads();                                    // protect sm from a previous use
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      double t = 0.0;
-      for (int q = lane; q < ng; q += 32) t += ld_cg(a.part + PF_GPART_OFFSET + k * CG_MAX_GROUPS + q);
-      t = warp_sum(t);
-      if (lane == 0) sm[k] = t;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NV; ++k) out[k] = sm[k];
 }
 
 // ---- lean row loops ---------------------------------------------------------------------------------------
