@@ -61,6 +61,8 @@ WORKLOADS = {
     # widths that are not a multiple of the TMA kernel's 1024-column chunk (clipped last chunk)
     "cavity4000": dict(nx=4000, ny=4000, Re=1000.0, scaling="weak", per_gpu=True),
     "cavity5000x3000": dict(nx=5000, ny=3000, Re=1000.0, scaling="weak", per_gpu=True),
+    # the slab ONE GPU owns in the 8-GPU strong-scaling run of config 4 (tile-geometry experiments on one GPU)
+    "slab8192x1024": dict(nx=8192, ny=1024, Re=5000.0, scaling="weak", per_gpu=True),
 }
 CG_BYTES_PER_CELL_ITER = 64.0     # SURVEY.md 8d contract figure
 STEP_BYTES_PER_CELL = 200.0

@@ -538,11 +538,19 @@ inline void tmad_geometry(CgArgs& a, int G, int force_tile_rows = 0, int force_s
   int hb = force_tile_rows > 0 ? force_tile_rows : 16;
   if (force_tile_rows <= 0) {
     while ((long long)a.nchunks * ((nyl + hb - 1) / hb) > CG_MAX_TILES / 2) hb *= 2;
-    // keep >= ~8 tiles per CTA so that the dynamic schedule can balance (4096^2: 12-row tiles, 9 per CTA; short
-    // slabs of a strong-scaling run: down to 4 rows).  With the lean row loops a tile's two extra row visits are
-    // cheap enough that 12-row tiles beat 16-row ones at 4096^2 (profiles/r2_tile_rows_sweep_v3.txt).
-    const int cand[] = {12, 8, 6, 4};
-    for (int q = 0; q < 4 && hb <= 16 && (long long)a.nchunks * ((nyl + hb - 1) / hb) < 8LL * G; ++q) hb = cand[q];
+    // 16-row tiles when that gives every CTA >= 8 of them; else 12-row tiles while a CTA still gets >= 4 (4096^2: 9 per
+    // CTA; the 8192 x 1024 slab of the 8-GPU strong-scaling run: 4.6 per CTA); shorter tiles only for very short slabs.
+    // Measured (one GPU, profiles/r2_tile_rows_sweep_v3.txt, r2_short_slab_tile_rows.txt): with the lean row loops a
+    // tile's two extra row visits are cheap enough that 12 rows beat 16 at 4096^2, but on the short slab 6-row tiles
+    // (a third more row visits) lose 5 % against 12-row ones even though they balance better.
+    const int G8 = 8 * G, G4 = 4 * G, G2 = 2 * G;
+    auto tiles = [&](int h) { return (long long)a.nchunks * ((nyl + h - 1) / h); };
+    if (hb <= 16 && tiles(16) < G8) {
+      if (tiles(12) >= G4) hb = 12;
+      else if (tiles(8) >= G4) hb = 8;
+      else if (tiles(6) >= G2) hb = 6;
+      else hb = 4;
+    }
   }
   int hs = force_small_rows >= 0 ? force_small_rows : (hb >= 8 ? hb / 4 : 0);
   // small end bands are OFF by default: measured at 4096^2 they cost more (two extra row visits per tile) than the

@@ -29,7 +29,7 @@ def _check(name, cfg, steps, options=None):
     print(f"PARITY {name} options={options} rel_l2={r['rel_l2']} dt_equal={r['dt_equal']} iters={r['iters']} "
           f"oracle_iters={r['oracle_iters']} oracle_s={r['oracle_s']} {'OK' if r['ok'] else 'FAIL'}")
     assert r["dt_equal"], r
-    assert r["max_iter_diff"] <= parity.ITER_BAR, r
+    assert r["max_iter_diff"] <= r["iter_bar"], r
     assert r["max_rel_l2"] <= parity.REL_BAR, r
     return r
 
