@@ -905,9 +905,8 @@ def _tmad_solve(emu, dev, S, sync, b, dx, dy, invd, tol, maxiter, tile_rows):
     (33, 1024, 16, True, True, 2),         # the library's default 16-row tiles: 16 + 16 + 1 rows
     (3, 1024, 4, True, True, 300),         # runs to convergence at a loose tolerance
     (13, 1024, (4, 1, 2), True, True, 4),  # two 1-row tiles at each end, 4 + 4 + 1 rows between them (both sweeps end on short tiles)
-    (70, 2048, (16, 4, 3), False, True, 2),   # 2 chunks: 3 x 4-row bands, 16 + 16 + 14 rows, 3 x 4-row bands = 18 tiles < one fold group
-    (40, 4096, (4, 2, 4), True, True, 2),  # 4 chunks x (4 + 6 + 4) bands = 56 tiles ... and
-    (70, 4096, (4, 1, 3), True, True, 2),  # 4 chunks x (3 + 16 + 3) bands = 88 tiles: two fold groups (64 + 24)
+    (40, 2048, (16, 4, 2), False, True, 2),   # 2 chunks: 2 x 4-row bands, 16 + 8 rows, 2 x 4-row bands: lean interior tiles
+    (36, 4096, (2, 1, 2), True, True, 2),  # 4 chunks x (2 + 16 + 2) bands = 80 tiles: two fold groups (64 + 16)
     (9, 1100, 4, True, True, 3),           # clipped last chunk: 76 columns = one full strip + a strip cut at 12 columns, 14 idle warps
     (11, 1030, 4, False, True, 3),         # last chunk of 6 columns (one cut strip), non-unit spacing
     (22, 2049, 4, True, True, 2),          # ODD width: the last chunk is ONE column (copied together with the padding column)
