@@ -21,16 +21,15 @@ for what in "$@"; do
       ncu --set full --clock-control none --import-source on -k regex:k_cg_tmad -s 2 -c 1 \
           -o gpurun_out/cg_tmad_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline \
           > gpurun_out/cg_tmad_full.log 2>&1
-      ncu -i gpurun_out/cg_tmad_full.ncu-rep --page raw --csv | grep -E \
-          'dram__bytes_(read|write)\.sum|gpu__dram_throughput|gpu__time_duration|launch__registers_per_thread|smsp__issue_active|long_scoreboard' \
-          > gpurun_out/cg_tmad_full_summary.txt ;;
+      python profiles/ncu_summary.py gpurun_out/cg_tmad_full.ncu-rep > gpurun_out/cg_tmad_full_summary.txt
+      # DRAM bytes of the launch + kernel name + source hash -> profiles/cg_traffic.json (a copy travels back)
+      python profiles/record_traffic.py cavity4096 gpurun_out/cg_tmad_full.ncu-rep && cp profiles/cg_traffic.json gpurun_out/ ;;
     full512)      # the shared-memory-resident CG kernel (512^2): what bounds 5.6 us per iteration
       ncu --set full --clock-control none --import-source on -k regex:k_cg_small -s 2 -c 1 \
           -o gpurun_out/cg_small_full -f python bench.py --workload cavity512 --steps 1 --warmup 3 --no-cpu-baseline \
           > gpurun_out/cg_small_full.log 2>&1
-      ncu -i gpurun_out/cg_small_full.ncu-rep --page raw --csv | grep -E \
-          'dram__bytes_(read|write)\.sum|lts__t_bytes|gpu__time_duration|launch__registers_per_thread|smsp__issue_active|smsp__average_warp.*stall|l1tex__data_bank_conflicts' \
-          > gpurun_out/cg_small_full_summary.txt ;;
+      python profiles/ncu_summary.py gpurun_out/cg_small_full.ncu-rep > gpurun_out/cg_small_full_summary.txt
+      python profiles/record_traffic.py cavity512 gpurun_out/cg_small_full.ncu-rep && cp profiles/cg_traffic.json gpurun_out/ ;;
     sanitize)     # memcheck + racecheck + synccheck + initcheck of every CG kernel variant on small grids
       for tool in memcheck racecheck synccheck initcheck; do
         timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python tests/sanitize_cases.py \
@@ -50,6 +49,10 @@ for what in "$@"; do
       done ;;
     reference)    # the CPU arm on the box's host cores
       python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_arm.json ;;
-    *) echo "unknown target $what (tests newtests bench launches full4096 full512 sanitize scaling reference)"; exit 2 ;;
+    timeline)     # where the time of one k_cg_small iteration goes; the phase-end exchange across 2 GPUs
+      python profiles/experiments/small_kernel_timeline.py 512 | tee gpurun_out/small_kernel_timeline.txt
+      [ "$(nvidia-smi -L | wc -l)" -ge 2 ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29701 profiles/experiments/barrier_timeline_multigpu.py 4096 4096 2>&1 | grep -E "rank|barrier" | tee gpurun_out/barrier_timeline_2gpu.txt ;;
+    *) echo "unknown target $what (tests newtests bench launches full4096 full512 sanitize scaling reference timeline)"; exit 2 ;;
   esac
 done
