@@ -55,12 +55,17 @@ WORKLOADS = {
     # name: nx, ny (per GPU or total), Re, scaling
     "cavity4096": dict(nx=4096, ny=4096, Re=1000.0, scaling="weak", per_gpu=True),
     "cavity512": dict(nx=512, ny=512, Re=1000.0, scaling="weak", per_gpu=True),
+    # config 1, the reference's own CPU-runnable default (`pyflow run`): the one the UNMODIFIED reference is timed on
+    "cavity64": dict(nx=64, ny=64, Re=100.0, scaling="weak", per_gpu=True),
     "strong8192": dict(nx=8192, ny=8192, Re=5000.0, scaling="strong", per_gpu=False),
     "weak16384": dict(nx=16384, ny=16384, Re=1000.0, scaling="weak", per_gpu=True),
     "weak16384_tight": dict(nx=16384, ny=16384, Re=1000.0, scaling="weak", per_gpu=True, lin_maxiter=10000),
     # widths that are not a multiple of the TMA kernel's 1024-column chunk (clipped last chunk)
     "cavity4000": dict(nx=4000, ny=4000, Re=1000.0, scaling="weak", per_gpu=True),
     "cavity5000x3000": dict(nx=5000, ny=3000, Re=1000.0, scaling="weak", per_gpu=True),
+    # general grid spacing (lx = ly = 1: dx = dy = 1/4095, the <false, ...> instantiations with the reference's IEEE
+    # divides; no BASELINE config uses it, the reference's config model and CLI have no lx / ly: VERDICT r1 item 13)
+    "cavity4096_lx1": dict(nx=4096, ny=4096, Re=1000.0, scaling="weak", per_gpu=True, lx=1.0, ly=1.0),
     # the slab ONE GPU owns in the 8-GPU strong-scaling run of config 4 (tile-geometry experiments on one GPU)
     "slab8192x1024": dict(nx=8192, ny=1024, Re=5000.0, scaling="weak", per_gpu=True),
 }
@@ -68,10 +73,13 @@ CG_BYTES_PER_CELL_ITER = 64.0     # SURVEY.md 8d contract figure
 STEP_BYTES_PER_CELL = 200.0
 
 
-def make_cfg(nx, ny, Re, lin_maxiter=300, lin_tol=1e-10):
-    return SimpleNamespace(nx=nx, ny=ny, Re=Re, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05,
-                           lin_tol=lin_tol, lin_maxiter=lin_maxiter, advection_scheme="quick",
-                           disable_advection=False, diagnostics=False)
+def make_cfg(nx, ny, Re, lin_maxiter=300, lin_tol=1e-10, lx=None, ly=None):
+    cfg = SimpleNamespace(nx=nx, ny=ny, Re=Re, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05,
+                          lin_tol=lin_tol, lin_maxiter=lin_maxiter, advection_scheme="quick",
+                          disable_advection=False, diagnostics=False)
+    if lx is not None:          # absent attributes = the reference's default lx = nx - 1, ly = ny - 1 (solver.py:19-22)
+        cfg.lx, cfg.ly = float(lx), float(ly if ly is not None else lx)
+    return cfg
 
 
 def lin_maxiter_of(args, wl):
@@ -222,6 +230,33 @@ def sized_oracle_rows(nx: int, ny_max: int, Re: float, lin_maxiter: int, total_s
     return rows
 
 
+def unmodified_reference_sample(cases=((64, 64, 100.0, 49), (512, 512, 1000.0, 1)), timeout_s=240.0):
+    """The UNMODIFIED reference -- CPython bytecode of /root/reference/src/pyflow compiled by oracle/build_ref.py
+    into oracle/_ref, nothing of this repo on its path -- driven through its own SimulationDriver.run on this box's
+    host cores (BASELINE configs 1 and 2; SURVEY 8d: "time the unmodified reference through SimulationDriver.run").
+    A subprocess per case: the reference package and the drop-in package are both called `pyflow`."""
+    script = os.path.join(ROOT, "oracle", "time_unmodified.py")
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "stamp.json")):
+        return {"unavailable": "oracle/_ref not built (python oracle/build_ref.py needs /root/reference)"}
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    env["OMP_NUM_THREADS"] = env["OPENBLAS_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun exports 1
+    out = {"what": "unmodified reference (bytecode in oracle/_ref), SimulationDriver.run from rest, step 0 untimed; "
+                   "single-threaded Python / numpy / scipy, BLAS dots on all host threads", "cases": {}}
+    for nx, ny, Re, steps in cases:
+        key = f"{nx}x{ny} Re={Re:g}"
+        try:
+            r = subprocess.run([sys.executable, script, str(nx), str(ny), str(Re), str(steps)], env=env, cwd="/tmp",
+                               capture_output=True, text=True, timeout=timeout_s)
+            if r.returncode != 0:
+                out["cases"][key] = {"error": (r.stderr or r.stdout).strip().splitlines()[-1:]}
+            else:
+                out["cases"][key] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as exc:
+            out["cases"][key] = {"error": repr(exc)}
+    return out
+
+
 def run_reference_arm(args, wl, rank):
     """`--impl reference`: the reference's CPU algorithm for the path on this box's host cores.  The reference
     itself is Python and cannot travel to the box; its restatement oracle/pyflow_oracle.c (pinned through the
@@ -253,7 +288,9 @@ def run_reference_arm(args, wl, rank):
         "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args.workload, wl, args.gpus, maxit),
         "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample,
-                         "sample_grid": {"nx": nx, "ny": rows}},
+                         "sample_grid": {"nx": nx, "ny": rows},
+                         "unmodified_reference": unmodified_reference_sample(
+                             cases=((64, 64, 100.0, int(getattr(args, "unmodified_steps", 49))),))},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -348,7 +385,8 @@ def run_gpu_arm(args, wl, rank, world):
     nx = wl["nx"]
     ny_global = wl["ny"] * world if wl["per_gpu"] else wl["ny"]
     maxit = lin_maxiter_of(args, wl)
-    cfg = make_cfg(nx, ny_global, wl["Re"], maxit)
+    cfg = make_cfg(nx, ny_global, wl["Re"], maxit, lx=wl.get("lx"),
+                   ly=(wl["ly"] * (world if wl["per_gpu"] else 1)) if wl.get("ly") else None)
     state = new_state(nx, ny_global)
     tracker = ResidualManager()
     warm = max(3, args.warmup)
@@ -451,7 +489,8 @@ def run_gpu_arm(args, wl, rank, world):
     other = None
     if not getattr(args, 'no_extra', False) and args.workload == "cavity4096":
         other = {}
-        extra = [("cavity512", 3, 50), ("cavity4000", 2, 6), ("cavity5000x3000", 2, 6)] if world == 1 else []
+        extra = ([("cavity64", 3, 49), ("cavity512", 3, 50), ("cavity4000", 2, 6), ("cavity5000x3000", 2, 6),
+                  ("cavity4096_lx1", 2, 4)] if world == 1 else [])
         extra += [("strong8192", 2, 4), ("weak16384", 2, 2), ("weak16384_tight", 1, 1)]
         for name, w2, n2 in extra:
             wl2 = WORKLOADS[name]
@@ -459,7 +498,8 @@ def run_gpu_arm(args, wl, rank, world):
             if ny2 % world or ny2 // world < 2:
                 continue
             try:
-                cfg2 = make_cfg(wl2["nx"], ny2, wl2["Re"], wl2.get("lin_maxiter", 300))
+                cfg2 = make_cfg(wl2["nx"], ny2, wl2["Re"], wl2.get("lin_maxiter", 300), lx=wl2.get("lx"),
+                                ly=(wl2["ly"] * (world if wl2["per_gpu"] else 1)) if wl2.get("ly") else None)
                 st2, tr2 = new_state(wl2["nx"], ny2), ResidualManager()
                 _it, ms2, cg2, its2, _sm = timed_steps(cfg2, st2, tr2, 0, w2, n2)
                 ach2, _b, cgs2 = cg_roofline(wl2["nx"], ny2 // world, cg2, its2)
@@ -468,7 +508,8 @@ def run_gpu_arm(args, wl, rank, world):
                     "scaling": wl2["scaling"], "steps": n2, "warmup": w2, "ms_per_step": ms2 / n2,
                     "MLUPS": wl2["nx"] * ny2 * n2 / (ms2 * 1e-3) / 1e6,
                     "cg_iters_per_step": statistics.mean(its2), "cg_iters_per_s": sum(its2) / cgs2 if cgs2 > 0 else None,
-                    "cg_kernel": cg_kernel_name(wl2["nx"], ny2 // world, world).split(" ")[0],
+                    "cg_kernel": cg_kernel_name(wl2["nx"], ny2 // world, world).split(" ")[0].replace(
+                        "<unit>", "<general spacing>" if wl2.get("lx") else "<unit>"),
                     "cg_hbm_gbs_algorithmic_per_gpu": ach2, "cg_frac_of_measured_peak_per_gpu": ach2 / peak,
                     "peer_kernel": bool(getattr(st2.fields._slab, "peer_mode", False))}
                 st2.fields._slab.close()
@@ -508,7 +549,10 @@ def run_gpu_arm(args, wl, rank, world):
                "sample_grid": {"nx": nx, "ny": rows},
                "numpy_port_mlups": np_mlups,
                "numpy_port_sample": f"1 step of a {npn}x{npn} cavity with the single-threaded numpy "
-                                    "oracle (the unmodified reference is slower still: Python loops for advection)"}
+                                    "oracle (the unmodified reference is slower still: Python loops for advection)",
+               # BASELINE configs 1 and 2 with the reference itself; the GPU figures for the same two configurations
+               # are other_configs.cavity64 / other_configs.cavity512 of this line
+               "unmodified_reference": unmodified_reference_sample()}
     line = {
         "metric": "MLUPS per projection step", "value": value, "unit": "MLUPS", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": elapsed_ms / args.steps,

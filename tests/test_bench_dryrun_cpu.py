@@ -68,7 +68,7 @@ def test_reference_arm_prints_on_rank_zero_only(rank, capsys):
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     args = SimpleNamespace(gpus=2, steps=1, warmup=1, impl="reference", workload="cavity4096", no_cpu_baseline=False,
-                           ref_grid=32)
+                           ref_grid=32, unmodified_steps=2)
     bench.run_reference_arm(args, bench.WORKLOADS["cavity4096"], rank)
     out = capsys.readouterr().out.strip()
     if rank:
@@ -80,6 +80,12 @@ def test_reference_arm_prints_on_rank_zero_only(rank, capsys):
         assert line["cpu_baseline"]["sample_grid"] == {"nx": 32, "ny": 32} and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
         # same `config` object as the GPU arm prints for this workload and GPU count
         assert line["config"] == bench.workload_config("cavity4096", bench.WORKLOADS["cavity4096"], 2, 300)
+        unmod = line["cpu_baseline"]["unmodified_reference"]
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "stamp.json")):
+            case = unmod["cases"]["64x64 Re=100"]
+            assert case["steps_timed"] == 2 and case["MLUPS"] > 0 and "error" not in case
+        else:
+            assert "unavailable" in unmod
 
 
 def test_reference_arm_uses_every_host_core_even_under_torchrun(monkeypatch):
@@ -99,3 +105,31 @@ def test_reference_sample_keeps_the_row_length_and_fits_the_budget():
     spec.loader.exec_module(bench)
     assert bench.sized_oracle_rows(256, 1024, 100.0, 20, 3, 1e9) == 1024          # fits: the whole slab
     assert bench.sized_oracle_rows(256, 1024, 100.0, 20, 3, 0.0) == 256           # never below 256 rows
+
+
+def test_unmodified_reference_bytecode_agrees_with_the_oracle():
+    """oracle/_ref (CPython bytecode of the unmodified reference, oracle/build_ref.py) stepped through its own
+    SimulationDriver.run in a subprocess ends on the fields the numpy oracle ends on -- the pin of the oracle
+    (oracle/make_golden.py) re-checked on whatever machine runs this suite, the GPU box included."""
+    import subprocess
+    import sys
+
+    import numpy as np
+    import build_ref
+    import pyflow_oracle as orc
+    if build_ref.build() is None:
+        pytest.skip("no /root/reference and no prebuilt oracle/_ref")
+    assert not [f for _d, _s, fs in os.walk(os.path.join(ROOT, "oracle", "_ref")) for f in fs if f.endswith(".py")], \
+        "oracle/_ref must hold bytecode only, never reference sources"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_unmodified.py"), "40", "24", "100", "5"],
+                       capture_output=True, text=True, cwd="/tmp", timeout=120,
+                       env={k: v for k, v in os.environ.items() if k != "PYTHONPATH"})
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    cfg = SimpleNamespace(nx=40, ny=24, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
+                          lin_maxiter=300, advection_scheme="quick", disable_advection=False, diagnostics=False)
+    st, diags = orc.run(cfg, 6)
+    assert got["final"]["dt"] == diags[-1]["dt"]
+    for name in ("u", "v", "p"):
+        want = float(np.linalg.norm(orc.interior(st.fields[name])))
+        assert abs(got["final"][f"{name}_norm"] - want) <= 1e-12 * max(1.0, want), (name, got["final"], want)
