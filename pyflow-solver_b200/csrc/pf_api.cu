@@ -15,6 +15,7 @@
 #include "pf_cg_tma.cuh"
 #include "pf_comm.h"
 #include "pf_kernels.cuh"
+#include "pf_step_fused.cuh"
 
 using namespace pf;
 
@@ -45,6 +46,9 @@ struct pf_ctx {
   long long launches = 0;          // kernels of this library launched so far
   bool center_valid = false;       // h_center holds u[:, nx/2] of the current device u
   dim3 sgrid;                      // grid of the simple kernels
+  dim3 fgrid;                      // grid of the two fused per-step passes (pf_step_fused.cuh); x = 0: not usable
+  int fthreads = 0;                //   threads per block
+  int fband = 0;                   //   rows per band
   pf::Comm* comm = nullptr;        // multi-GPU slabs (null when nranks == 1)
   char* ws_base = nullptr;         // device workspace (field k lives at k * field_stride)
   size_t field_stride = 0;
@@ -57,6 +61,7 @@ struct pf_ctx {
   int opt_tile_rows = 0;           // TMA kernel: force the big-tile height (0: automatic)
   int opt_small_rows = -1;         // TMA kernel: force the small-tile height (-1: automatic, 0: uniform tiles)
   int opt_nb_small = -1;           // TMA kernel: force the number of small bands at each end (-1: automatic)
+  int opt_step_fused = 1;          // 1: one GPU steps with the two fused passes k_front / k_finish; 0: the seven separate kernels
   int opt_kernel = 3;              // 3: auto = shared-memory-resident kernel for small grids, TMA-fed dynamically scheduled
                                    //    kernel when nx % 1024 == 0, else the register-window kernels; 2: static TMA tiles;
                                    //    1: register-window only
@@ -120,6 +125,14 @@ dim3 simple_grid(const Slab& s) {
   int gy = std::max(1, 2368 / gx);
   gy = std::min(gy, s.nyl);
   return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+// Grid of the fused per-step passes (pf_step_fused.cuh).
+void fused_geometry(pf_ctx* c) {
+  const FusedGeometry g = pf::fused_geometry(c->s.nx, c->s.nyl, c->sm_count);
+  c->fgrid = dim3((unsigned)g.gx, (unsigned)(g.gy > 0 ? g.gy : 1), 1);      // gx = 0: not usable
+  c->fthreads = g.threads;
+  c->fband = g.rows;
 }
 
 bool is_unit(double dx, double dy) { return dx == 1.0 && dy == 1.0; }
@@ -214,7 +227,7 @@ int launch_cg(pf_ctx* c, CgArgs& a, cudaStream_t st) {
 // rhs already in c->b (raw); finishes it, solves, leaves x in c->x and the true
 // residual in S_RES_SUMSQ.
 int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_interior, double tol, int maxiter,
-                    int subtract_mean, int pin, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+                    int subtract_mean, int pin, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool with_resid = true) {
   const Slab& s = c->s;
   const Red red{c->red_part, c->red_counter, c->scal};
   const double invd = jacobi ? invd_interior : 1.0;
@@ -334,6 +347,7 @@ int solve_on_device(pf_ctx* c, double dx, double dy, int jacobi, double invd_int
     else PF_TRY(launch_cg<false>(c, a, st));
   }
   if (e1) PF_CUDA(c, cudaEventRecord(e1, st));
+  if (!with_resid) return PF_OK;          // the caller's next pass forms ||b - A x|| itself (k_finish)
   if (c->comm) PF_TRY(comm_halo(c->comm, c->x, 1, 1, st, c->err));
   if (unit) k_resid<true><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
   else k_resid<false><<<c->sgrid, KT, 0, st>>>(s, c->b, c->x, dx, dy, red);
@@ -363,6 +377,28 @@ int d2h_field(pf_ctx* c, double* dst, const double* src, int64_t stride, cudaStr
   PF_CUDA(c, cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)stride, src + cell(c->s, 0, 0),
                                sizeof(double) * (size_t)c->s.pitch, sizeof(double) * (size_t)c->s.nx, (size_t)c->s.nyl,
                                cudaMemcpyDeviceToHost, st));
+  return PF_OK;
+}
+
+// predictor + rhs pass 1 in one pass: (u, v) -> (uo, vo) buffers = u*, v*; b
+template <bool UNIT>
+int launch_front(pf_ctx* c, int scheme, double dt, double dt_safe, double dx, double dy, cudaStream_t st) {
+  const Slab& s = c->s;
+  const Red red{c->red_part, c->red_counter, c->scal};
+  switch (scheme) {
+    case PF_ADV_UPWIND:
+      k_front<UNIT, PF_ADV_UPWIND><<<c->fgrid, c->fthreads, 0, st>>>(s, c->u, c->v, c->uo, c->vo, c->b, dt, dt_safe, dx, dy, c->fband, red);
+      break;
+    case PF_ADV_QUICK:
+      k_front<UNIT, PF_ADV_QUICK><<<c->fgrid, c->fthreads, 0, st>>>(s, c->u, c->v, c->uo, c->vo, c->b, dt, dt_safe, dx, dy, c->fband, red);
+      break;
+    case PF_ADV_NONE:
+      k_front<UNIT, PF_ADV_NONE><<<c->fgrid, c->fthreads, 0, st>>>(s, c->u, c->v, c->uo, c->vo, c->b, dt, dt_safe, dx, dy, c->fband, red);
+      break;
+    default:
+      return fail(c, PF_ERR_ARG, "pf_step", "unknown advection scheme");
+  }
+  PF_LAUNCHED(c);
   return PF_OK;
 }
 
@@ -455,6 +491,7 @@ int pf_create(pf_ctx** out, int64_t nx, int64_t ny_local, int64_t ny_global, int
   c->small_part = (double*)(small + L.small_part);
   c->sync_off = (size_t)NFIELDS * fb + L.sync;
   c->sgrid = simple_grid(c->s);
+  fused_geometry(c);
 #define PF_CREATE_CUDA(call)                                  \
   do {                                                        \
     cudaError_t e__ = (call);                                 \
@@ -544,6 +581,7 @@ int pf_set_option(pf_ctx* c, const char* key, int value) {
   if (strcmp(key, "cg_multi_single") == 0) { c->opt_multi_single = value; return PF_OK; }
   if (strcmp(key, "cg_sync_opt") == 0) { c->opt_sync = value; return PF_OK; }
   if (strcmp(key, "cg_kernel") == 0) { c->opt_kernel = value; return PF_OK; }
+  if (strcmp(key, "step_fused") == 0) { c->opt_step_fused = value ? 1 : 0; return PF_OK; }
   if (strcmp(key, "cg_rows_min") == 0 && value >= 1) { c->opt_rows_min = value; return PF_OK; }
   if (strcmp(key, "cg_tile_rows") == 0 && value >= 0) { c->opt_tile_rows = value; return PF_OK; }
   if (strcmp(key, "cg_small_rows") == 0 && value >= -1) { c->opt_small_rows = value; return PF_OK; }
@@ -613,43 +651,73 @@ int pf_step(pf_ctx* c, const pf_step_params* P, pf_step_out* out, void* stream) 
   const double dt_safe = (1e-14 > dt) ? 1e-14 : dt;      // Python max(dt, 1e-14) incl. NaN behaviour
   PF_CUDA(c, cudaEventRecord(c->ev[0], st));
 
-  if (!P->projection_only) {
-    // predictor: (u, v) -> (uo, vo) buffers, then swap so that u/v hold u*, v*
-    // and uo/vo keep the previous step's fields for the residuals.
-    if (c->comm) {
-      PF_TRY(comm_halo(c->comm, c->u, 2, 2, st, c->err));
-      PF_TRY(comm_halo(c->comm, c->v, 2, 2, st, c->err));
-    }
-    if (unit) PF_TRY(launch_predict<true>(c, P->scheme, dt, dx, dy, st));
-    else PF_TRY(launch_predict<false>(c, P->scheme, dt, dx, dy, st));
-    std::swap(c->u, c->uo);
-    std::swap(c->v, c->vo);
-  }
-  // rhs pass 1
-  if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 0, st, c->err));
-  if (unit) k_rhs1<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
-  else k_rhs1<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
-  PF_LAUNCHED(c);
-  if (c->comm) PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVB_SUMSQ, 1, 0, st, c->err));
-  // rhs pass 2 + CG + true residual
-  PF_TRY(solve_on_device(c, dx, dy, P->jacobi, P->inv_diag_interior, P->lin_tol, P->lin_maxiter, 1, 1, st, c->ev[1],
-                         c->ev[2]));
-  // correction
-  if (unit) k_correct<true><<<c->sgrid, KT, 0, st>>>(s, c->x, c->x, c->u, c->v, dt, dx, dy, c->scal);
-  else k_correct<false><<<c->sgrid, KT, 0, st>>>(s, c->x, c->x, c->u, c->v, dt, dx, dy, c->scal);
-  PF_LAUNCHED(c);
-  if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 0, st, c->err));
-  if (unit) k_divnorm<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, red, S_DIVA_SUMSQ);
-  else k_divnorm<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, red, S_DIVA_SUMSQ);
-  PF_LAUNCHED(c);
-  if (!P->projection_only) {
-    if (P->lid_set) {
-      k_lid<<<(s.nx + KT - 1) / KT, KT, 0, st>>>(s, c->u, P->lid_velocity);
+  const bool fused = c->opt_step_fused && !c->comm && c->fgrid.x > 0;
+  if (fused) {
+    // one GPU: two passes around the solve (pf_step_fused.cuh); u, v ping-pong between the two buffer pairs
+    if (!P->projection_only) {
+      if (unit) PF_TRY(launch_front<true>(c, P->scheme, dt, dt_safe, dx, dy, st));
+      else PF_TRY(launch_front<false>(c, P->scheme, dt, dt_safe, dx, dy, st));
+      std::swap(c->u, c->uo);
+      std::swap(c->v, c->vo);
+    } else {
+      if (unit) k_rhs1<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
+      else k_rhs1<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
       PF_LAUNCHED(c);
     }
-    if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 1, st, c->err));
-    k_post<<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->uo, c->vo, c->x, c->center, red);
+    PF_TRY(solve_on_device(c, dx, dy, P->jacobi, P->inv_diag_interior, P->lin_tol, P->lin_maxiter, 1, 1, st, c->ev[1],
+                           c->ev[2], /*with_resid=*/false));
+    // residual + correction + divergence + lid row + post pass: (u*, v*) in c->u / c->v, the previous step's fields
+    // in c->uo / c->vo, which receive the new fields
+    const int lid_set = P->lid_set ? 1 : 0;
+    if (P->projection_only) {
+      if (unit) k_finish<true, false><<<c->fgrid, c->fthreads, 0, st>>>(s, c->b, c->x, c->u, c->v, c->uo, c->vo, dt, dx, dy, 0, 0.0, c->center, c->fband, red);
+      else k_finish<false, false><<<c->fgrid, c->fthreads, 0, st>>>(s, c->b, c->x, c->u, c->v, c->uo, c->vo, dt, dx, dy, 0, 0.0, c->center, c->fband, red);
+    } else {
+      if (unit) k_finish<true, true><<<c->fgrid, c->fthreads, 0, st>>>(s, c->b, c->x, c->u, c->v, c->uo, c->vo, dt, dx, dy, lid_set, P->lid_velocity, c->center, c->fband, red);
+      else k_finish<false, true><<<c->fgrid, c->fthreads, 0, st>>>(s, c->b, c->x, c->u, c->v, c->uo, c->vo, dt, dx, dy, lid_set, P->lid_velocity, c->center, c->fband, red);
+    }
     PF_LAUNCHED(c);
+    std::swap(c->u, c->uo);
+    std::swap(c->v, c->vo);
+  } else {
+    if (!P->projection_only) {
+      // predictor: (u, v) -> (uo, vo) buffers, then swap so that u/v hold u*, v*
+      // and uo/vo keep the previous step's fields for the residuals.
+      if (c->comm) {
+        PF_TRY(comm_halo(c->comm, c->u, 2, 2, st, c->err));
+        PF_TRY(comm_halo(c->comm, c->v, 2, 2, st, c->err));
+      }
+      if (unit) PF_TRY(launch_predict<true>(c, P->scheme, dt, dx, dy, st));
+      else PF_TRY(launch_predict<false>(c, P->scheme, dt, dx, dy, st));
+      std::swap(c->u, c->uo);
+      std::swap(c->v, c->vo);
+    }
+    // rhs pass 1
+    if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 0, st, c->err));
+    if (unit) k_rhs1<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
+    else k_rhs1<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->b, dt_safe, dx, dy, red);
+    PF_LAUNCHED(c);
+    if (c->comm) PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_DIVB_SUMSQ, 1, 0, st, c->err));
+    // rhs pass 2 + CG + true residual
+    PF_TRY(solve_on_device(c, dx, dy, P->jacobi, P->inv_diag_interior, P->lin_tol, P->lin_maxiter, 1, 1, st, c->ev[1],
+                           c->ev[2]));
+    // correction
+    if (unit) k_correct<true><<<c->sgrid, KT, 0, st>>>(s, c->x, c->x, c->u, c->v, dt, dx, dy, c->scal);
+    else k_correct<false><<<c->sgrid, KT, 0, st>>>(s, c->x, c->x, c->u, c->v, dt, dx, dy, c->scal);
+    PF_LAUNCHED(c);
+    if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 0, st, c->err));
+    if (unit) k_divnorm<true><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, red, S_DIVA_SUMSQ);
+    else k_divnorm<false><<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, dx, dy, red, S_DIVA_SUMSQ);
+    PF_LAUNCHED(c);
+    if (!P->projection_only) {
+      if (P->lid_set) {
+        k_lid<<<(s.nx + KT - 1) / KT, KT, 0, st>>>(s, c->u, P->lid_velocity);
+        PF_LAUNCHED(c);
+      }
+      if (c->comm) PF_TRY(comm_halo(c->comm, c->v, 1, 1, st, c->err));
+      k_post<<<c->sgrid, KT, 0, st>>>(s, c->u, c->v, c->uo, c->vo, c->x, c->center, red);
+      PF_LAUNCHED(c);
+    }
   }
   if (c->comm) {
     PF_TRY(comm_allreduce_scalars(c->comm, c->scal + S_UMAX, 2, 1, st, c->err));

@@ -14,7 +14,7 @@ namespace pf {
 
 constexpr int KT = 256;          // threads per block of the simple kernels
 constexpr int MAX_RED_BLOCKS = 4096;
-constexpr int MAX_RED_VALS = 8;
+constexpr int MAX_RED_VALS = 10;
 
 // Reduction scratch shared by the simple kernels (one launch at a time).
 struct Red {

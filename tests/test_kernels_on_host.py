@@ -284,6 +284,9 @@ def emu(tmp_path_factory):
     lib.emu_divnorm.argtypes = [i, i, dp, dp, d, d, dp, dp]
     lib.emu_post.argtypes = [i, i, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.emu_divc_stats.argtypes = [i, i, dp, dp, d, d, i, dp, dp]
+    lib.emu_fused_geometry.argtypes = [i, i, i, C.POINTER(C.c_int)]
+    lib.emu_front.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
+    lib.emu_finish.argtypes = [i, i, i, dp, dp, dp, dp, dp, dp, d, d, d, i, d, dp, i, dp, dp]
     lib.emu_cg_generic.argtypes = [i, i, i, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
     lib.emu_cg_persistent.argtypes = [i, i, dp, dp, dp, dp, dp, d, d, d, d, i, i, dp, dp]
     lib.emu_krylov.argtypes = [i, i, i, dp, dp, dp, dp, dp, dp, dp, d, d, d, d, i, dp, dp]
@@ -643,12 +646,14 @@ def test_plain_cg_kernel_dirichlet_mode_vs_oracle(emu):
     assert np.linalg.norm(x - po) <= 1e-9 * np.linalg.norm(po)
 
 
+@pytest.mark.parametrize("chain", ["separate", "fused"])
 @pytest.mark.parametrize("scheme_name,nx,ny,spacing,solver", [("quick", 8, 6, None, "generic"),
                                                               ("upwind", 7, 5, (2.0, 1.0), "register-window")])
-def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_name, nx, ny, spacing, solver):
+def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_name, nx, ny, spacing, solver, chain):
     """The kernels chained in the order of pf_step (pf_api.cu) -- the solve by the plain CG kernel or by the
     register-window kernel the library itself picks for an odd width --, host dt logic from the oracle: three steps
-    of a driven cavity against the oracle."""
+    of a driven cavity against the oracle.  chain "separate": the seven per-step kernels of pf_kernels.cuh (several
+    GPUs, tiny grids); "fused": the two passes of pf_step_fused.cuh one GPU steps with."""
     from types import SimpleNamespace
     cfg = SimpleNamespace(nx=nx, ny=ny, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05, lin_tol=1e-10,
                           lin_maxiter=3000, advection_scheme=scheme_name, disable_advection=False, diagnostics=False)
@@ -665,9 +670,14 @@ def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_na
         _, ores, od = orc.step(cfg, ost, it)
         dt, dx, dy = od["dt"], ost.meta["dx"], ost.meta["dy"]
         invd = 1.0 / (2.0 / dx ** 2 + 2.0 / dy ** 2)
-        emu.emu_predict(scheme, nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), dt, dx, dy)
-        u, uo, v, vo = uo, u, vo, v                                   # u, v hold u*, v*; uo, vo the previous step
-        emu.emu_rhs1(nx, ny, ptr(u), ptr(v), ptr(b), max(dt, 1e-14), dx, dy, ptr(S.scratch), ptr(S.scal))
+        if chain == "fused":
+            assert emu.emu_front(scheme, nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), ptr(b), dt, max(dt, 1e-14), dx, dy,
+                                 148, ptr(S.scratch), ptr(S.scal))
+            u, uo, v, vo = uo, u, vo, v
+        else:
+            emu.emu_predict(scheme, nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), dt, dx, dy)
+            u, uo, v, vo = uo, u, vo, v                               # u, v hold u*, v*; uo, vo the previous step
+            emu.emu_rhs1(nx, ny, ptr(u), ptr(v), ptr(b), max(dt, 1e-14), dx, dy, ptr(S.scratch), ptr(S.scal))
         emu.emu_rhs2(nx, ny, ptr(b), ptr(x), ptr(r), 1, 1, invd, ptr(S.scratch), ptr(S.scal))
         if solver == "generic":
             emu.emu_cg_generic(0, nx, ny, ptr(b), ptr(x), ptr(r), ptr(p), ptr(q), dx, dy, invd, 1e-10, 3000, ptr(part),
@@ -676,18 +686,129 @@ def test_whole_projection_steps_from_the_cuda_sources_on_the_host(emu, scheme_na
             emu.emu_cg_persistent(nx, ny, ptr(b), ptr(x), ptr(r), ptr(p), ptr(q), dx, dy, invd, 1e-10, 3000, 4,
                                   ptr(part), ptr(S.scal))
         assert abs(int(S["S_ITERS"]) - od["true_iterations"]) <= 1
-        emu.emu_resid(nx, ny, ptr(b), ptr(x), dx, dy, ptr(S.scratch), ptr(S.scal))
-        emu.emu_correct(nx, ny, ptr(x), ptr(u), ptr(v), dt, dx, dy, S["S_X0"])
-        emu.emu_divnorm(nx, ny, ptr(u), ptr(v), dx, dy, ptr(S.scratch), ptr(S.scal))
-        assert close(S["S_DIVA_SUMSQ"] ** 0.5, od["divergence_norm"], 1e-6)
-        emu.emu_lid(nx, ny, ptr(u), 1.0)
-        emu.emu_post(nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), ptr(x), ptr(center), ptr(S.scratch), ptr(S.scal))
+        if chain == "fused":
+            assert emu.emu_finish(1, nx, ny, ptr(b), ptr(x), ptr(u), ptr(v), ptr(uo), ptr(vo), dt, dx, dy, 1, 1.0,
+                                  ptr(center), 148, ptr(S.scratch), ptr(S.scal))
+            u, uo, v, vo = uo, u, vo, v                               # the new fields landed in the other buffer pair
+            assert close(S["S_DIVA_SUMSQ"] ** 0.5, od["divergence_norm"], 1e-6)
+            # a converged solve stops at the noise level of its own summation order: same magnitude, not same digits
+            assert 0.3 * od["Rp_residual"] <= S["S_RES_SUMSQ"] ** 0.5 <= 3.0 * od["Rp_residual"] + 1e-300
+        else:
+            emu.emu_resid(nx, ny, ptr(b), ptr(x), dx, dy, ptr(S.scratch), ptr(S.scal))
+            emu.emu_correct(nx, ny, ptr(x), ptr(u), ptr(v), dt, dx, dy, S["S_X0"])
+            emu.emu_divnorm(nx, ny, ptr(u), ptr(v), dx, dy, ptr(S.scratch), ptr(S.scal))
+            assert close(S["S_DIVA_SUMSQ"] ** 0.5, od["divergence_norm"], 1e-6)
+            emu.emu_lid(nx, ny, ptr(u), 1.0)
+            emu.emu_post(nx, ny, ptr(u), ptr(v), ptr(uo), ptr(vo), ptr(x), ptr(center), ptr(S.scratch), ptr(S.scal))
         assert close(S["S_RU_SUMSQ"] ** 0.5 / (nx * ny), ores["Ru"], 1e-8) and S["S_NONFINITE"] == 0.0
         assert close(S["S_DIVC_SUMSQ"] ** 0.5 / (nx * ny), ores["continuity"], 1e-8)
     for name, buf in (("u", u), ("v", v), ("p", x)):
         a, want = dev.get(buf), orc.interior(ost.fields[name])
         assert np.linalg.norm(a - want) <= 1e-9 * (np.linalg.norm(want) or 1.0), name
     assert same(center, dev.get(u)[:, nx // 2])
+
+
+# ===================================================================================================================
+# the two fused per-step passes (pf_step_fused.cuh) against the seven separate kernels they replace on one GPU
+# ===================================================================================================================
+# shape (ny, nx), unit spacing?, SMs the launch geometry is computed for (fewer SMs: taller bands).  Widths chosen around
+# the 60 columns a warp owns (one warp, warp boundaries, odd widths, a second column block) and bands of 2 .. ny rows.
+FUSED_CASES = [((9, 13), True, 148), ((14, 300), False, 148), ((11, 513), True, 148), ((7, 61), True, 2),
+               ((12, 121), False, 3), ((13, 500), True, 148), ((6, 4), True, 148), ((4, 5), False, 1),
+               ((5, 60), True, 1), ((17, 59), False, 148), ((6, 962), True, 148)]
+
+
+@pytest.mark.parametrize("shape,unit,sms", FUSED_CASES)
+def test_fused_front_pass_equals_predictor_plus_rhs_pass_1(emu, shape, unit, sms):
+    ny, nx = shape
+    rng = np.random.default_rng(ny * 131 + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.37, 1.9)
+    dt = 0.0123
+    u, v = rng.standard_normal(shape), rng.standard_normal(shape)
+    u[rng.random(shape) < 0.1] = 0.0                       # QUICK's >= against upwind's >
+    v[rng.random(shape) < 0.1] = 0.0
+    dev, S, F = Dev(emu, ny, nx), Scalars(emu), Scalars(emu)
+    geo = (C.c_int * 4)()
+    assert emu.emu_fused_geometry(nx, ny, sms, geo) == 1 and geo[0] * geo[1] >= 1 and geo[3] >= 2
+    for scheme in (QUICK, UPWIND, NONE):
+        du, dv_ = dev.put(u), dev.put(v)
+        us, vs, b = dev.put(), dev.put(), dev.put()
+        emu.emu_predict(scheme, nx, ny, ptr(du), ptr(dv_), ptr(us), ptr(vs), dt, dx, dy)
+        emu.emu_rhs1(nx, ny, ptr(us), ptr(vs), ptr(b), dt, dx, dy, ptr(S.scratch), ptr(S.scal))
+        fus, fvs, fb = dev.put(), dev.put(), dev.put()
+        assert emu.emu_front(scheme, nx, ny, ptr(du), ptr(dv_), ptr(fus), ptr(fvs), ptr(fb), dt, dt, dx, dy, sms,
+                             ptr(F.scratch), ptr(F.scal)) == 1
+        # dev.get also asserts that halo rows and padding columns were never stored to
+        assert same(dev.get(fus), dev.get(us)) and same(dev.get(fvs), dev.get(vs)) and same(dev.get(fb), dev.get(b)), scheme
+        assert close(F["S_DIVB_SUMSQ"], S["S_DIVB_SUMSQ"]) and close(F["S_RHS_SUM"], S["S_RHS_SUM"], 1e-10), scheme
+
+
+@pytest.mark.parametrize("poison", [None, "nan_u", "nan_x0", "inf_v"])
+@pytest.mark.parametrize("shape,unit,sms", FUSED_CASES)
+def test_fused_finish_pass_equals_the_five_kernels_after_the_solve(emu, shape, unit, sms, poison):
+    ny, nx = shape
+    if poison and (ny, nx) not in ((9, 13), (12, 121)):
+        pytest.skip("poisoned inputs on two shapes only")
+    rng = np.random.default_rng(ny * 173 + nx)
+    dx, dy = (1.0, 1.0) if unit else (0.37, 1.9)
+    dt, lid = 0.0123, 1.25
+    b, x, us, vs, uo, vo = (rng.standard_normal(shape) for _ in range(6))
+    x[0, 0] = 0.0                                          # the pin keeps x[0] at exactly 0 (or NaN)
+    if poison == "nan_u":
+        us[ny // 2, nx // 2] = np.nan
+    elif poison == "nan_x0":
+        x[0, 0] = np.nan
+    elif poison == "inf_v":
+        vs[ny - 2, 1] = np.inf
+    dev, S, F = Dev(emu, ny, nx), Scalars(emu), Scalars(emu)
+    with np.errstate(invalid="ignore"):
+        for post in (1, 0):
+            # the separate kernels in the order of pf_step
+            db, dxx, du, dv_, duo, dvo = dev.put(b), dev.put(x), dev.put(us), dev.put(vs), dev.put(uo), dev.put(vo)
+            center = np.full(ny, np.nan)
+            emu.emu_resid(nx, ny, ptr(db), ptr(dxx), dx, dy, ptr(S.scratch), ptr(S.scal))
+            emu.emu_correct(nx, ny, ptr(dxx), ptr(du), ptr(dv_), dt, dx, dy, S["S_X0"])
+            emu.emu_divnorm(nx, ny, ptr(du), ptr(dv_), dx, dy, ptr(S.scratch), ptr(S.scal))
+            if post:
+                emu.emu_lid(nx, ny, ptr(du), lid)
+                emu.emu_post(nx, ny, ptr(du), ptr(dv_), ptr(duo), ptr(dvo), ptr(dxx), ptr(center), ptr(S.scratch),
+                             ptr(S.scal))
+            # the fused pass: new fields land in the buffers that held the previous step's
+            fb, fx, fu, fv, fuo, fvo = dev.put(b), dev.put(x), dev.put(us), dev.put(vs), dev.put(uo), dev.put(vo)
+            fcenter = np.full(ny, np.nan)
+            assert emu.emu_finish(post, nx, ny, ptr(fb), ptr(fx), ptr(fu), ptr(fv), ptr(fuo), ptr(fvo), dt, dx, dy, 1,
+                                  lid, ptr(fcenter), sms, ptr(F.scratch), ptr(F.scal)) == 1
+            assert same(dev.get(fuo), dev.get(du)) and same(dev.get(fvo), dev.get(dv_)), (post, poison)
+            assert same(dev.get(fx), dev.get(dxx)), "p = x - x[0]"
+            assert same(dev.get(fu), us) and same(dev.get(fv), vs) and same(dev.get(fb), b), "inputs are read-only"
+            names = ["S_RES_SUMSQ", "S_DIVA_SUMSQ"]
+            if post:
+                names += ["S_RU_SUMSQ", "S_RV_SUMSQ", "S_DIVC_SUMSQ", "S_NONFINITE", "S_UNAN", "S_VNAN", "S_UMAX", "S_VMAX"]
+                assert same(fcenter, center)
+            for name in names:
+                a, w = F[name], S[name]
+                assert (np.isnan(a) and np.isnan(w)) or a == w or close(a, w, 1e-12), (name, a, w, post, poison)
+            xs, fs = S["S_X0"], F["S_X0"]
+            assert xs == fs or (np.isnan(xs) and np.isnan(fs))
+            if poison == "nan_u" and post:
+                assert F["S_UNAN"] == 1.0 and F["S_NONFINITE"] >= 1.0
+            if poison == "nan_x0":
+                assert np.isnan(dev.get(fx)).all() and np.isnan(dev.get(fvo)[:-1]).all()     # p = x - NaN everywhere
+
+
+def test_fused_geometry_covers_every_row_and_column_once(emu):
+    """Every cell belongs to exactly one (column block, warp, owning lane) and one band -- for the grids of the
+    BASELINE configs and a few awkward ones."""
+    geo = (C.c_int * 4)()
+    for nx, ny, sms in ((64, 64, 148), (512, 512, 148), (4096, 4096, 148), (8192, 8192, 148), (16384, 16384, 148),
+                        (4000, 4000, 148), (5000, 3000, 148), (4097, 1500, 132), (61, 7, 2), (4, 4, 148), (100000, 8, 148)):
+        assert emu.emu_fused_geometry(nx, ny, sms, geo) == 1, (nx, ny)
+        gx, gy, threads, rows = geo[0], geo[1], geo[2], geo[3]
+        assert threads % 32 == 0 and 32 <= threads <= 256 and gx * gy <= 4096
+        assert gx * (threads // 32) * 60 >= nx > (gx - 1) * (threads // 32) * 60          # columns covered, no empty block
+        assert gy * rows >= ny > (gy - 1) * rows                                           # rows covered, no empty band
+    for nx, ny in ((3, 100), (100, 3), (2, 2)):
+        assert emu.emu_fused_geometry(nx, ny, 148, geo) == 0        # tiny grids keep the separate kernels
 
 
 # ===================================================================================================================

@@ -34,11 +34,12 @@ def _check(name, cfg, steps, options=None):
     return r
 
 
-@pytest.mark.parametrize("options", [None, "cg_kernel=1", "cg_kernel=2"])
+@pytest.mark.parametrize("options", [None, "cg_kernel=1", "cg_kernel=2", "step_fused=0"])
 def test_config3_4096_three_steps_vs_c_oracle(options):
     """BASELINE config 3 exactly as bench.py runs it (4096^2, Re=1000, QUICK, 300 iterations per step), 3 steps
-    from rest: the dynamically scheduled TMA kernel (default), the register-window kernel (cg_kernel=1) and the
-    static TMA kernel (cg_kernel=2)."""
+    from rest: the dynamically scheduled TMA kernel (default), the register-window kernel (cg_kernel=1), the
+    static TMA kernel (cg_kernel=2), and the default CG kernel between the seven separate per-step kernels instead of
+    the two fused passes (step_fused=0)."""
     r = _check("config3 4096x4096", parity.make_cfg(4096, 4096, 1000.0), 3, options)
     assert r["iters"] == [0, 300, 300]
 
