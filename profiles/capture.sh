@@ -53,6 +53,12 @@ for what in "$@"; do
       python profiles/experiments/small_kernel_timeline.py 512 | tee gpurun_out/small_kernel_timeline.txt
       [ "$(nvidia-smi -L | wc -l)" -ge 2 ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29701 profiles/experiments/barrier_timeline_multigpu.py 4096 4096 2>&1 | grep -E "rank|barrier" | tee gpurun_out/barrier_timeline_2gpu.txt ;;
-    *) echo "unknown target $what (tests newtests bench launches full4096 full512 sanitize scaling reference timeline)"; exit 2 ;;
+    steppasses)   # the two fused per-step passes against the seven separate kernels: A/B of the non-CG part of a step, then
+                  # per-kernel times of both chains (ncu launch list; short solves so that the list stays small)
+      python profiles/experiments/step_passes_ab.py 2>&1 | grep STEPPASS | tee gpurun_out/step_passes_ab.txt
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/step_passes_launches.csv \
+          -k 'regex:k_front|k_finish|k_rhs|k_predict|k_resid|k_correct|k_divnorm|k_lid|k_post' \
+          python profiles/experiments/step_passes_ab.py 4096 4096 5 2 512 512 5 2 > gpurun_out/step_passes_ncu.log 2>&1 ;;
+    *) echo "unknown target $what (tests newtests bench launches full4096 full512 sanitize scaling reference timeline steppasses)"; exit 2 ;;
   esac
 done
