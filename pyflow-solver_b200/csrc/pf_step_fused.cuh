@@ -17,19 +17,37 @@
 //
 // Work distribution: a warp marches up a band of rows.  A lane holds TWO adjacent columns (16-byte loads / stores); the
 // rows a stencil needs below and above live in a register window that slides one row per step, so every operand is
-// loaded once per band.  Lanes 1..30 OWN their pair (store it, add it to the sums); lanes 0 and 31 hold the pair just
-// left / right of the warp's 60 columns and only supply neighbours through shuffles -- no lane ever needs a value
-// from another warp, no shared memory, no block barrier inside the sweep.  Grid: x = column blocks of
-// 60 * (warps per block) columns, y = bands.  u and v are written OUT OF PLACE (into the buffers that held the previous
-// step's fields, each cell after its owner read the old value): a neighbour's u*, v* can be read at any time.
+// loaded once per band.  Lanes 2..30 OWN their pair (store it, add it to the sums); lanes 0, 1 and 31 hold the pairs
+// just left / right of the warp's 58 columns and only supply neighbours through shuffles -- no lane ever needs a value
+// from another warp, no shared memory, no block barrier inside the sweep, and all 32 lanes run the same code.  Grid:
+// x = column blocks of 58 * (warps per block) columns, y = bands.  u and v are written OUT OF PLACE (into the buffers
+// that held the previous step's fields, each cell after its owner read the old value): a neighbour's u*, v* can be read
+// at any time.
+//
+// Latency: with ~110 registers per thread only 16 warps fit on an SM, so a sweep that waited for its loads where it
+// uses them ran at a quarter of the issue rate and no faster than the seven kernels together (first B200 run).  Hence
+// (i) every load of a row step is UNCONDITIONAL and stands at the top of the step: a lane without a column, or a row
+// beyond the wall, reads a clamped, valid address and the value is discarded by the "neighbour exists" selects that
+// guard every use anyway; (ii) the loads are issued one row step AHEAD of their use (PF_FUSED_PREFETCH).
 #pragma once
 
 #include "pf_kernels.cuh"
 
 namespace pf {
 
-constexpr int FT = 256;             // threads per block (at most; narrow grids launch fewer warps)
-constexpr int F_OWN = 60;           // columns a warp owns
+#ifndef PF_FUSED_FT
+#define PF_FUSED_FT 256
+#endif
+#ifndef PF_FUSED_MINB
+#define PF_FUSED_MINB 2
+#endif
+#ifndef PF_FUSED_PREFETCH
+#define PF_FUSED_PREFETCH 1
+#endif
+constexpr int FT = PF_FUSED_FT;     // threads per block (at most; narrow grids launch fewer warps)
+constexpr int F_MINB = PF_FUSED_MINB;            // blocks per SM the register budget is set for
+constexpr bool F_PREFETCH = PF_FUSED_PREFETCH;   // loads run one row step ahead of their use
+constexpr int F_OWN = 58;           // columns a warp owns (lanes 2..30)
 
 // Launch geometry of the two passes (host side; shared by pf_api.cu and the host emulation of the tests): a block is
 // up to FT / 32 warps side by side (as few column blocks as cover the row, warps spread evenly over them), a band as
@@ -55,35 +73,31 @@ inline FusedGeometry fused_geometry(int nx, int nyl, int sm_count) {
 }
 
 struct FCols {
-  int c0;        // first column of the lane's pair (even; -2 on lane 0 of the first warp of a row)
+  int c0;        // first column of the lane's pair (even; negative on lanes 0 and 1 of the first warp of a row)
+  int cl;        // the column the lane LOADS from: c0 clamped into the row (even, so the pair lies inside the pitch)
   bool va, vb;   // the grid has column c0 / c0 + 1
-  bool own;      // lanes 1..30
+  bool own;      // lanes 2..30
 };
 
 __device__ __forceinline__ FCols fused_cols(const Slab& s) {
   const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
   const int wpb = (int)blockDim.x >> 5;
   FCols c;
-  c.c0 = F_OWN * ((int)blockIdx.x * wpb + warp) + 2 * (lane - 1);
+  c.c0 = F_OWN * ((int)blockIdx.x * wpb + warp) + 2 * (lane - 2);
+  c.cl = clampi(c.c0, 0, (s.nx - 1) & ~1);
   c.va = c.c0 >= 0 && c.c0 < s.nx;
   c.vb = c.c0 >= 0 && c.c0 + 1 < s.nx;
-  c.own = lane >= 1 && lane <= 30;
+  c.own = lane >= 2 && lane <= 30;
   return c;
 }
 
-// The lane's two cells of local row jl; 0.0 where the grid has no such column (every use of a neighbour is behind an
-// "exists" select, as in the separate kernels, so the zeros never reach a result).
-__device__ __forceinline__ double2 ld_pair(const double* f, const Slab& s, int jl, const FCols& c) {
-  double2 v = make_double2(0.0, 0.0);
-  if (c.va) {
-    v = ld2(f + cell(s, jl, c.c0));
-    if (!c.vb) v.y = 0.0;          // odd nx: the padding column came along with the 16-byte load
-  }
-  return v;
-}
-__device__ __forceinline__ void st_pair(double* f, const Slab& s, int jl, const FCols& c, double a, double b) {
-  if (c.vb) st2(f + cell(s, jl, c.c0), a, b);
-  else st1(f + cell(s, jl, c.c0), a);        // padding columns are never stored to
+// Offset (in doubles) of the lane's load column in local row jl.
+__device__ __forceinline__ size_t fused_off(const Slab& s, int jl, const FCols& c) { return cell(s, jl, c.cl); }
+
+// Stores go to the lane's own pair (caller: own && va); padding columns are never stored to.
+__device__ __forceinline__ void st_pair(double* f, size_t off, const FCols& c, double a, double b) {
+  if (c.vb) st2(f + off, a, b);
+  else st1(f + off, a);
 }
 
 __device__ __forceinline__ double shfl_left(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
@@ -157,40 +171,46 @@ __device__ __forceinline__ double div_coh_vals(double uc, double uw, double vc, 
 // ---- pass 1: predictor + rhs pass 1 -----------------------------------------------------------------------------------
 // (u, v) -> (us, vs) = u*, v*;  b = (-div_coherent(u*, v*)) / max(dt, 1e-14);  sums: div^2, b.
 // The band's first row needs v* of the row below it: one warm-up row is computed (not stored) before the band.
+// Row step j loads row j + 2 (QUICK's window: j - 2 .. j + 1), i.e. one step ahead of its use.
 template <bool UNIT, int SCHEME>
-__global__ void __launch_bounds__(FT, 2)
+__global__ void __launch_bounds__(FT, F_MINB)
 k_front(Slab s, const double* u, const double* v, double* us, double* vs, double* b, double dt, double dt_safe,
         double dx, double dy, int band_rows, Red red) {
   const FCols c = fused_cols(s);
-  const int lane = (int)threadIdx.x & 31;
   const int top = s.nyg - 1 - s.row0;                      // local index of the global top row
+  const int bot = -s.row0;                                 // ... and of the global bottom row
   const int y0 = (int)blockIdx.y * band_rows;
   const int y1 = (y0 + band_rows < s.nyl) ? y0 + band_rows : s.nyl;
   const bool has_w = c.c0 > 0;                             // column c0 - 1 exists
   const bool has_e = c.c0 + 2 < s.nx;                      // column c0 + 2 exists
-  const bool edge_w = c.c0 > 0 && c.c0 <= s.nx;            // ... and lies inside the grid (lane 0's scalar load)
+  const size_t pitch = (size_t)s.pitch;
   double vals[2] = {0.0, 0.0};
   if (y0 < y1) {
-    const int js = (s.row0 + y0 > 0) ? y0 - 1 : y0;
-    auto rowc = [&](int jl) { return clampi(s.row0 + jl, 0, s.nyg - 1) - s.row0; };
-    double2 u2 = make_double2(0.0, 0.0), u1 = u2, uc = u2, un = u2, v2 = u2, v1 = u2, vc = u2, vn = u2;
-    uc = ld_pair(u, s, js, c);
-    vc = ld_pair(v, s, js, c);
+    const int js = (y0 > bot) ? y0 - 1 : y0;
+    auto rowc = [&](int jl) { return clampi(jl, bot, top); };       // np.pad(..., 'edge') in y
+    double2 u2, u1, uc, un, v2, v1, vc, vn;
+    uc = ld2(u + fused_off(s, js, c));
+    vc = ld2(v + fused_off(s, js, c));
+    u2 = u1 = un = uc;
+    v2 = v1 = vn = vc;
     if (SCHEME != PF_ADV_NONE) {
-      u2 = ld_pair(u, s, rowc(js - 2), c); u1 = ld_pair(u, s, rowc(js - 1), c); un = ld_pair(u, s, rowc(js + 1), c);
-      v2 = ld_pair(v, s, rowc(js - 2), c); v1 = ld_pair(v, s, rowc(js - 1), c); vn = ld_pair(v, s, rowc(js + 1), c);
+      u2 = ld2(u + fused_off(s, rowc(js - 2), c)); u1 = ld2(u + fused_off(s, rowc(js - 1), c));
+      un = ld2(u + fused_off(s, rowc(js + 1), c));
+      v2 = ld2(v + fused_off(s, rowc(js - 2), c)); v1 = ld2(v + fused_off(s, rowc(js - 1), c));
+      vn = ld2(v + fused_off(s, rowc(js + 1), c));
     }
     double2 vs_south = make_double2(0.0, 0.0);             // v* of row j - 1
-    for (int j = js; j < y1; ++j) {
+    size_t off = fused_off(s, js, c);                      // row j, the lane's load column
+    for (int j = js; j < y1; ++j, off += pitch) {
+      // the row the NEXT step needs: j + 2 (the top row again beyond the wall), resp. j + 1 without advection
+      const int ahead = (SCHEME != PF_ADV_NONE) ? (top - j < 2 ? top - j : 2) : (j + 1 < y1 ? 1 : 0);
+      const double2 nu = ld2(u + off + (size_t)ahead * pitch);
+      const double2 nv = ld2(v + off + (size_t)ahead * pitch);
       double2 ust = uc, vst = vc;
       if (SCHEME != PF_ADV_NONE) {
         // the pair to the left (x = column c0 - 2, y = c0 - 1) and the first cell to the right (column c0 + 2)
-        double ulx = shfl_left(uc.x), uly = shfl_left(uc.y), urx = shfl_right(uc.x);
-        double vlx = shfl_left(vc.x), vly = shfl_left(vc.y), vrx = shfl_right(vc.x);
-        if (lane == 0) {     // lane 0 forms u*, v* of its SECOND cell for lane 1's divergence: needs column c0 - 1 only
-          uly = edge_w ? ld1(u + cell(s, j, c.c0 - 1)) : 0.0;
-          vly = edge_w ? ld1(v + cell(s, j, c.c0 - 1)) : 0.0;
-        }
+        const double ulx = shfl_left(uc.x), uly = shfl_left(uc.y), urx = shfl_right(uc.x);
+        const double vlx = shfl_left(vc.x), vly = shfl_left(vc.y), vrx = shfl_right(vc.x);
         // np.pad(field, 2, 'edge'): a neighbour beyond a wall is the wall cell itself
         const double uW_a = has_w ? uly : uc.x, uWW_a = has_w ? ulx : uc.x, uE_a = c.vb ? uc.y : uc.x;
         const double uW_b = uc.x, uWW_b = has_w ? uly : uc.x, uE_b = has_e ? urx : uc.y;
@@ -205,7 +225,8 @@ k_front(Slab s, const double* u, const double* v, double* us, double* vs, double
       }
       const double ust_w = shfl_left(ust.y);               // u* of column c0 - 1
       if (j >= y0 && c.own && c.va) {
-        const bool hs = s.row0 + j > 0;
+        const bool hs = j > bot;
+        const size_t so = off + (size_t)(c.c0 - c.cl);      // own && va: c0 == cl
         const double d_a = div_coh_vals<UNIT>(ust.x, ust_w, vst.x, vs_south.x, has_w, hs, dx, dy);
         const double rb_a = (-d_a) / dt_safe;
         double rb_b = 0.0;
@@ -217,21 +238,17 @@ k_front(Slab s, const double* u, const double* v, double* us, double* vs, double
           vals[0] += d_b * d_b;
           vals[1] += rb_b;
         }
-        st_pair(us, s, j, c, ust.x, ust.y);
-        st_pair(vs, s, j, c, vst.x, vst.y);
-        st_pair(b, s, j, c, rb_a, rb_b);
+        st_pair(us, so, c, ust.x, ust.y);
+        st_pair(vs, so, c, vst.x, vst.y);
+        st_pair(b, so, c, rb_a, rb_b);
       }
       vs_south = vst;
       if (SCHEME != PF_ADV_NONE) {
-        u2 = u1; u1 = uc; uc = un;
-        v2 = v1; v1 = vc; vc = vn;
-        if (j + 2 <= top) {                                // else the new north row is the (clamped) top row itself
-          un = ld_pair(u, s, j + 2, c);
-          vn = ld_pair(v, s, j + 2, c);
-        }
-      } else if (j + 1 < y1) {
-        uc = ld_pair(u, s, j + 1, c);
-        vc = ld_pair(v, s, j + 1, c);
+        u2 = u1; u1 = uc; uc = un; un = nu;
+        v2 = v1; v1 = vc; vc = vn; vn = nv;
+      } else {
+        uc = nu;
+        vc = nv;
       }
     }
   }
@@ -244,55 +261,78 @@ k_front(Slab s, const double* u, const double* v, double* us, double* vs, double
 // fields on entry (POST) and the new fields on return.
 // vals: ||b - A x||^2, ||div_coherent(u, v)||^2 after the correction; POST adds max|u|, max|v|, sum (u-uo)^2,
 // sum (v-vo)^2, sum div_central^2, #nonfinite, #nan u, #nan v (the slots k_post writes).
+struct FinRow {              // what row step j loads
+  double2 X2;                // x   of row j + 2
+  double2 VS1;               // v*  of row j + 1
+  double2 U, B, UO, VO;      // u*, b, previous u, previous v of row j
+};
+
 template <bool UNIT, bool POST>
-__global__ void __launch_bounds__(FT, 2)
+__global__ void __launch_bounds__(FT, F_MINB)
 k_finish(Slab s, const double* b, double* x, const double* us, const double* vs, double* uout, double* vout, double dt,
          double dx, double dy, int lid_set, double lid, double* center, int band_rows, Red red) {
   constexpr int NV = POST ? 10 : 2;
   const FCols c = fused_cols(s);
   const int nx = s.nx;
   const int top = s.nyg - 1 - s.row0;
+  const int bot = -s.row0;
   const int y0 = (int)blockIdx.y * band_rows;
   const int y1 = (y0 + band_rows < s.nyl) ? y0 + band_rows : s.nyl;
   const bool has_w = c.c0 > 0;                 // column c0 - 1 exists
   const bool he_b = c.c0 + 2 < nx;             // column c0 + 2 exists (east neighbour of the second cell)
+  const size_t pitch = (size_t)s.pitch;
   double vals[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) vals[k] = 0.0;
   if (y0 < y1) {
     // p = x - x[0] (pressure_solver.py:148): an exact no-op unless x[0] != 0 (x[0] stays 0 under the pin; NaN poisons all)
-    const double x0 = ld1(x + cell(s, -s.row0, 0));
+    const double x0 = ld1(x + cell(s, bot, 0));
     const bool shift = !(x0 == 0.0);
-    const double2 zero = make_double2(0.0, 0.0);
     // v after the correction at local row jl: v* - dt * dp/dy, dp/dy = 0 in the top row (gradient_coherent)
     auto v_corrected = [&](const double2& vstar, const double2& xr, const double2& xabove, int jl) {
       double2 o;
-      double gya = 0.0, gyb = 0.0;
-      if (jl < top) {
-        gya = dv<UNIT>((xabove.x - x0) - (xr.x - x0), dy);
-        gyb = dv<UNIT>((xabove.y - x0) - (xr.y - x0), dy);
-      }
+      const bool inner = jl < top;
+      const double gya = inner ? dv<UNIT>((xabove.x - x0) - (xr.x - x0), dy) : 0.0;
+      const double gyb = inner ? dv<UNIT>((xabove.y - x0) - (xr.y - x0), dy) : 0.0;
       o.x = vstar.x - dt * gya;
       o.y = vstar.y - dt * gyb;
       return o;
     };
-    const bool below = s.row0 + y0 > 0;
-    double2 Xm = below ? ld_pair(x, s, y0 - 1, c) : zero;
-    double2 Xc = ld_pair(x, s, y0, c);
-    double2 Xp = (y0 + 1 <= top) ? ld_pair(x, s, y0 + 1, c) : zero;
-    double2 Vm = below ? v_corrected(ld_pair(vs, s, y0 - 1, c), Xm, Xc, y0 - 1) : zero;
-    double2 Vc = v_corrected(ld_pair(vs, s, y0, c), Xc, Xp, y0);
-    for (int j = y0; j < y1; ++j) {
-      const int jg = s.row0 + j;
-      const bool hs = jg > 0, hn = j < top;
-      const double2 Xpp = (j + 2 <= top) ? ld_pair(x, s, j + 2, c) : zero;
-      const double2 Vp = hn ? v_corrected(ld_pair(vs, s, j + 1, c), Xp, Xpp, j + 1) : zero;
-      const double2 U = ld_pair(us, s, j, c);
-      double2 B = zero, UO = zero, VO = zero;
-      if (c.own) {
-        B = ld_pair(b, s, j, c);
-        if (POST) { UO = ld_pair(uout, s, j, c); VO = ld_pair(vout, s, j, c); }
+    // all loads of a row step, unconditional: rows beyond the top wall read the top row (discarded by the selects)
+    auto load_row = [&](int j) {
+      const size_t o = fused_off(s, j, c);
+      const int d1 = top - j < 1 ? top - j : 1, d2 = top - j < 2 ? top - j : 2;
+      FinRow r;
+      r.X2 = ld2(x + o + (size_t)d2 * pitch);
+      r.VS1 = ld2(vs + o + (size_t)d1 * pitch);
+      r.U = ld2(us + o);
+      r.B = ld2(b + o);
+      if (POST) {
+        r.UO = ld2(uout + o);
+        r.VO = ld2(vout + o);
+      } else {
+        r.UO = r.VO = r.U;
       }
+      return r;
+    };
+    const bool below = y0 > bot;
+    const int ym = below ? y0 - 1 : y0, yp = y0 < top ? y0 + 1 : y0;
+    double2 Xm = ld2(x + fused_off(s, ym, c));
+    double2 Xc = ld2(x + fused_off(s, y0, c));
+    double2 Xp = ld2(x + fused_off(s, yp, c));
+    const double2 vs_m = ld2(vs + fused_off(s, ym, c)), vs_c = ld2(vs + fused_off(s, y0, c));
+    FinRow cur = load_row(y0);
+    double2 Vm = v_corrected(vs_m, Xm, Xc, y0 - 1);          // unused when there is no row below
+    double2 Vc = v_corrected(vs_c, Xc, Xp, y0);
+    size_t off = fused_off(s, y0, c);
+    for (int j = y0; j < y1; ++j, off += pitch) {
+      FinRow nxt;
+      if (F_PREFETCH) nxt = load_row(j + 1 < y1 ? j + 1 : j);      // the next step's operands, before this step's math
+      else if (j > y0) cur = load_row(j);
+      const bool hs = j > bot, hn = j < top;
+      const double2 Xpp = cur.X2;
+      const double2 Vp = v_corrected(cur.VS1, Xp, Xpp, j + 1);     // unused in the top row
+      const double2 U = cur.U, B = cur.B, UO = cur.UO, VO = cur.VO;
       const double xw = shfl_left(Xc.y);        // x at column c0 - 1
       const double xe = shfl_right(Xc.x);       // x at column c0 + 2
       // u after the correction: u* - dt * dp/dx, dp/dx = 0 in the last column
@@ -303,6 +343,7 @@ k_finish(Slab s, const double* b, double* x, const double* us, const double* vs,
       const double un_w = shfl_left(un_b);      // corrected u at column c0 - 1
       const double un_e = shfl_right(un_a);     // corrected u at column c0 + 2
       if (c.own && c.va) {
+        const int jg = s.row0 + j;
         // true residual b - A x, A = pinned -laplacian_coherent
         double ax_a = neg_lap<UNIT>(Xc.x, has_w ? xw : 0.0, c.vb ? Xc.y : 0.0, hs ? Xm.x : 0.0, hn ? Xp.x : 0.0,
                                     has_w, c.vb, hs, hn, dx, dy);
@@ -326,13 +367,13 @@ k_finish(Slab s, const double* b, double* x, const double* us, const double* vs,
           vals[1] += db * db;
         }
         if (POST) {
-          const bool bot = jg == 0, topr = jg == s.nyg - 1;
+          const bool botr = jg == 0, topr = jg == s.nyg - 1;
           const double du = uf_a - UO.x, dvv = Vc.x - VO.x;
           vals[2] = fmax(vals[2], fabs(uf_a));
           vals[3] = fmax(vals[3], fabs(Vc.x));
           vals[4] += du * du;
           vals[5] += dvv * dvv;
-          const double dc = div_central_vals<true>(uf_a, uf_w, uf_b, Vc.x, Vm.x, Vp.x, c.c0 == 0, c.c0 == nx - 1, bot,
+          const double dc = div_central_vals<true>(uf_a, uf_w, uf_b, Vc.x, Vm.x, Vp.x, c.c0 == 0, c.c0 == nx - 1, botr,
                                                    topr, 1.0, 1.0);
           vals[6] += dc * dc;
           vals[7] += ((isfinite(uf_a) && isfinite(Vc.x) && isfinite(pa)) ? 0.0 : 1.0);
@@ -346,7 +387,7 @@ k_finish(Slab s, const double* b, double* x, const double* us, const double* vs,
             vals[4] += du2 * du2;
             vals[5] += dv2 * dv2;
             const double dc2 = div_central_vals<true>(uf_b, uf_a, uf_e, Vc.y, Vm.y, Vp.y, false, c.c0 + 1 == nx - 1,
-                                                      bot, topr, 1.0, 1.0);
+                                                      botr, topr, 1.0, 1.0);
             vals[6] += dc2 * dc2;
             vals[7] += ((isfinite(uf_b) && isfinite(Vc.y) && isfinite(pb)) ? 0.0 : 1.0);
             vals[8] += (uf_b != uf_b) ? 1.0 : 0.0;
@@ -354,12 +395,13 @@ k_finish(Slab s, const double* b, double* x, const double* us, const double* vs,
             if (c.c0 + 1 == nx / 2) center[j] = uf_b;
           }
         }
-        st_pair(uout, s, j, c, uf_a, uf_b);
-        st_pair(vout, s, j, c, Vc.x, Vc.y);
-        if (shift) st_pair(x, s, j, c, pa, pb);
+        st_pair(uout, off, c, uf_a, uf_b);       // own && va: the load column IS the lane's column
+        st_pair(vout, off, c, Vc.x, Vc.y);
+        if (shift) st_pair(x, off, c, pa, pb);
       }
       Xm = Xc; Xc = Xp; Xp = Xpp;
       Vm = Vc; Vc = Vp;
+      if (F_PREFETCH) cur = nxt;
     }
   }
   if constexpr (POST) {
