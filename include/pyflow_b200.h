@@ -203,8 +203,13 @@ int pf_comm_set_peers(pf_ctx* ctx, const void* const* peer_workspaces, int n);
 
 /* Introspection used by bench.py / tests. */
 int pf_device_info(pf_ctx* ctx, int* sm_count, int* cg_grid_blocks, int* cg_block_threads);
-/* tuning / debugging switches (key: "cg_multi_single" = run the multi-GPU
- * persistent kernel, own barrier included, on a single-GPU context) */
+/* tuning / debugging switches: "cg_kernel" (3 automatic, 2 static TMA tiles,
+ * 1 register-window kernels only), "step_fused" (1: one GPU runs the per-step
+ * work around the solve as the two fused passes of pf_step_fused.cuh, the
+ * default; 0: the seven separate kernels that slab runs on several GPUs use),
+ * "cg_multi_single" (run the multi-GPU persistent kernel, own barrier included,
+ * on a single-GPU context), "cg_tile_rows" / "cg_small_rows" / "cg_nb_small" /
+ * "cg_rows_min" / "cg_sync_opt" (tile geometry and protocol experiments). */
 int pf_set_option(pf_ctx* ctx, const char* key, int value);
 /* debugging: copy n doubles of the CG partial-sum scratch (barrier timeline when
  * option "cg_sync_opt" bit 4 is set) */

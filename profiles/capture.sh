@@ -16,7 +16,7 @@ for what in "$@"; do
       python bench.py --workload cavity512 --steps 50 --no-cpu-baseline > gpurun_out/bench_cavity512.json ;;
     launches)     # launch list of the bench command (kernel shares of a step)
       ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-          python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1 ;;
+          python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/launches_bench.log 2>&1 ;;
     full4096)     # ncu --set full of the TMA-fed CG kernel (4096^2): DRAM bytes -> profiles/cg_traffic.json
       ncu --set full --clock-control none --import-source on -k regex:k_cg_tmad -s 2 -c 1 \
           -o gpurun_out/cg_tmad_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline \
@@ -35,6 +35,12 @@ for what in "$@"; do
         timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python tests/sanitize_cases.py \
           > gpurun_out/sanitizer_$tool.log 2>&1
         echo "$tool rc=$? $(grep -c SANITIZE gpurun_out/sanitizer_$tool.log) lines, $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_$tool.log | tail -1)" | tee -a gpurun_out/sanitizer_summary.txt
+      done ;;
+    sanitize_steps)   # the per-step passes (fused and separate) under memcheck / synccheck / initcheck
+      for tool in memcheck synccheck initcheck; do
+        timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python tests/sanitize_cases.py steps \
+          > gpurun_out/sanitizer_steps_$tool.log 2>&1
+        echo "steps $tool rc=$? $(grep -c SANITIZE gpurun_out/sanitizer_steps_$tool.log) lines, $(grep -E 'ERROR SUMMARY' gpurun_out/sanitizer_steps_$tool.log | tail -1)" | tee -a gpurun_out/sanitizer_steps_summary.txt
       done ;;
     scaling)      # configs 4 and 5 at every GPU count the box has (`gpurun --gpus 8 -- 'bash profiles/capture.sh scaling'`)
       ngpu=$(nvidia-smi -L | wc -l)
@@ -59,6 +65,6 @@ for what in "$@"; do
       ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/step_passes_launches.csv \
           -k 'regex:k_front|k_finish|k_rhs|k_predict|k_resid|k_correct|k_divnorm|k_lid|k_post' \
           python profiles/experiments/step_passes_ab.py 4096 4096 5 2 512 512 5 2 > gpurun_out/step_passes_ncu.log 2>&1 ;;
-    *) echo "unknown target $what (tests newtests bench launches full4096 full512 sanitize scaling reference timeline steppasses)"; exit 2 ;;
+    *) echo "unknown target $what (tests newtests bench launches full4096 full512 sanitize sanitize_steps scaling reference timeline steppasses)"; exit 2 ;;
   esac
 done

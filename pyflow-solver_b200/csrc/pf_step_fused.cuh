@@ -29,6 +29,12 @@
 // (i) every load of a row step is UNCONDITIONAL and stands at the top of the step: a lane without a column, or a row
 // beyond the wall, reads a clamped, valid address and the value is discarded by the "neighbour exists" selects that
 // guard every use anyway; (ii) the loads are issued one row step AHEAD of their use (PF_FUSED_PREFETCH).
+// Measured on a B200 at 4096^2 (profiles/r2b_step_passes_*.txt): k_finish 217 us against 432 us for the five kernels it
+// replaces (DRAM traffic 1.06 GB = the 64 B / cell, 76 % of the copy peak; still latency-bound: long-scoreboard 3.7 per
+// issue at 16 warps per SM), k_front 223 us against 253 us (issue-bound: 63 % issue utilisation, QUICK's arithmetic and
+// the two IEEE divisions of the rhs are 530 instructions per 58 cells); the non-CG part of a step 810 -> 553 us.
+// Build knobs tried and left at their defaults: no prefetch 570 us, 128-thread blocks x 3 per SM (140 registers) 682 us,
+// row loop unrolled by 2 / 4 (window rotation by renaming) 545 / 560 us, QUICK with operand selects 543 us.
 #pragma once
 
 #include "pf_kernels.cuh"
@@ -44,9 +50,13 @@ namespace pf {
 #ifndef PF_FUSED_PREFETCH
 #define PF_FUSED_PREFETCH 1
 #endif
+#ifndef PF_FUSED_UNROLL
+#define PF_FUSED_UNROLL 1
+#endif
 constexpr int FT = PF_FUSED_FT;     // threads per block (at most; narrow grids launch fewer warps)
 constexpr int F_MINB = PF_FUSED_MINB;            // blocks per SM the register budget is set for
 constexpr bool F_PREFETCH = PF_FUSED_PREFETCH;   // loads run one row step ahead of their use
+constexpr int F_UNROLL = PF_FUSED_UNROLL;        // row steps per loop body (> 1: the window rotation becomes renaming)
 constexpr int F_OWN = 58;           // columns a warp owns (lanes 2..30)
 
 // Launch geometry of the two passes (host side; shared by pf_api.cu and the host emulation of the tests): a block is
@@ -201,6 +211,7 @@ k_front(Slab s, const double* u, const double* v, double* us, double* vs, double
     }
     double2 vs_south = make_double2(0.0, 0.0);             // v* of row j - 1
     size_t off = fused_off(s, js, c);                      // row j, the lane's load column
+#pragma unroll(F_UNROLL)
     for (int j = js; j < y1; ++j, off += pitch) {
       // the row the NEXT step needs: j + 2 (the top row again beyond the wall), resp. j + 1 without advection
       const int ahead = (SCHEME != PF_ADV_NONE) ? (top - j < 2 ? top - j : 2) : (j + 1 < y1 ? 1 : 0);
@@ -325,6 +336,7 @@ k_finish(Slab s, const double* b, double* x, const double* us, const double* vs,
     double2 Vm = v_corrected(vs_m, Xm, Xc, y0 - 1);          // unused when there is no row below
     double2 Vc = v_corrected(vs_c, Xc, Xp, y0);
     size_t off = fused_off(s, y0, c);
+#pragma unroll(F_UNROLL)
     for (int j = y0; j < y1; ++j, off += pitch) {
       FinRow nxt;
       if (F_PREFETCH) nxt = load_row(j + 1 < y1 ? j + 1 : j);      // the next step's operands, before this step's math

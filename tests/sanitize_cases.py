@@ -36,7 +36,43 @@ def check(tag, x, ny, nx, b, maxiter, dx=1.0, dy=1.0):
     return err < 1e-9
 
 
+def steps_only():
+    """`python tests/sanitize_cases.py steps`: whole projection steps only -- the two fused per-step passes
+    (pf_step_fused.cuh: shuffles between the lanes of a warp, clamped loads, out-of-place u / v) and the seven
+    separate kernels (step_fused=0), on an even, an odd and a TMA-kernel width, both advection schemes."""
+    from types import SimpleNamespace
+    from pyflow.core.ghost_fields import allocate_state
+    from pyflow.residuals.manager import ResidualManager
+    from pyflow.solvers.solver import step
+    ok = True
+    for opts in (None, "step_fused=0"):
+        for nx, ny, maxiter, scheme in ((64, 48, 20, "quick"), (59, 37, 15, "upwind"), (117, 9, 10, "quick"),
+                                        (1024, 1100, 5, "quick")):
+            if opts:
+                os.environ["PYFLOW_B200_OPTIONS"] = opts
+            else:
+                os.environ.pop("PYFLOW_B200_OPTIONS", None)
+            cfg = SimpleNamespace(nx=nx, ny=ny, Re=100.0, lid_velocity=1.0, cfl_target=0.5, cfl_growth=1.05,
+                                  lin_tol=1e-10, lin_maxiter=maxiter, advection_scheme=scheme, disable_advection=False,
+                                  diagnostics=False)
+            st, tr = allocate_state(nx, ny), ResidualManager()
+            for it in range(3):
+                step(cfg, st, tr, it)
+            ost, _od = orc.run(cfg, 3)
+            err = max(float(np.linalg.norm(st.fields[f][1:-1, 1:-1] - orc.interior(ost.fields[f])) /
+                            (np.linalg.norm(orc.interior(ost.fields[f])) or 1.0)) for f in ("u", "v", "p"))
+            print(f"SANITIZE step {nx}x{ny} {scheme} options={opts}: max rel err vs oracle {err:.2e} "
+                  f"{'OK' if err < 1e-9 else 'FAIL'}", flush=True)
+            ok = ok and err < 1e-9
+            st.fields._slab.close()
+    os.environ.pop("PYFLOW_B200_OPTIONS", None)
+    print("SANITIZE_ALL_OK" if ok else "SANITIZE_FAILED", flush=True)
+    return 0 if ok else 1
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "steps":
+        return steps_only()
     ok = True
     cases = [
         # tag, ny, nx, options, maxiter
