@@ -236,7 +236,7 @@ def unmodified_reference_sample(cases=((64, 64, 100.0, 49), (512, 512, 1000.0, 1
     host cores (BASELINE configs 1 and 2; SURVEY 8d: "time the unmodified reference through SimulationDriver.run").
     A subprocess per case: the reference package and the drop-in package are both called `pyflow`."""
     script = os.path.join(ROOT, "oracle", "time_unmodified.py")
-    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "stamp.json")):
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pyflow", "__init__.pfbc")):
         return {"unavailable": "oracle/_ref not built (python oracle/build_ref.py needs /root/reference)"}
     env = dict(os.environ)
     env.pop("PYTHONPATH", None)

@@ -26,6 +26,7 @@ from types import SimpleNamespace
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
+sys.path.insert(0, HERE)
 
 
 def main(argv):
@@ -34,7 +35,8 @@ def main(argv):
     stamp = json.load(open(os.path.join(REF, "stamp.json")))
     if stamp.get("magic") != importlib.util.MAGIC_NUMBER.hex():
         raise SystemExit(f"oracle/_ref was compiled by Python {stamp.get('python')}, this is {sys.version.split()[0]}")
-    sys.path.insert(0, REF)
+    import build_ref
+    build_ref.install_importer()
     import numpy as np
     from pyflow.drivers.simulation_driver import SimulationDriver
     assert os.path.dirname(os.path.dirname(os.path.abspath(sys.modules["pyflow"].__file__))) == REF, "wrong pyflow imported"

@@ -81,7 +81,7 @@ def test_reference_arm_prints_on_rank_zero_only(rank, capsys):
         # same `config` object as the GPU arm prints for this workload and GPU count
         assert line["config"] == bench.workload_config("cavity4096", bench.WORKLOADS["cavity4096"], 2, 300)
         unmod = line["cpu_baseline"]["unmodified_reference"]
-        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "stamp.json")):
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pyflow", "__init__.pfbc")):
             case = unmod["cases"]["64x64 Re=100"]
             assert case["steps_timed"] == 2 and case["MLUPS"] > 0 and "error" not in case
         else:
@@ -119,8 +119,8 @@ def test_unmodified_reference_bytecode_agrees_with_the_oracle():
     import pyflow_oracle as orc
     if build_ref.build() is None:
         pytest.skip("no /root/reference and no prebuilt oracle/_ref")
-    assert not [f for _d, _s, fs in os.walk(os.path.join(ROOT, "oracle", "_ref")) for f in fs if f.endswith(".py")], \
-        "oracle/_ref must hold bytecode only, never reference sources"
+    assert not [f for _d, _s, fs in os.walk(os.path.join(ROOT, "oracle", "_ref")) for f in fs
+                if not (f.endswith(".pfbc") or f == "stamp.json")], "oracle/_ref must hold bytecode only, never reference sources"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_unmodified.py"), "40", "24", "100", "5"],
                        capture_output=True, text=True, cwd="/tmp", timeout=120,
                        env={k: v for k, v in os.environ.items() if k != "PYTHONPATH"})
