@@ -96,7 +96,7 @@ __device__ __forceinline__ double div_central(const Slab& s, const double* u, co
     xt = dv<UNIT>(uc - u[cell(s, jl, i - 1)], dx);
   } else {
     const double d = u[cell(s, jl, i + 1)] - u[cell(s, jl, i - 1)];
-    xt = UNIT ? d * 0.5 : d / tdx;      // d/2.0 == d*0.5 exactly
+    xt = UNIT ? d * 0.5 : dv<false>(d, tdx);      // d/2.0 == d*0.5 exactly
   }
   if (bot) {
     yt = dv<UNIT>(v[cell(s, jl + 1, i)] - vc, dy);
@@ -104,7 +104,7 @@ __device__ __forceinline__ double div_central(const Slab& s, const double* u, co
     yt = dv<UNIT>(vc - v[cell(s, jl - 1, i)], dy);
   } else {
     const double d = v[cell(s, jl + 1, i)] - v[cell(s, jl - 1, i)];
-    yt = UNIT ? d * 0.5 : d / tdy;
+    yt = UNIT ? d * 0.5 : dv<false>(d, tdy);
   }
   return xt + yt;
 }
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(KT) k_rhs1(Slab s, const double* u, const doub
   if (i < s.nx) {
     for (int jl = blockIdx.y; jl < s.nyl; jl += gridDim.y) {
       const double d = div_coh<UNIT>(s, u, v, jl, i, dx, dy);
-      const double rb = (-d) / dt_safe;
+      const double rb = dv<false>(-d, dt_safe);       // invariant divisor: exact, see pf_common.cuh
       b[cell(s, jl, i)] = rb;
       vals[0] += d * d;
       vals[1] += rb;
@@ -417,7 +417,7 @@ __device__ __forceinline__ double grad_central(const Slab& s, const double* p, i
     inner = (jg > 0) && (jg < s.nyg - 1);
     d = p[cell(s, clampi(jg + 1, 0, s.nyg - 1) - s.row0, i)] - p[cell(s, clampi(jg - 1, 0, s.nyg - 1) - s.row0, i)];
   }
-  if (inner) return UNIT ? d * 0.5 : d / (2.0 * h);      // d/2.0 == d*0.5 exactly
+  if (inner) return UNIT ? d * 0.5 : dv<false>(d, 2.0 * h);      // d/2.0 == d*0.5 exactly
   return dv<UNIT>(d, h);
 }
 

@@ -156,7 +156,7 @@ __device__ __forceinline__ double div_central_vals(double uc, double uw, double 
     xt = dv<UNIT>(uc - uw, dx);
   } else {
     const double d = ue - uw;
-    xt = UNIT ? d * 0.5 : d / tdx;
+    xt = UNIT ? d * 0.5 : dv<false>(d, tdx);
   }
   if (bot) {
     yt = dv<UNIT>(vn - vc, dy);
@@ -164,7 +164,7 @@ __device__ __forceinline__ double div_central_vals(double uc, double uw, double 
     yt = dv<UNIT>(vc - vs, dy);
   } else {
     const double d = vn - vs;
-    yt = UNIT ? d * 0.5 : d / tdy;
+    yt = UNIT ? d * 0.5 : dv<false>(d, tdy);
   }
   return xt + yt;
 }
@@ -239,13 +239,13 @@ k_front(Slab s, const double* u, const double* v, double* us, double* vs, double
         const bool hs = j > bot;
         const size_t so = off + (size_t)(c.c0 - c.cl);      // own && va: c0 == cl
         const double d_a = div_coh_vals<UNIT>(ust.x, ust_w, vst.x, vs_south.x, has_w, hs, dx, dy);
-        const double rb_a = (-d_a) / dt_safe;
+        const double rb_a = dv<false>(-d_a, dt_safe);      // invariant divisor: exact, see pf_common.cuh
         double rb_b = 0.0;
         vals[0] += d_a * d_a;
         vals[1] += rb_a;
         if (c.vb) {
           const double d_b = div_coh_vals<UNIT>(ust.y, ust.x, vst.y, vs_south.y, true, hs, dx, dy);
-          rb_b = (-d_b) / dt_safe;
+          rb_b = dv<false>(-d_b, dt_safe);
           vals[0] += d_b * d_b;
           vals[1] += rb_b;
         }
