@@ -2,12 +2,12 @@
 # profiles/sass_summary.sh -- instruction census of the CG kernels in the built library (cuobjdump -sass):
 # proves the TMA bulk copies (UBLKCP), mbarriers (SYNCS), 128-bit shared loads / global stores, the absence of fused
 # multiply-adds in the unit-spacing kernels (-fmad=false; DFMA only from the scalar divide / sqrt sequences), and
-# which fences the exchanges use.  Usage: bash profiles/sass_summary.sh > profiles/r2_sass_summary.txt
+# which fences the exchanges use.  Usage: bash profiles/sass_summary.sh > profiles/r2b_sass_summary.txt
 LIB=pyflow-solver_b200/pyflow/_b200/libpyflow_b200.so
 echo "library: $LIB  sha256 $(sha256sum $LIB | cut -c1-16)  source hash $(python -c 'import bench; print(bench.kernel_source_hash())')"
 cuobjdump -sass $LIB 2>/dev/null | awk '
   /Function : / { fn=$3; next }
-  fn ~ /k_cg_tmad|k_cg_small|k_cg_persistent|k_cg_tma[^d]|k_cg_generic|k_bicgstab/ {
+  fn ~ /k_cg_tmad|k_cg_small|k_cg_persistent|k_cg_tma[^d]|k_cg_generic|k_bicgstab|k_front|k_finish/ {
     n[fn]++
     if ($0 ~ /UBLKCP/) ublkcp[fn]++
     if ($0 ~ /UTMALDG/) utmaldg[fn]++

@@ -86,9 +86,11 @@ def test_product_package_never_imports_the_oracle():
                 assert "pyflow_oracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f
                 # ... nor the test doubles (oracle-backed stand-in slab, host emulation of the kernels)
                 assert "cpu_slab" not in src and "emu_kernels" not in src, f
-                # (the only hook for tests is one #ifdef PF_HOST_EMULATION ... #endif around the block of PTX load /
-                # store helpers in pf_common.cuh; never defined in the product build)
-                assert src.count("PF_HOST_EMULATION") == (5 if f == "pf_common.cuh" else 0), f   # three #ifdef blocks: loads / stores, LL words, fences
+                # (the only hooks for tests are the #ifdef PF_HOST_EMULATION ... #endif blocks around PTX helpers in
+                # pf_common.cuh; never defined in the product build)
+                # four #ifdef blocks: loads / stores, LL words, fences, the out-of-line copy of the IEEE division
+                # (a __noinline__ device function there, a plain inline one on the host)
+                assert src.count("PF_HOST_EMULATION") == (6 if f == "pf_common.cuh" else 0), f
 
 
 # ------------------------------------------------------------------ config
