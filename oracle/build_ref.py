@@ -35,7 +35,8 @@ def install_importer() -> None:
     hook = mach.FileFinder.path_hook((mach.SourcelessFileLoader, [SUFFIX]))
 
     def ref_only(path):
-        if os.path.abspath(path).startswith(OUT):
+        ap = os.path.abspath(path)
+        if ap == OUT or ap.startswith(OUT + os.sep):
             return hook(path)
         raise ImportError
     sys.path_hooks.insert(0, ref_only)
